@@ -1,0 +1,2309 @@
+// b200sv.cu — C ABI + non-fused kernels of the B200-native state-vector core (sm_100a).
+//
+// What this file replaces in the reference (unitaryfoundation/qrack): the QEngineCUDA host driver
+// (src/qengine/cuda.cu) and the non-ALU kernels of src/common/qengine.cu.  Semantics follow QEngineCPU
+// (src/qengine/state.cpp), which is the parity oracle; each ABI function cites the lines it mirrors in
+// include/b200sv.h.  Nothing here is a translation of the reference kernels: index generation, vector widths,
+// launch shapes and reductions are designed for B200 (128-bit accesses, 256-thread CTAs sized in multiples of
+// the SM count, on-device final reductions with double atomics, no per-gate host synchronisation).
+#include "sv_common.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+
+namespace b200sv {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return (e == cudaErrorMemoryAllocation) ? B200SV_ENOMEM : B200SV_ECUDA;
+}
+static int einval(const char* msg)
+{
+    g_err = msg;
+    return B200SV_EINVAL;
+}
+
+int sm_count(int dev)
+{
+    static std::mutex mtx;
+    static std::map<int, int> cache;
+    std::lock_guard<std::mutex> lk(mtx);
+    auto it = cache.find(dev);
+    if (it != cache.end()) {
+        return it->second;
+    }
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n;
+    return n;
+}
+
+// grid for a streaming kernel: enough CTAs for `items` one-per-thread, capped at 16 CTAs/SM (grid-stride beyond)
+static inline unsigned stream_grid(int dev, uint64_t items, int block)
+{
+    const uint64_t need = (items + block - 1) / block;
+    const uint64_t cap = (uint64_t)sm_count(dev) * 16U;
+    return (unsigned)std::max<uint64_t>(1, std::min(need, cap));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// reductions helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return v;
+}
+// block-wide sum -> one double atomic per CTA
+__device__ __forceinline__ void block_atomic_add(double v, double* out)
+{
+    __shared__ double sh[32];
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+        sh[w] = v;
+    }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        v = (lane < nw) ? sh[lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0) {
+            atomicAdd(out, v);
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 (unfused form): generic Apply2x2 for arbitrary (offset1, offset2, sorted powers)
+//   V = amplitudes per vector access (fp32: 2 -> 128-bit when the lowest involved qubit is >= 1)
+//   ILP = independent pairs in flight per thread
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, int V> struct VecT;
+template <> struct VecT<float, 1> {
+    typedef float2 type;
+};
+template <> struct VecT<float, 2> {
+    typedef float4 type;
+};
+template <> struct VecT<double, 1> {
+    typedef double2 type;
+};
+
+template <typename R, int V, bool NORM, int ILP>
+__global__ void __launch_bounds__(256) k_apply2x2(typename Cx<R>::type* __restrict__ psi, uint64_t items, uint64_t off1,
+    uint64_t off2, Mat2<R> mt, PowList pw, R thresh, double* normOut)
+{
+    typedef typename Cx<R>::type C;
+    typedef typename VecT<R, V>::type Vec;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < items; j0 += stride * ILP) {
+        Vec a[ILP], b[ILP];
+        uint64_t ia[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const uint64_t j = j0 + (uint64_t)u * stride;
+            if (j < items) {
+                const uint64_t i = push_apart(j * V, pw);
+                ia[u] = i;
+                a[u] = *reinterpret_cast<const Vec*>(psi + i + off1);
+                b[u] = *reinterpret_cast<const Vec*>(psi + i + off2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const uint64_t j = j0 + (uint64_t)u * stride;
+            if (j < items) {
+                C* pa = reinterpret_cast<C*>(&a[u]);
+                C* pb = reinterpret_cast<C*>(&b[u]);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    C na = cmad2(mt.m[0], pa[v], mt.m[1], pb[v]);
+                    C nb = cmad2(mt.m[2], pa[v], mt.m[3], pb[v]);
+                    if (NORM) {
+                        R n0 = cnorm(na), n1 = cnorm(nb);
+                        if (n0 < thresh) {
+                            na = mk<R>(0, 0);
+                        } else {
+                            acc += (double)n0;
+                        }
+                        if (n1 < thresh) {
+                            nb = mk<R>(0, 0);
+                        } else {
+                            acc += (double)n1;
+                        }
+                    }
+                    pa[v] = na;
+                    pb[v] = nb;
+                }
+                *reinterpret_cast<Vec*>(psi + ia[u] + off1) = a[u];
+                *reinterpret_cast<Vec*>(psi + ia[u] + off2) = b[u];
+            }
+        }
+    }
+    if (NORM) {
+        block_atomic_add(acc, normOut);
+    }
+}
+
+template <typename R> static Mat2<R> make_mat(const double* m8, double nrm)
+{
+    Mat2<R> mt;
+    for (int k = 0; k < 4; ++k) {
+        mt.m[k] = mk<R>((R)(m8[2 * k] * nrm), (R)(m8[2 * k + 1] * nrm));
+    }
+    return mt;
+}
+
+template <typename R>
+static int launch_apply2x2(State* s, uint64_t off1, uint64_t off2, const double* m8, int nb, const uint64_t* pows,
+    double nrm, double thresh, double* normOutDev)
+{
+    typedef typename Cx<R>::type C;
+    PowList pw;
+    pw.n = nb;
+    for (int k = 0; k < nb; ++k) {
+        pw.low[k] = pows[k] - 1U;
+    }
+    // For fp32 R the matrix is rounded to fp32 BEFORE the nrm fold when nrm==1 (bit-identical inputs to the oracle).
+    Mat2<R> mt = make_mat<R>(m8, nrm);
+    const uint64_t nItems = s->dim() >> nb;
+    const bool norm = normOutDev != nullptr;
+    C* psi = (C*)s->amps;
+    const bool vec2 = (sizeof(R) == 4) && (nb == 0 || pows[0] >= 2U) && (nItems >= 2U);
+    if (vec2) {
+        const uint64_t items = nItems / 2U;
+        const unsigned grid = stream_grid(s->dev, (items + 3) / 4, 256);
+        if (norm) {
+            k_apply2x2<float, 2, true, 4><<<grid, 256, 0, s->stream>>>(
+                (float2*)psi, items, off1, off2, *(Mat2<float>*)&mt, pw, (float)thresh, normOutDev);
+        } else {
+            k_apply2x2<float, 2, false, 4><<<grid, 256, 0, s->stream>>>(
+                (float2*)psi, items, off1, off2, *(Mat2<float>*)&mt, pw, (float)thresh, normOutDev);
+        }
+    } else {
+        const unsigned grid = stream_grid(s->dev, (nItems + 3) / 4, 256);
+        if (norm) {
+            k_apply2x2<R, 1, true, 4><<<grid, 256, 0, s->stream>>>(psi, nItems, off1, off2, mt, pw, (R)thresh, normOutDev);
+        } else {
+            k_apply2x2<R, 1, false, 4><<<grid, 256, 0, s->stream>>>(psi, nItems, off1, off2, mt, pw, (R)thresh, normOutDev);
+        }
+    }
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    s->stats.single_launches++;
+    s->stats.bytes_swept += 2ULL * (nItems * 2ULL) * s->amp_bytes();
+    return B200SV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// elementwise sweeps
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) k_apply_m(typename Cx<R>::type* psi, uint64_t n, uint64_t mask, uint64_t result,
+    typename Cx<R>::type nrm)
+{
+    typedef typename Cx<R>::type C;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if ((i & mask) == result) {
+            psi[i] = cmul<C>(nrm, psi[i]);
+        } else {
+            psi[i] = mk<R>(0, 0);
+        }
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_collapse_parity(typename Cx<R>::type* psi, uint64_t n, uint64_t mask, int result,
+    double* out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if ((__popcll(i & mask) & 1) == result) {
+            acc += (double)cnorm(psi[i]);
+        } else {
+            psi[i] = mk<R>(0, 0);
+        }
+    }
+    block_atomic_add(acc, out);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_xmask(typename Cx<R>::type* psi, uint64_t half, uint64_t topLow, uint64_t mask)
+{
+    typedef typename Cx<R>::type C;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
+        const uint64_t lo = j & topLow;
+        const uint64_t i = ((j ^ lo) << 1) | lo; // top mask bit clear
+        const C a = psi[i];
+        const C b = psi[i ^ mask];
+        psi[i] = b;
+        psi[i ^ mask] = a;
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_phase_parity(typename Cx<R>::type* psi, uint64_t n, uint64_t mask, uint64_t cmask,
+    typename Cx<R>::type odd, typename Cx<R>::type even)
+{
+    typedef typename Cx<R>::type C;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if ((i & cmask) != cmask) {
+            continue;
+        }
+        const bool p = __popcll(i & mask) & 1;
+        psi[i] = cmul<C>(p ? odd : even, psi[i]);
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_phase_root_n(typename Cx<R>::type* psi, uint64_t n, uint64_t mask, uint64_t nPhases,
+    R radians)
+{
+    typedef typename Cx<R>::type C;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t steps = (uint64_t)__popcll(i & mask) % nPhases;
+        if (steps) {
+            R sn, cs;
+            sincos(radians * (R)steps, &sn, &cs);
+            psi[i] = cmul<C>(mk<R>(cs, sn), psi[i]);
+        }
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_normalize(typename Cx<R>::type* psi, uint64_t n, typename Cx<R>::type f, R thresh)
+{
+    typedef typename Cx<R>::type C;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        C a = psi[i];
+        if (cnorm(a) < thresh) {
+            a = mk<R>(0, 0);
+        }
+        psi[i] = cmul<C>(f, a);
+    }
+}
+
+// UniformlyControlledSingleBit (reference state.cpp:1094-1198)
+struct UcArgs {
+    int nc;
+    uint64_t cpow[32];
+    int nskip;
+    uint64_t skip[32];
+    uint64_t skipValue;
+};
+template <typename R>
+__global__ void __launch_bounds__(256) k_uniformly_controlled(typename Cx<R>::type* psi, uint64_t half, uint64_t tpow,
+    const typename Cx<R>::type* __restrict__ mtrxs, UcArgs ua, R nrm)
+{
+    typedef typename Cx<R>::type C;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
+        const uint64_t lo = j & (tpow - 1U);
+        const uint64_t i = ((j ^ lo) << 1) | lo;
+        uint64_t off = 0;
+        for (int c = 0; c < ua.nc; ++c) {
+            if (i & ua.cpow[c]) {
+                off |= 1ULL << c;
+            }
+        }
+        uint64_t idx = 0, hi = off;
+        for (int p = 0; p < ua.nskip; ++p) {
+            const uint64_t l = hi & (ua.skip[p] - 1U);
+            idx |= l;
+            hi = (hi ^ l) << 1;
+        }
+        idx |= hi;
+        const C* m = mtrxs + (idx | ua.skipValue) * 4U;
+        const C a = psi[i], b = psi[i | tpow];
+        C na = cmad2(m[0], a, m[1], b);
+        C nb = cmad2(m[2], a, m[3], b);
+        na.x *= nrm;
+        na.y *= nrm;
+        nb.x *= nrm;
+        nb.y *= nrm;
+        psi[i] = na;
+        psi[i | tpow] = nb;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) k_prob_mask(const typename Cx<R>::type* __restrict__ psi, uint64_t n, uint64_t mask,
+    uint64_t perm, double* out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0;
+    R part = 0;
+    int cnt = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if ((i & mask) == perm) {
+            part += cnorm(psi[i]);
+        }
+        if (++cnt == 64) {
+            acc += (double)part;
+            part = 0;
+            cnt = 0;
+        }
+    }
+    acc += (double)part;
+    block_atomic_add(acc, out);
+}
+
+// subset form: only the matching amplitudes are read (mask bits all >= 2^lowBit): j enumerates the free bits
+template <typename R>
+__global__ void __launch_bounds__(256) k_prob_mask_subset(const typename Cx<R>::type* __restrict__ psi, uint64_t items,
+    PowList pw, uint64_t perm, double* out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0;
+    R part = 0;
+    int cnt = 0;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < items; j += stride) {
+        part += cnorm(psi[push_apart(j, pw) | perm]);
+        if (++cnt == 64) {
+            acc += (double)part;
+            part = 0;
+            cnt = 0;
+        }
+    }
+    acc += (double)part;
+    block_atomic_add(acc, out);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_prob_parity(const typename Cx<R>::type* __restrict__ psi, uint64_t n, uint64_t mask,
+    double* out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (__popcll(i & mask) & 1) {
+            acc += (double)cnorm(psi[i]);
+        }
+    }
+    block_atomic_add(acc, out);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_norm(const typename Cx<R>::type* __restrict__ psi, uint64_t n, R thresh, double* out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0;
+    R part = 0;
+    int cnt = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const R v = cnorm(psi[i]);
+        if (v >= thresh) {
+            part += v;
+        }
+        if (++cnt == 64) {
+            acc += (double)part;
+            part = 0;
+            cnt = 0;
+        }
+    }
+    acc += (double)part;
+    block_atomic_add(acc, out);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_inner(const typename Cx<R>::type* __restrict__ a, const typename Cx<R>::type* __restrict__ b,
+    uint64_t n, double* out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double re = 0, im = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const auto x = a[i];
+        const auto y = b[i];
+        // conj(x) * y
+        re += (double)x.x * y.x + (double)x.y * y.y;
+        im += (double)x.x * y.y - (double)x.y * y.x;
+    }
+    block_atomic_add(re, out);
+    block_atomic_add(im, out + 1);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_expectation(const typename Cx<R>::type* __restrict__ psi, uint64_t n, int start,
+    uint64_t lenMask, double* out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        acc += (double)cnorm(psi[i]) * (double)((i >> start) & lenMask);
+    }
+    block_atomic_add(acc, out);
+}
+
+template <typename R, typename RO>
+__global__ void __launch_bounds__(256) k_probs(const typename Cx<R>::type* __restrict__ psi, uint64_t n, RO* out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        out[i] = (RO)cnorm(psi[i]);
+    }
+}
+
+__device__ __forceinline__ uint64_t pext64(uint64_t x, uint64_t mask)
+{
+    uint64_t r = 0;
+    int k = 0;
+    while (mask) {
+        const uint64_t b = mask & (~mask + 1);
+        if (x & b) {
+            r |= 1ULL << k;
+        }
+        ++k;
+        mask ^= b;
+    }
+    return r;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_prob_mask_all(const typename Cx<R>::type* __restrict__ psi, uint64_t n, uint64_t mask,
+    double* bins, int useShared, int nbins)
+{
+    extern __shared__ double shbins[];
+    if (useShared) {
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+            shbins[b] = 0;
+        }
+        __syncthreads();
+    }
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = (double)cnorm(psi[i]);
+        if (v != 0.0) {
+            const uint64_t b = pext64(i, mask);
+            if (useShared) {
+                atomicAdd(&shbins[b], v);
+            } else {
+                atomicAdd(&bins[b], v);
+            }
+        }
+    }
+    if (useShared) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+            if (shbins[b] != 0.0) {
+                atomicAdd(&bins[b], shbins[b]);
+            }
+        }
+    }
+}
+
+// per-chunk sums of |psi|^2 (only terms > eps) for sampling; one CTA per chunk
+template <typename R>
+__global__ void __launch_bounds__(256) k_chunk_sums(const typename Cx<R>::type* __restrict__ psi, uint64_t chunk, R eps,
+    double* sums)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * chunk;
+    double acc = 0;
+    for (uint64_t i = threadIdx.x; i < chunk; i += blockDim.x) {
+        const R v = cnorm(psi[base + i]);
+        if (v > eps) {
+            acc += (double)v;
+        }
+    }
+    sums[blockIdx.x] = 0;
+    __syncthreads();
+    block_atomic_add(acc, sums + blockIdx.x);
+}
+
+// argmax |psi|^2 : packed (value bits, index) via 2-step: per-block best to arrays
+template <typename R>
+__global__ void __launch_bounds__(256) k_argmax(const typename Cx<R>::type* __restrict__ psi, uint64_t n, double* bestVal,
+    unsigned long long* bestIdx)
+{
+    __shared__ double sv[256];
+    __shared__ unsigned long long si[256];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double bv = -1;
+    unsigned long long bi = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = (double)cnorm(psi[i]);
+        if (v > bv) {
+            bv = v;
+            bi = i;
+        }
+    }
+    sv[threadIdx.x] = bv;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double ov = sv[threadIdx.x + o];
+            const unsigned long long oi = si[threadIdx.x + o];
+            if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) {
+                sv[threadIdx.x] = ov;
+                si[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        bestVal[blockIdx.x] = sv[0];
+        bestIdx[blockIdx.x] = si[0];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// structure kernels: Compose / Decompose / Dispose
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) k_compose(typename Cx<R>::type* __restrict__ out, const typename Cx<R>::type* __restrict__ a,
+    const typename Cx<R>::type* __restrict__ b, uint64_t n, uint64_t startMask, uint64_t midMask, uint64_t endMask, int start,
+    int nb)
+{
+    typedef typename Cx<R>::type C;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += stride) {
+        const C x = a[(l & startMask) | ((l & endMask) >> nb)];
+        const C y = b[(l & midMask) >> start];
+        out[l] = cmul<C>(x, y);
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_dispose_perm(typename Cx<R>::type* __restrict__ out,
+    const typename Cx<R>::type* __restrict__ in, uint64_t n, uint64_t skipMask, int length, uint64_t disposedRes)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += stride) {
+        const uint64_t lo = h & skipMask;
+        out[h] = in[lo | ((h ^ lo) << length) | disposedRes];
+    }
+}
+
+// One pass over psi accumulating the four marginals of DecomposeDispose (reference state.cpp:1605-1675):
+//   remProb[r] = sum_k |psi|^2, remAngle[r] = sum_k arg(psi)|psi|^2 (only |psi|^2 > floor)
+//   partProb[k] = sum_r |psi|^2, partAngle[k] = sum_r arg(psi)|psi|^2 (only |psi|^2 > floor)
+// Accumulation is in double with atomics (shared-memory bins for the part side when it is small).
+template <typename R>
+__global__ void __launch_bounds__(256) k_decompose_marginals(const typename Cx<R>::type* __restrict__ psi, uint64_t n, int start,
+    int length, R floorv, double* remProb, double* remAngle, double* partProb, double* partAngle, int partShared)
+{
+    extern __shared__ double sh[];
+    const uint64_t partPower = 1ULL << length;
+    if (partShared) {
+        for (uint64_t b = threadIdx.x; b < 2 * partPower; b += blockDim.x) {
+            sh[b] = 0;
+        }
+        __syncthreads();
+    }
+    const uint64_t startMask = (1ULL << start) - 1U;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const auto amp = psi[i];
+        const R nrm = cnorm(amp);
+        const uint64_t k = (i >> start) & (partPower - 1U);
+        const uint64_t r = (i & startMask) | ((i >> (start + length)) << start);
+        const double dn = (double)nrm;
+        double ang = 0;
+        if (nrm > floorv) {
+            ang = (double)atan2(amp.y, amp.x) * dn;
+        }
+        if (dn != 0.0) {
+            atomicAdd(&remProb[r], dn);
+            if (ang != 0.0) {
+                atomicAdd(&remAngle[r], ang);
+            }
+            if (partProb) {
+                if (partShared) {
+                    atomicAdd(&sh[k], dn);
+                    atomicAdd(&sh[partPower + k], ang);
+                } else {
+                    atomicAdd(&partProb[k], dn);
+                    atomicAdd(&partAngle[k], ang);
+                }
+            }
+        }
+    }
+    if (partShared && partProb) {
+        __syncthreads();
+        for (uint64_t b = threadIdx.x; b < partPower; b += blockDim.x) {
+            if (sh[b] != 0.0) {
+                atomicAdd(&partProb[b], sh[b]);
+            }
+            if (sh[partPower + b] != 0.0) {
+                atomicAdd(&partAngle[b], sh[partPower + b]);
+            }
+        }
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_polar_rebuild(typename Cx<R>::type* out, uint64_t n, const double* prob, const double* angle,
+    R floorv)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const R p = (R)prob[i];
+        R ang = (R)angle[i];
+        if (p > floorv) {
+            ang = (R)(angle[i] / prob[i]);
+        }
+        const R mag = (R)sqrt((double)p);
+        R sn, cs;
+        sincos(ang, &sn, &cs);
+        out[i] = mk<R>(mag * cs, mag * sn);
+    }
+}
+
+template <typename C> __global__ void __launch_bounds__(256) k_swap_ranges(C* a, C* b, uint64_t n)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const C x = a[i];
+        a[i] = b[i];
+        b[i] = x;
+    }
+}
+
+__global__ void k_fill_bytes(uint4* p, uint64_t n, unsigned v)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        p[i] = make_uint4(v, v, v, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------------------------------------
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) {
+            cudaSetDevice(dev);
+        }
+    }
+    ~DevGuard()
+    {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) {
+            cudaSetDevice(prev);
+        }
+    }
+};
+
+static int ensure_scratch(State* s, size_t doubles)
+{
+    if (s->scratch_doubles >= doubles) {
+        return B200SV_OK;
+    }
+    if (s->d_scratch) {
+        cudaFree(s->d_scratch);
+        cudaFreeHost(s->h_scratch);
+        s->d_scratch = nullptr;
+        s->h_scratch = nullptr;
+        s->scratch_doubles = 0;
+    }
+    const size_t want = std::max<size_t>(doubles, 4096);
+    SV_CUDA(cudaMalloc(&s->d_scratch, want * sizeof(double)));
+    SV_CUDA(cudaMallocHost(&s->h_scratch, want * sizeof(double)));
+    s->scratch_doubles = want;
+    return B200SV_OK;
+}
+
+static int alloc_amps(State* s, bool clear)
+{
+    if (s->amps) {
+        return B200SV_OK;
+    }
+    if (s->external) {
+        return einval("external buffer was released; cannot re-allocate");
+    }
+    const size_t bytes = (size_t)s->dim() * s->amp_bytes();
+    cudaError_t e = cudaMalloc(&s->amps, bytes);
+    if (e != cudaSuccess) {
+        s->amps = nullptr;
+        return cuda_fail(e, "cudaMalloc(state)");
+    }
+    if (clear) {
+        SV_CUDA(cudaMemsetAsync(s->amps, 0, bytes, s->stream));
+    }
+    return B200SV_OK;
+}
+
+static void free_amps(State* s)
+{
+    if (s->amps && !s->external) {
+        cudaStreamSynchronize(s->stream);
+        cudaFree(s->amps);
+    }
+    s->amps = nullptr;
+}
+
+// make stream `waiter` wait for everything queued so far on `other`
+static int cross_wait(State* waiter, State* other)
+{
+    if (waiter->stream == other->stream) {
+        return B200SV_OK;
+    }
+    DevGuard g(other->dev);
+    SV_CUDA(cudaEventRecord(other->evx, other->stream));
+    SV_CUDA(cudaStreamWaitEvent(waiter->stream, other->evx, 0));
+    return B200SV_OK;
+}
+
+static int read_scratch(State* s, int count)
+{
+    SV_CUDA(cudaMemcpyAsync(s->h_scratch, s->d_scratch, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    SV_CUDA(cudaStreamSynchronize(s->stream));
+    return B200SV_OK;
+}
+
+static int flush_queue(State* s)
+{
+    if (s->queue.empty()) {
+        return B200SV_OK;
+    }
+    return fused_flush(s);
+}
+
+} // namespace b200sv
+
+using namespace b200sv;
+
+#define SV_ENTER(s)                                                                                                    \
+    if (!(s)) {                                                                                                        \
+        set_error("null state handle");                                                                                \
+        return B200SV_EINVAL;                                                                                          \
+    }                                                                                                                  \
+    DevGuard guard__((s)->dev)
+
+#define DISPATCH_PREC(s, expr32, expr64)                                                                               \
+    if ((s)->prec == 32) {                                                                                             \
+        typedef float R;                                                                                               \
+        typedef float2 C;                                                                                              \
+        (void)sizeof(R);                                                                                               \
+        (void)sizeof(C);                                                                                               \
+        expr32;                                                                                                        \
+    } else {                                                                                                           \
+        typedef double R;                                                                                              \
+        typedef double2 C;                                                                                             \
+        (void)sizeof(R);                                                                                               \
+        (void)sizeof(C);                                                                                               \
+        expr64;                                                                                                        \
+    }
+
+extern "C" {
+
+int b200sv_abi_version(void) { return 1; }
+const char* b200sv_last_error(void) { return g_err.c_str(); }
+
+int b200sv_device_count(int* count)
+{
+    if (!count) {
+        return einval("null out pointer");
+    }
+    SV_CUDA(cudaGetDeviceCount(count));
+    return B200SV_OK;
+}
+
+int b200sv_device_info(int dev, uint64_t* total_bytes, uint64_t* free_bytes, int* sms)
+{
+    DevGuard g(dev);
+    size_t f = 0, t = 0;
+    SV_CUDA(cudaMemGetInfo(&f, &t));
+    if (total_bytes) {
+        *total_bytes = t;
+    }
+    if (free_bytes) {
+        *free_bytes = f;
+    }
+    if (sms) {
+        *sms = sm_count(dev);
+    }
+    return B200SV_OK;
+}
+
+int b200sv_can_access_peer(int dev, int peer, int* can)
+{
+    if (!can) {
+        return einval("null out pointer");
+    }
+    if (dev == peer) {
+        *can = 1;
+        return B200SV_OK;
+    }
+    SV_CUDA(cudaDeviceCanAccessPeer(can, dev, peer));
+    return B200SV_OK;
+}
+
+static int create_common(int device, int n_qubits, int precision, void* ext, b200sv_t* out)
+{
+    if (!out) {
+        return einval("null out pointer");
+    }
+    if (n_qubits < 0 || n_qubits > 40) {
+        return einval("qubit count out of range");
+    }
+    if (precision != 32 && precision != 64) {
+        return einval("precision must be 32 or 64");
+    }
+    int ndev = 0;
+    SV_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0) {
+        device = 0;
+    }
+    if (device >= ndev) {
+        return einval("device index out of range");
+    }
+    DevGuard g(device);
+    b200sv_state* s = new b200sv_state();
+    s->dev = device;
+    s->nq = n_qubits;
+    s->prec = precision;
+    s->amps = ext;
+    s->external = ext != nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        e = cudaEventCreate(&s->ev0);
+    }
+    if (e == cudaSuccess) {
+        e = cudaEventCreate(&s->ev1);
+    }
+    if (e == cudaSuccess) {
+        e = cudaEventCreateWithFlags(&s->evx, cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        delete s;
+        return cuda_fail(e, "stream/event creation");
+    }
+    int r = ensure_scratch(s, 4096);
+    if (r != B200SV_OK) {
+        delete s;
+        return r;
+    }
+    *out = s;
+    return B200SV_OK;
+}
+
+int b200sv_create(int device, int n_qubits, int precision, b200sv_t* out)
+{
+    return create_common(device, n_qubits, precision, nullptr, out);
+}
+
+int b200sv_create_external(int device, int n_qubits, int precision, void* device_ptr, b200sv_t* out)
+{
+    if (!device_ptr) {
+        return einval("null device pointer");
+    }
+    return create_common(device, n_qubits, precision, device_ptr, out);
+}
+
+int b200sv_destroy(b200sv_t s)
+{
+    if (!s) {
+        return B200SV_OK;
+    }
+    DevGuard g(s->dev);
+    cudaStreamSynchronize(s->stream);
+    free_amps(s);
+    if (s->d_scratch) {
+        cudaFree(s->d_scratch);
+    }
+    if (s->h_scratch) {
+        cudaFreeHost(s->h_scratch);
+    }
+    if (s->d_flush) {
+        cudaFree(s->d_flush);
+    }
+    cudaEventDestroy(s->ev0);
+    cudaEventDestroy(s->ev1);
+    cudaEventDestroy(s->evx);
+    cudaStreamDestroy(s->stream);
+    delete s;
+    return B200SV_OK;
+}
+
+int b200sv_qubit_count(b200sv_t s, int* n)
+{
+    if (!s || !n) {
+        return einval("null argument");
+    }
+    *n = s->nq;
+    return B200SV_OK;
+}
+int b200sv_precision(b200sv_t s, int* p)
+{
+    if (!s || !p) {
+        return einval("null argument");
+    }
+    *p = s->prec;
+    return B200SV_OK;
+}
+int b200sv_device(b200sv_t s, int* d)
+{
+    if (!s || !d) {
+        return einval("null argument");
+    }
+    *d = s->dev;
+    return B200SV_OK;
+}
+
+int b200sv_flush(b200sv_t s)
+{
+    SV_ENTER(s);
+    return flush_queue(s);
+}
+
+int b200sv_finish(b200sv_t s)
+{
+    SV_ENTER(s);
+    SV_TRY(flush_queue(s));
+    SV_CUDA(cudaStreamSynchronize(s->stream));
+    return B200SV_OK;
+}
+
+int b200sv_set_fusion(b200sv_t s, int mode)
+{
+    SV_ENTER(s);
+    SV_TRY(flush_queue(s));
+    s->fusion = mode;
+    return B200SV_OK;
+}
+
+int b200sv_device_ptr(b200sv_t s, void** ptr)
+{
+    SV_ENTER(s);
+    if (!ptr) {
+        return einval("null out pointer");
+    }
+    SV_TRY(flush_queue(s));
+    *ptr = s->amps;
+    return B200SV_OK;
+}
+
+int b200sv_clone(b200sv_t s, b200sv_t* out)
+{
+    SV_ENTER(s);
+    SV_TRY(flush_queue(s));
+    b200sv_t c = nullptr;
+    SV_TRY(b200sv_create(s->dev, s->nq, s->prec, &c));
+    c->fusion = s->fusion;
+    if (s->amps) {
+        int r = alloc_amps(c, false);
+        if (r != B200SV_OK) {
+            b200sv_destroy(c);
+            return r;
+        }
+        cross_wait(c, s);
+        cudaError_t e = cudaMemcpyAsync(c->amps, s->amps, (size_t)s->dim() * s->amp_bytes(), cudaMemcpyDeviceToDevice, c->stream);
+        if (e != cudaSuccess) {
+            b200sv_destroy(c);
+            return cuda_fail(e, "clone copy");
+        }
+        cross_wait(s, c);
+    }
+    *out = c;
+    return B200SV_OK;
+}
+
+int b200sv_set_device(b200sv_t s, int device)
+{
+    SV_ENTER(s);
+    if (device < 0 || device == s->dev) {
+        return B200SV_OK;
+    }
+    int ndev = 0;
+    SV_CUDA(cudaGetDeviceCount(&ndev));
+    if (device >= ndev) {
+        return einval("device index out of range");
+    }
+    if (s->external) {
+        return einval("cannot migrate an external buffer");
+    }
+    SV_TRY(flush_queue(s));
+    SV_CUDA(cudaStreamSynchronize(s->stream));
+    // build the new-device resources, then move the buffer with a peer copy
+    b200sv_t n = nullptr;
+    SV_TRY(b200sv_create(device, s->nq, s->prec, &n));
+    if (s->amps) {
+        int r;
+        {
+            DevGuard g2(device);
+            r = alloc_amps(n, false);
+            if (r == B200SV_OK) {
+                cudaError_t e = cudaMemcpyPeerAsync(n->amps, device, s->amps, s->dev, (size_t)s->dim() * s->amp_bytes(), n->stream);
+                if (e == cudaSuccess) {
+                    e = cudaStreamSynchronize(n->stream);
+                }
+                if (e != cudaSuccess) {
+                    r = cuda_fail(e, "peer copy");
+                }
+            }
+        }
+        if (r != B200SV_OK) {
+            b200sv_destroy(n);
+            return r;
+        }
+    }
+    // swap guts
+    free_amps(s);
+    std::swap(s->amps, n->amps);
+    std::swap(s->stream, n->stream);
+    std::swap(s->d_scratch, n->d_scratch);
+    std::swap(s->h_scratch, n->h_scratch);
+    std::swap(s->scratch_doubles, n->scratch_doubles);
+    std::swap(s->d_flush, n->d_flush);
+    std::swap(s->flush_bytes, n->flush_bytes);
+    std::swap(s->ev0, n->ev0);
+    std::swap(s->ev1, n->ev1);
+    std::swap(s->evx, n->evx);
+    std::swap(s->dev, n->dev);
+    b200sv_destroy(n);
+    return B200SV_OK;
+}
+
+// ---- state I/O ----------------------------------------------------------------------------------------------------
+
+int b200sv_set_permutation(b200sv_t s, uint64_t perm, double re, double im)
+{
+    SV_ENTER(s);
+    if (perm >= s->dim()) {
+        return einval("SetPermutation: permutation out of bounds");
+    }
+    s->queue.clear(); // Dump(): pending gates are irrelevant (reference state.cpp:230)
+    SV_TRY(alloc_amps(s, false));
+    SV_CUDA(cudaMemsetAsync(s->amps, 0, (size_t)s->dim() * s->amp_bytes(), s->stream));
+    if (s->prec == 32) {
+        const float2 v = make_float2((float)re, (float)im);
+        SV_CUDA(cudaMemcpyAsync((float2*)s->amps + perm, &v, sizeof(v), cudaMemcpyHostToDevice, s->stream));
+        SV_CUDA(cudaStreamSynchronize(s->stream));
+    } else {
+        const double2 v = make_double2(re, im);
+        SV_CUDA(cudaMemcpyAsync((double2*)s->amps + perm, &v, sizeof(v), cudaMemcpyHostToDevice, s->stream));
+        SV_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return B200SV_OK;
+}
+
+int b200sv_zero(b200sv_t s)
+{
+    SV_ENTER(s);
+    s->queue.clear();
+    if (s->external) {
+        if (s->amps) {
+            SV_CUDA(cudaMemsetAsync(s->amps, 0, (size_t)s->dim() * s->amp_bytes(), s->stream));
+        }
+        return B200SV_OK;
+    }
+    free_amps(s);
+    return B200SV_OK;
+}
+
+int b200sv_is_zero(b200sv_t s, int* z)
+{
+    if (!s || !z) {
+        return einval("null argument");
+    }
+    *z = (s->amps == nullptr);
+    return B200SV_OK;
+}
+
+int b200sv_set_state(b200sv_t s, const void* host)
+{
+    SV_ENTER(s);
+    if (!host) {
+        return einval("null host pointer");
+    }
+    s->queue.clear();
+    SV_TRY(alloc_amps(s, false));
+    SV_CUDA(cudaMemcpyAsync(s->amps, host, (size_t)s->dim() * s->amp_bytes(), cudaMemcpyHostToDevice, s->stream));
+    SV_CUDA(cudaStreamSynchronize(s->stream));
+    return B200SV_OK;
+}
+
+int b200sv_get_state(b200sv_t s, void* host)
+{
+    SV_ENTER(s);
+    if (!host) {
+        return einval("null host pointer");
+    }
+    SV_TRY(flush_queue(s));
+    const size_t bytes = (size_t)s->dim() * s->amp_bytes();
+    if (!s->amps) {
+        memset(host, 0, bytes);
+        return B200SV_OK;
+    }
+    SV_CUDA(cudaMemcpyAsync(host, s->amps, bytes, cudaMemcpyDeviceToHost, s->stream));
+    SV_CUDA(cudaStreamSynchronize(s->stream));
+    return B200SV_OK;
+}
+
+int b200sv_get_probs(b200sv_t s, void* host)
+{
+    SV_ENTER(s);
+    if (!host) {
+        return einval("null host pointer");
+    }
+    SV_TRY(flush_queue(s));
+    const uint64_t n = s->dim();
+    const size_t rbytes = (s->prec == 32) ? 4 : 8;
+    if (!s->amps) {
+        memset(host, 0, n * rbytes);
+        return B200SV_OK;
+    }
+    void* tmp = nullptr;
+    SV_CUDA(cudaMalloc(&tmp, n * rbytes));
+    const unsigned grid = stream_grid(s->dev, n, 256);
+    if (s->prec == 32) {
+        k_probs<float, float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, n, (float*)tmp);
+    } else {
+        k_probs<double, double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, n, (double*)tmp);
+    }
+    s->stats.kernel_launches++;
+    cudaError_t e = cudaMemcpyAsync(host, tmp, n * rbytes, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) {
+        e = cudaStreamSynchronize(s->stream);
+    }
+    cudaFree(tmp);
+    if (e != cudaSuccess) {
+        return cuda_fail(e, "get_probs");
+    }
+    return B200SV_OK;
+}
+
+static bool bad_range(uint64_t off, uint64_t len, uint64_t dim) { return off > dim || len > dim - off; }
+
+int b200sv_get_page(b200sv_t s, void* host, uint64_t offset, uint64_t length)
+{
+    SV_ENTER(s);
+    if (bad_range(offset, length, s->dim())) {
+        return einval("GetAmplitudePage range is out-of-bounds");
+    }
+    SV_TRY(flush_queue(s));
+    const size_t ab = s->amp_bytes();
+    if (!s->amps) {
+        memset(host, 0, length * ab);
+        return B200SV_OK;
+    }
+    SV_CUDA(cudaMemcpyAsync(host, (char*)s->amps + offset * ab, length * ab, cudaMemcpyDeviceToHost, s->stream));
+    SV_CUDA(cudaStreamSynchronize(s->stream));
+    return B200SV_OK;
+}
+
+int b200sv_set_page(b200sv_t s, const void* host, uint64_t offset, uint64_t length)
+{
+    SV_ENTER(s);
+    if (bad_range(offset, length, s->dim())) {
+        return einval("SetAmplitudePage range is out-of-bounds");
+    }
+    SV_TRY(flush_queue(s));
+    if (!s->amps) {
+        SV_TRY(alloc_amps(s, true));
+    }
+    const size_t ab = s->amp_bytes();
+    SV_CUDA(cudaMemcpyAsync((char*)s->amps + offset * ab, host, length * ab, cudaMemcpyHostToDevice, s->stream));
+    SV_CUDA(cudaStreamSynchronize(s->stream));
+    return B200SV_OK;
+}
+
+static int enable_peer(int dev, int peer)
+{
+    if (dev == peer) {
+        return B200SV_OK;
+    }
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, dev, peer);
+    if (!can) {
+        return B200SV_ESTATE;
+    }
+    DevGuard g(dev);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        e = cudaSuccess;
+    }
+    return e == cudaSuccess ? B200SV_OK : B200SV_ESTATE;
+}
+
+int b200sv_copy_page(b200sv_t dst, b200sv_t src, uint64_t src_off, uint64_t dst_off, uint64_t length)
+{
+    SV_ENTER(dst);
+    if (!src) {
+        return einval("null source handle");
+    }
+    if (dst->prec != src->prec) {
+        return einval("precision mismatch");
+    }
+    if (bad_range(dst_off, length, dst->dim()) || bad_range(src_off, length, src->dim())) {
+        return einval("SetAmplitudePage source/destination range is out-of-bounds");
+    }
+    {
+        DevGuard g2(src->dev);
+        SV_TRY(flush_queue(src));
+    }
+    SV_TRY(flush_queue(dst));
+    if (!dst->amps && !src->amps) {
+        return B200SV_OK;
+    }
+    if (!src->amps && length == dst->dim()) {
+        return b200sv_zero(dst);
+    }
+    if (!dst->amps) {
+        SV_TRY(alloc_amps(dst, true));
+    }
+    const size_t ab = dst->amp_bytes();
+    if (!src->amps) {
+        SV_CUDA(cudaMemsetAsync((char*)dst->amps + dst_off * ab, 0, length * ab, dst->stream));
+        return B200SV_OK;
+    }
+    SV_TRY(cross_wait(dst, src));
+    if (dst->dev == src->dev) {
+        SV_CUDA(cudaMemcpyAsync((char*)dst->amps + dst_off * ab, (char*)src->amps + src_off * ab, length * ab,
+            cudaMemcpyDeviceToDevice, dst->stream));
+    } else {
+        enable_peer(dst->dev, src->dev);
+        SV_CUDA(cudaMemcpyPeerAsync((char*)dst->amps + dst_off * ab, dst->dev, (char*)src->amps + src_off * ab, src->dev,
+            length * ab, dst->stream));
+    }
+    SV_TRY(cross_wait(src, dst));
+    return B200SV_OK;
+}
+
+int b200sv_shuffle(b200sv_t a, b200sv_t b)
+{
+    SV_ENTER(a);
+    if (!b) {
+        return einval("null handle");
+    }
+    if (a->nq != b->nq || a->prec != b->prec) {
+        return einval("ShuffleBuffers argument size differs from this");
+    }
+    {
+        DevGuard g2(b->dev);
+        SV_TRY(flush_queue(b));
+    }
+    SV_TRY(flush_queue(a));
+    if (!a->amps && !b->amps) {
+        return B200SV_OK;
+    }
+    if (!a->amps) {
+        SV_TRY(alloc_amps(a, true));
+    }
+    if (!b->amps) {
+        DevGuard g2(b->dev);
+        SV_TRY(alloc_amps(b, true));
+    }
+    const uint64_t half = a->dim() >> 1;
+    const size_t ab = a->amp_bytes();
+    SV_TRY(cross_wait(a, b));
+    char* pa = (char*)a->amps + half * ab; // upper half of a
+    char* pb = (char*)b->amps;             // lower half of b
+    const bool direct = (a->dev == b->dev) || (enable_peer(a->dev, b->dev) == B200SV_OK);
+    if (direct) {
+        // one kernel on a's SMs reads and writes b's half through NVLink peer mapping
+        const uint64_t n16 = half * ab / 16;
+        const unsigned grid = stream_grid(a->dev, n16, 256);
+        k_swap_ranges<uint4><<<grid, 256, 0, a->stream>>>((uint4*)pa, (uint4*)pb, n16);
+        SV_CUDA(cudaGetLastError());
+        a->stats.kernel_launches++;
+    } else {
+        void* tmp = nullptr;
+        SV_CUDA(cudaMalloc(&tmp, half * ab));
+        cudaMemcpyAsync(tmp, pa, half * ab, cudaMemcpyDeviceToDevice, a->stream);
+        cudaMemcpyPeerAsync(pa, a->dev, pb, b->dev, half * ab, a->stream);
+        cudaMemcpyPeerAsync(pb, b->dev, tmp, a->dev, half * ab, a->stream);
+        cudaStreamSynchronize(a->stream);
+        cudaFree(tmp);
+        SV_CUDA(cudaGetLastError());
+    }
+    SV_TRY(cross_wait(b, a));
+    return B200SV_OK;
+}
+
+int b200sv_copy_state(b200sv_t dst, b200sv_t src)
+{
+    if (!dst || !src) {
+        return einval("null handle");
+    }
+    if (dst->nq != src->nq) {
+        return einval("CopyStateVec argument size differs from this");
+    }
+    if (!src->amps && src->queue.empty()) {
+        return b200sv_zero(dst);
+    }
+    dst->queue.clear();
+    return b200sv_copy_page(dst, src, 0, 0, src->dim());
+}
+
+int b200sv_get_amplitude(b200sv_t s, uint64_t perm, double* re, double* im)
+{
+    SV_ENTER(s);
+    if (perm >= s->dim()) {
+        return einval("GetAmplitude argument out-of-bounds");
+    }
+    SV_TRY(flush_queue(s));
+    if (!s->amps) {
+        *re = 0;
+        *im = 0;
+        return B200SV_OK;
+    }
+    if (s->prec == 32) {
+        float2 v;
+        SV_CUDA(cudaMemcpyAsync(&v, (float2*)s->amps + perm, sizeof(v), cudaMemcpyDeviceToHost, s->stream));
+        SV_CUDA(cudaStreamSynchronize(s->stream));
+        *re = v.x;
+        *im = v.y;
+    } else {
+        double2 v;
+        SV_CUDA(cudaMemcpyAsync(&v, (double2*)s->amps + perm, sizeof(v), cudaMemcpyDeviceToHost, s->stream));
+        SV_CUDA(cudaStreamSynchronize(s->stream));
+        *re = v.x;
+        *im = v.y;
+    }
+    return B200SV_OK;
+}
+
+int b200sv_set_amplitude(b200sv_t s, uint64_t perm, double re, double im)
+{
+    SV_ENTER(s);
+    if (perm >= s->dim()) {
+        return einval("SetAmplitude argument out-of-bounds");
+    }
+    SV_TRY(flush_queue(s));
+    if (!s->amps) {
+        if (re == 0.0 && im == 0.0) {
+            return B200SV_OK;
+        }
+        SV_TRY(alloc_amps(s, true));
+    }
+    if (s->prec == 32) {
+        const float2 v = make_float2((float)re, (float)im);
+        SV_CUDA(cudaMemcpyAsync((float2*)s->amps + perm, &v, sizeof(v), cudaMemcpyHostToDevice, s->stream));
+    } else {
+        const double2 v = make_double2(re, im);
+        SV_CUDA(cudaMemcpyAsync((double2*)s->amps + perm, &v, sizeof(v), cudaMemcpyHostToDevice, s->stream));
+    }
+    SV_CUDA(cudaStreamSynchronize(s->stream));
+    return B200SV_OK;
+}
+
+// ---- gates -----------------------------------------------------------------------------------------------------------
+
+int b200sv_apply2x2(b200sv_t s, uint64_t off1, uint64_t off2, const double* m8, int bit_count, const uint64_t* pows,
+    double nrm, double norm_thresh, double* norm_out)
+{
+    SV_ENTER(s);
+    if (!m8 || (bit_count > 0 && !pows)) {
+        return einval("Apply2x2: null argument");
+    }
+    const uint64_t dim = s->dim();
+    if (off1 >= dim || off2 >= dim) {
+        return einval("Apply2x2 offset1 and offset2 parameters must be within allocated qubit bounds!");
+    }
+    if (bit_count < 0 || bit_count > s->nq) {
+        return einval("Apply2x2: bad bit count");
+    }
+    uint64_t pmask = 0;
+    for (int k = 0; k < bit_count; ++k) {
+        if (pows[k] >= dim || !pows[k] || (pows[k] & (pows[k] - 1U))) {
+            return einval("Apply2x2 parameter qPowsSorted array values must be within allocated qubit bounds!");
+        }
+        if (k && pows[k - 1] >= pows[k]) {
+            return einval("Apply2x2 parameter qPowSorted array values must be sorted and cannot be duplicated!");
+        }
+        pmask |= pows[k];
+    }
+    if ((off1 & ~pmask) || (off2 & ~pmask)) {
+        return einval("Apply2x2: offsets must be combinations of the given powers");
+    }
+    if (!s->amps) { // CHECK_ZERO_SKIP
+        if (norm_out) {
+            *norm_out = 0;
+        }
+        return B200SV_OK;
+    }
+    s->stats.gates_submitted++;
+    // queue single-target gates for the fused sweep
+    const uint64_t diff = off1 ^ off2;
+    if (!norm_out && s->fusion && diff && !(diff & (diff - 1U))) {
+        GateOp g;
+        g.target = __builtin_ctzll(diff);
+        g.cmask = pmask & ~diff;
+        g.cval = off1 & ~diff;
+        const bool swapped = (off1 & diff) != 0; // off1 holds the |1> branch: reorder the matrix
+        const int ord[4] = { 3, 2, 1, 0 };
+        for (int k = 0; k < 4; ++k) {
+            const int src = swapped ? ord[k] : k;
+            g.m[2 * k] = m8[2 * src] * nrm;
+            g.m[2 * k + 1] = m8[2 * src + 1] * nrm;
+        }
+        if (s->prec == 32) {
+            for (int k = 0; k < 8; ++k) {
+                g.m[k] = (double)(float)g.m[k];
+            }
+        }
+        const bool z1 = g.m[2] == 0 && g.m[3] == 0, z2 = g.m[4] == 0 && g.m[5] == 0;
+        const bool z0 = g.m[0] == 0 && g.m[1] == 0, z3 = g.m[6] == 0 && g.m[7] == 0;
+        g.kind = (z1 && z2) ? 1 : ((z0 && z3) ? 2 : 0);
+        if (fused_accepts(s, g)) {
+            s->queue.push_back(g);
+            if (s->queue.size() >= 4096) {
+                SV_TRY(flush_queue(s));
+            }
+            return B200SV_OK;
+        }
+    }
+    SV_TRY(flush_queue(s));
+    double* dn = nullptr;
+    if (norm_out) {
+        dn = s->d_scratch;
+        SV_CUDA(cudaMemsetAsync(dn, 0, sizeof(double), s->stream));
+    }
+    if (s->prec == 32) {
+        SV_TRY(launch_apply2x2<float>(s, off1, off2, m8, bit_count, pows, nrm, norm_thresh, dn));
+    } else {
+        SV_TRY(launch_apply2x2<double>(s, off1, off2, m8, bit_count, pows, nrm, norm_thresh, dn));
+    }
+    if (norm_out) {
+        SV_TRY(read_scratch(s, 1));
+        *norm_out = s->h_scratch[0];
+    }
+    return B200SV_OK;
+}
+
+int b200sv_xmask(b200sv_t s, uint64_t mask)
+{
+    SV_ENTER(s);
+    if (mask >= s->dim()) {
+        return einval("XMask mask out-of-bounds!");
+    }
+    if (!s->amps || !mask) {
+        return B200SV_OK;
+    }
+    SV_TRY(flush_queue(s));
+    const uint64_t half = s->dim() >> 1;
+    const uint64_t top = 1ULL << (63 - __builtin_clzll(mask));
+    const unsigned grid = stream_grid(s->dev, half, 256);
+    DISPATCH_PREC(s, (k_xmask<float><<<grid, 256, 0, s->stream>>>((float2*)s->amps, half, top - 1U, mask)),
+        (k_xmask<double><<<grid, 256, 0, s->stream>>>((double2*)s->amps, half, top - 1U, mask)));
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200SV_OK;
+}
+
+int b200sv_phase_parity(b200sv_t s, double radians, uint64_t mask)
+{
+    SV_ENTER(s);
+    if (mask >= s->dim()) {
+        return einval("PhaseParity mask out-of-bounds!");
+    }
+    if (!s->amps || !mask) {
+        return B200SV_OK;
+    }
+    SV_TRY(flush_queue(s));
+    const uint64_t n = s->dim();
+    const unsigned grid = stream_grid(s->dev, n, 256);
+    if (s->prec == 32) {
+        const float ang = (float)(radians / 2);
+        const float cs = (float)cos(ang), sn = (float)sin(ang);
+        k_phase_parity<float><<<grid, 256, 0, s->stream>>>((float2*)s->amps, n, mask, 0, make_float2(cs, sn), make_float2(cs, -sn));
+    } else {
+        const double ang = radians / 2;
+        const double cs = cos(ang), sn = sin(ang);
+        k_phase_parity<double><<<grid, 256, 0, s->stream>>>((double2*)s->amps, n, mask, 0, make_double2(cs, sn), make_double2(cs, -sn));
+    }
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200SV_OK;
+}
+
+int b200sv_uniform_parity_rz(b200sv_t s, uint64_t control_mask, uint64_t mask, double angle)
+{
+    SV_ENTER(s);
+    if (mask >= s->dim() || control_mask >= s->dim()) {
+        return einval("UniformParityRZ mask out-of-bounds!");
+    }
+    if (!s->amps) {
+        return B200SV_OK;
+    }
+    SV_TRY(flush_queue(s));
+    const uint64_t n = s->dim();
+    const unsigned grid = stream_grid(s->dev, n, 256);
+    if (s->prec == 32) {
+        const float cs = (float)cos(angle), sn = (float)sin(angle);
+        k_phase_parity<float><<<grid, 256, 0, s->stream>>>((float2*)s->amps, n, mask, control_mask, make_float2(cs, sn), make_float2(cs, -sn));
+    } else {
+        const double cs = cos(angle), sn = sin(angle);
+        k_phase_parity<double><<<grid, 256, 0, s->stream>>>((double2*)s->amps, n, mask, control_mask, make_double2(cs, sn), make_double2(cs, -sn));
+    }
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200SV_OK;
+}
+
+int b200sv_phase_root_n_mask(b200sv_t s, int n, uint64_t mask)
+{
+    SV_ENTER(s);
+    if (mask >= s->dim()) {
+        return einval("PhaseRootNMask mask out-of-bounds!");
+    }
+    if (!s->amps || !n || !mask) {
+        return B200SV_OK;
+    }
+    SV_TRY(flush_queue(s));
+    const uint64_t dim = s->dim();
+    const unsigned grid = stream_grid(s->dev, dim, 256);
+    const uint64_t nPhases = 1ULL << n;
+    if (s->prec == 32) {
+        const float radians = (float)(-(double)(float)M_PI / (double)(1ULL << (n - 1)));
+        k_phase_root_n<float><<<grid, 256, 0, s->stream>>>((float2*)s->amps, dim, mask, nPhases, radians);
+    } else {
+        const double radians = -M_PI / (double)(1ULL << (n - 1));
+        k_phase_root_n<double><<<grid, 256, 0, s->stream>>>((double2*)s->amps, dim, mask, nPhases, radians);
+    }
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200SV_OK;
+}
+
+int b200sv_uniformly_controlled(b200sv_t s, int n_controls, const int* controls, int target, const double* mtrxs, int n_skip,
+    const uint64_t* skip_powers, uint64_t skip_value_mask, double nrm)
+{
+    SV_ENTER(s);
+    if (target < 0 || target >= s->nq || n_controls < 0 || n_controls > 30 || n_skip < 0 || n_skip > 30) {
+        return einval("UniformlyControlledSingleBit argument out-of-bounds!");
+    }
+    for (int c = 0; c < n_controls; ++c) {
+        if (controls[c] < 0 || controls[c] >= s->nq) {
+            return einval("UniformlyControlledSingleBit control is out-of-bounds!");
+        }
+    }
+    if (!s->amps) {
+        return B200SV_OK;
+    }
+    SV_TRY(flush_queue(s));
+    UcArgs ua;
+    ua.nc = n_controls;
+    for (int c = 0; c < n_controls; ++c) {
+        ua.cpow[c] = 1ULL << controls[c];
+    }
+    ua.nskip = n_skip;
+    for (int c = 0; c < n_skip; ++c) {
+        ua.skip[c] = skip_powers[c];
+    }
+    ua.skipValue = skip_value_mask;
+    const size_t nm = ((size_t)1 << (n_controls + n_skip)) * 4U;
+    const uint64_t half = s->dim() >> 1;
+    const unsigned grid = stream_grid(s->dev, half, 256);
+    void* dm = nullptr;
+    if (s->prec == 32) {
+        std::vector<float2> hm(nm);
+        for (size_t k = 0; k < nm; ++k) {
+            hm[k] = make_float2((float)mtrxs[2 * k], (float)mtrxs[2 * k + 1]);
+        }
+        SV_CUDA(cudaMalloc(&dm, nm * sizeof(float2)));
+        cudaMemcpyAsync(dm, hm.data(), nm * sizeof(float2), cudaMemcpyHostToDevice, s->stream);
+        cudaStreamSynchronize(s->stream);
+        k_uniformly_controlled<float><<<grid, 256, 0, s->stream>>>((float2*)s->amps, half, 1ULL << target, (const float2*)dm, ua, (float)nrm);
+    } else {
+        SV_CUDA(cudaMalloc(&dm, nm * sizeof(double2)));
+        cudaMemcpyAsync(dm, mtrxs, nm * sizeof(double2), cudaMemcpyHostToDevice, s->stream);
+        cudaStreamSynchronize(s->stream);
+        k_uniformly_controlled<double><<<grid, 256, 0, s->stream>>>((double2*)s->amps, half, 1ULL << target, (const double2*)dm, ua, nrm);
+    }
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(dm);
+    if (e != cudaSuccess) {
+        return cuda_fail(e, "uniformly_controlled");
+    }
+    s->stats.kernel_launches++;
+    return B200SV_OK;
+}
+
+int b200sv_apply_m(b200sv_t s, uint64_t mask, uint64_t result, double nre, double nim)
+{
+    SV_ENTER(s);
+    if (!s->amps) {
+        return B200SV_OK;
+    }
+    SV_TRY(flush_queue(s));
+    const uint64_t n = s->dim();
+    const unsigned grid = stream_grid(s->dev, n, 256);
+    DISPATCH_PREC(s, (k_apply_m<float><<<grid, 256, 0, s->stream>>>((float2*)s->amps, n, mask, result, make_float2((float)nre, (float)nim))),
+        (k_apply_m<double><<<grid, 256, 0, s->stream>>>((double2*)s->amps, n, mask, result, make_double2(nre, nim))));
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200SV_OK;
+}
+
+int b200sv_collapse_parity(b200sv_t s, uint64_t mask, int result, double* kept)
+{
+    SV_ENTER(s);
+    if (mask >= s->dim()) {
+        return einval("ForceMParity mask out-of-bounds!");
+    }
+    if (!s->amps) {
+        if (kept) {
+            *kept = 0;
+        }
+        return B200SV_OK;
+    }
+    SV_TRY(flush_queue(s));
+    const uint64_t n = s->dim();
+    const unsigned grid = stream_grid(s->dev, n, 256);
+    SV_CUDA(cudaMemsetAsync(s->d_scratch, 0, sizeof(double), s->stream));
+    DISPATCH_PREC(s, (k_collapse_parity<float><<<grid, 256, 0, s->stream>>>((float2*)s->amps, n, mask, result ? 1 : 0, s->d_scratch)),
+        (k_collapse_parity<double><<<grid, 256, 0, s->stream>>>((double2*)s->amps, n, mask, result ? 1 : 0, s->d_scratch)));
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    SV_TRY(read_scratch(s, 1));
+    if (kept) {
+        *kept = s->h_scratch[0];
+    }
+    return B200SV_OK;
+}
+
+// ---- reductions --------------------------------------------------------------------------------------------------
+
+int b200sv_prob_mask(b200sv_t s, uint64_t mask, uint64_t perm, double* out)
+{
+    SV_ENTER(s);
+    if (!out) {
+        return einval("null out pointer");
+    }
+    if (mask >= s->dim() || (perm & ~mask)) {
+        return einval("ProbMask mask out-of-bounds!");
+    }
+    SV_TRY(flush_queue(s));
+    if (!s->amps) {
+        *out = 0;
+        return B200SV_OK;
+    }
+    const uint64_t n = s->dim();
+    SV_CUDA(cudaMemsetAsync(s->d_scratch, 0, sizeof(double), s->stream));
+    // subset iteration when every mask bit is >= 2^4 (reads stay >= 128 B contiguous); else predicate scan
+    if (mask && !(mask & 15U)) {
+        PowList pw;
+        pw.n = 0;
+        for (uint64_t m = mask; m; m &= m - 1U) {
+            pw.low[pw.n++] = (m & (~m + 1U)) - 1U;
+        }
+        const uint64_t items = n >> pw.n;
+        const unsigned grid = stream_grid(s->dev, items, 256);
+        DISPATCH_PREC(s, (k_prob_mask_subset<float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, items, pw, perm, s->d_scratch)),
+            (k_prob_mask_subset<double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, items, pw, perm, s->d_scratch)));
+    } else {
+        const unsigned grid = stream_grid(s->dev, n, 256);
+        DISPATCH_PREC(s, (k_prob_mask<float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, n, mask, perm, s->d_scratch)),
+            (k_prob_mask<double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, n, mask, perm, s->d_scratch)));
+    }
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    SV_TRY(read_scratch(s, 1));
+    *out = s->h_scratch[0];
+    return B200SV_OK;
+}
+
+int b200sv_prob_parity(b200sv_t s, uint64_t mask, double* out)
+{
+    SV_ENTER(s);
+    if (!out) {
+        return einval("null out pointer");
+    }
+    if (mask >= s->dim()) {
+        return einval("ProbParity mask out-of-bounds!");
+    }
+    SV_TRY(flush_queue(s));
+    if (!s->amps || !mask) {
+        *out = 0;
+        return B200SV_OK;
+    }
+    const uint64_t n = s->dim();
+    const unsigned grid = stream_grid(s->dev, n, 256);
+    SV_CUDA(cudaMemsetAsync(s->d_scratch, 0, sizeof(double), s->stream));
+    DISPATCH_PREC(s, (k_prob_parity<float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, n, mask, s->d_scratch)),
+        (k_prob_parity<double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, n, mask, s->d_scratch)));
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    SV_TRY(read_scratch(s, 1));
+    *out = s->h_scratch[0];
+    return B200SV_OK;
+}
+
+int b200sv_prob_mask_all(b200sv_t s, uint64_t mask, void* host_probs)
+{
+    SV_ENTER(s);
+    if (!host_probs) {
+        return einval("null out pointer");
+    }
+    if (mask >= s->dim()) {
+        return einval("ProbMaskAll mask out-of-bounds!");
+    }
+    const int k = __builtin_popcountll(mask);
+    if (k > 28) {
+        return einval("ProbMaskAll: too many mask bits");
+    }
+    SV_TRY(flush_queue(s));
+    const size_t nb = (size_t)1 << k;
+    const size_t rbytes = s->prec == 32 ? 4 : 8;
+    if (!s->amps) {
+        memset(host_probs, 0, nb * rbytes);
+        return B200SV_OK;
+    }
+    double* bins = nullptr;
+    SV_CUDA(cudaMalloc(&bins, nb * sizeof(double)));
+    cudaMemsetAsync(bins, 0, nb * sizeof(double), s->stream);
+    const uint64_t n = s->dim();
+    const int useShared = nb <= 4096;
+    const unsigned grid = std::min<unsigned>(stream_grid(s->dev, n, 256), (unsigned)sm_count(s->dev) * 4U);
+    const size_t shm = useShared ? nb * sizeof(double) : 0;
+    DISPATCH_PREC(s, (k_prob_mask_all<float><<<grid, 256, shm, s->stream>>>((const float2*)s->amps, n, mask, bins, useShared, (int)nb)),
+        (k_prob_mask_all<double><<<grid, 256, shm, s->stream>>>((const double2*)s->amps, n, mask, bins, useShared, (int)nb)));
+    s->stats.kernel_launches++;
+    std::vector<double> hb(nb);
+    cudaError_t e = cudaMemcpyAsync(hb.data(), bins, nb * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) {
+        e = cudaStreamSynchronize(s->stream);
+    }
+    cudaFree(bins);
+    if (e != cudaSuccess) {
+        return cuda_fail(e, "prob_mask_all");
+    }
+    if (s->prec == 32) {
+        for (size_t i = 0; i < nb; ++i) {
+            ((float*)host_probs)[i] = (float)hb[i];
+        }
+    } else {
+        memcpy(host_probs, hb.data(), nb * sizeof(double));
+    }
+    return B200SV_OK;
+}
+
+int b200sv_norm(b200sv_t s, double thresh, double* out)
+{
+    SV_ENTER(s);
+    if (!out) {
+        return einval("null out pointer");
+    }
+    SV_TRY(flush_queue(s));
+    if (!s->amps) {
+        *out = 0;
+        return B200SV_OK;
+    }
+    const uint64_t n = s->dim();
+    const unsigned grid = stream_grid(s->dev, n, 256);
+    SV_CUDA(cudaMemsetAsync(s->d_scratch, 0, sizeof(double), s->stream));
+    DISPATCH_PREC(s, (k_norm<float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, n, (float)thresh, s->d_scratch)),
+        (k_norm<double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, n, thresh, s->d_scratch)));
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    SV_TRY(read_scratch(s, 1));
+    *out = s->h_scratch[0];
+    return B200SV_OK;
+}
+
+int b200sv_normalize(b200sv_t s, double nrm, double thresh, double phase_arg)
+{
+    SV_ENTER(s);
+    if (!s->amps) {
+        return B200SV_OK;
+    }
+    if (nrm <= 0) {
+        return einval("normalize: non-positive norm");
+    }
+    SV_TRY(flush_queue(s));
+    const uint64_t n = s->dim();
+    const unsigned grid = stream_grid(s->dev, n, 256);
+    if (s->prec == 32) {
+        const float f = 1.0f / sqrtf((float)nrm);
+        const float2 c = make_float2(f * cosf((float)phase_arg), f * sinf((float)phase_arg));
+        k_normalize<float><<<grid, 256, 0, s->stream>>>((float2*)s->amps, n, c, (float)std::max(thresh, 0.0));
+    } else {
+        const double f = 1.0 / sqrt(nrm);
+        const double2 c = make_double2(f * cos(phase_arg), f * sin(phase_arg));
+        k_normalize<double><<<grid, 256, 0, s->stream>>>((double2*)s->amps, n, c, std::max(thresh, 0.0));
+    }
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200SV_OK;
+}
+
+int b200sv_inner(b200sv_t a, b200sv_t b, double* re, double* im)
+{
+    SV_ENTER(a);
+    if (!b || !re || !im) {
+        return einval("null argument");
+    }
+    if (a->nq != b->nq || a->prec != b->prec) {
+        return einval("inner: size mismatch");
+    }
+    {
+        DevGuard g2(b->dev);
+        SV_TRY(flush_queue(b));
+    }
+    SV_TRY(flush_queue(a));
+    if (!a->amps || !b->amps) {
+        *re = 0;
+        *im = 0;
+        return B200SV_OK;
+    }
+    if (a->dev != b->dev && enable_peer(a->dev, b->dev) != B200SV_OK) {
+        return einval("inner: states on devices without peer access");
+    }
+    SV_TRY(cross_wait(a, b));
+    const uint64_t n = a->dim();
+    const unsigned grid = stream_grid(a->dev, n, 256);
+    SV_CUDA(cudaMemsetAsync(a->d_scratch, 0, 2 * sizeof(double), a->stream));
+    DISPATCH_PREC(a, (k_inner<float><<<grid, 256, 0, a->stream>>>((const float2*)a->amps, (const float2*)b->amps, n, a->d_scratch)),
+        (k_inner<double><<<grid, 256, 0, a->stream>>>((const double2*)a->amps, (const double2*)b->amps, n, a->d_scratch)));
+    SV_CUDA(cudaGetLastError());
+    a->stats.kernel_launches++;
+    SV_TRY(read_scratch(a, 2));
+    *re = a->h_scratch[0];
+    *im = a->h_scratch[1];
+    return B200SV_OK;
+}
+
+int b200sv_expectation(b200sv_t s, int start, int length, double* out)
+{
+    SV_ENTER(s);
+    if (!out || start < 0 || length < 0 || start + length > s->nq) {
+        return einval("GetExpectation range is out-of-bounds!");
+    }
+    SV_TRY(flush_queue(s));
+    if (!s->amps) {
+        *out = 0;
+        return B200SV_OK;
+    }
+    const uint64_t n = s->dim();
+    const unsigned grid = stream_grid(s->dev, n, 256);
+    SV_CUDA(cudaMemsetAsync(s->d_scratch, 0, sizeof(double), s->stream));
+    const uint64_t lm = (1ULL << length) - 1U;
+    DISPATCH_PREC(s, (k_expectation<float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, n, start, lm, s->d_scratch)),
+        (k_expectation<double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, n, start, lm, s->d_scratch)));
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    SV_TRY(read_scratch(s, 1));
+    *out = s->h_scratch[0];
+    return B200SV_OK;
+}
+
+int b200sv_highest_prob(b200sv_t s, uint64_t* perm)
+{
+    SV_ENTER(s);
+    if (!perm) {
+        return einval("null out pointer");
+    }
+    SV_TRY(flush_queue(s));
+    *perm = 0;
+    if (!s->amps) {
+        return B200SV_OK;
+    }
+    const uint64_t n = s->dim();
+    const unsigned grid = std::min<unsigned>(stream_grid(s->dev, n, 256), 1024U);
+    SV_TRY(ensure_scratch(s, 2 * 1024));
+    double* bv = s->d_scratch;
+    unsigned long long* bi = (unsigned long long*)(s->d_scratch + 1024);
+    DISPATCH_PREC(s, (k_argmax<float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, n, bv, bi)),
+        (k_argmax<double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, n, bv, bi)));
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    SV_TRY(read_scratch(s, 2048));
+    double best = -1;
+    uint64_t bidx = 0;
+    for (unsigned b = 0; b < grid; ++b) {
+        const double v = s->h_scratch[b];
+        const uint64_t i = ((unsigned long long*)(s->h_scratch + 1024))[b];
+        if (v > best || (v == best && i < bidx)) {
+            best = v;
+            bidx = i;
+        }
+    }
+    *perm = bidx;
+    return B200SV_OK;
+}
+
+int b200sv_sample(b200sv_t s, double rnd, uint64_t* perm)
+{
+    SV_ENTER(s);
+    if (!perm) {
+        return einval("null out pointer");
+    }
+    SV_TRY(flush_queue(s));
+    const uint64_t n = s->dim();
+    *perm = n - 1U;
+    if (!s->amps) {
+        return B200SV_OK;
+    }
+    // two-level search: per-chunk sums on the device, prefix on the host, then one chunk scanned on the host
+    const uint64_t chunk = std::min<uint64_t>(n, 1ULL << 14);
+    const uint64_t nchunks = n / chunk;
+    SV_TRY(ensure_scratch(s, nchunks));
+    const double eps = (s->prec == 32) ? 1.7763568394002505e-15 : 6.310887241768095e-30; // REAL1_EPSILON (qrack_types.hpp:206,209)
+    DISPATCH_PREC(s, (k_chunk_sums<float><<<(unsigned)nchunks, 256, 0, s->stream>>>((const float2*)s->amps, chunk, (float)eps, s->d_scratch)),
+        (k_chunk_sums<double><<<(unsigned)nchunks, 256, 0, s->stream>>>((const double2*)s->amps, chunk, eps, s->d_scratch)));
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    SV_TRY(read_scratch(s, (int)nchunks));
+    const double fpEps = (s->prec == 32) ? 2.98023223876953125e-08 : 5.551115123125783e-17; // FP_NORM_EPSILON
+    double tot = 0;
+    uint64_t lastNonzeroChunk = nchunks;
+    uint64_t pick = nchunks;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const double cs = s->h_scratch[c];
+        if (cs > 0) {
+            lastNonzeroChunk = c;
+            if ((tot + cs > rnd) || ((1.0 - (tot + cs)) <= fpEps)) {
+                pick = c;
+                break;
+            }
+            tot += cs;
+        }
+    }
+    if (pick == nchunks) {
+        pick = lastNonzeroChunk;
+        if (pick == nchunks) {
+            return B200SV_OK; // all-zero state: last index (reference MAll falls through to lastNonzero = max)
+        }
+        tot -= 0; // scan that chunk for its last nonzero entry below
+    }
+    const size_t ab = s->amp_bytes();
+    std::vector<char> host(chunk * ab);
+    SV_CUDA(cudaMemcpyAsync(host.data(), (char*)s->amps + pick * chunk * ab, chunk * ab, cudaMemcpyDeviceToHost, s->stream));
+    SV_CUDA(cudaStreamSynchronize(s->stream));
+    uint64_t lastNz = n - 1U;
+    bool found = false;
+    for (uint64_t i = 0; i < chunk; ++i) {
+        double p;
+        if (s->prec == 32) {
+            const float2 v = ((float2*)host.data())[i];
+            p = (double)(v.x * v.x + v.y * v.y);
+        } else {
+            const double2 v = ((double2*)host.data())[i];
+            p = v.x * v.x + v.y * v.y;
+        }
+        if (p > eps) {
+            tot += p;
+            lastNz = pick * chunk + i;
+            if ((tot > rnd) || ((1.0 - tot) <= fpEps)) {
+                *perm = lastNz;
+                found = true;
+                break;
+            }
+        }
+    }
+    if (!found) {
+        *perm = lastNz;
+    }
+    return B200SV_OK;
+}
+
+// ---- structure ---------------------------------------------------------------------------------------------------------
+
+int b200sv_compose(b200sv_t a, b200sv_t b, int start)
+{
+    SV_ENTER(a);
+    if (!b) {
+        return einval("null handle");
+    }
+    if (a->prec != b->prec) {
+        return einval("Compose: precision mismatch");
+    }
+    if (start < 0 || start > a->nq) {
+        return einval("Compose start index is out-of-bounds!");
+    }
+    if (a->external) {
+        return einval("Compose on an external buffer");
+    }
+    {
+        DevGuard g2(b->dev);
+        SV_TRY(flush_queue(b));
+    }
+    SV_TRY(flush_queue(a));
+    if (!b->nq) {
+        return B200SV_OK;
+    }
+    const int nq = a->nq + b->nq;
+    if (nq > 40) {
+        return einval("Compose: too many qubits");
+    }
+    if (!a->amps || !b->amps) {
+        free_amps(a);
+        a->nq = nq;
+        return B200SV_OK;
+    }
+    if (a->dev != b->dev && enable_peer(a->dev, b->dev) != B200SV_OK) {
+        return einval("Compose: states on devices without peer access");
+    }
+    const uint64_t n = 1ULL << nq;
+    void* out = nullptr;
+    cudaError_t e = cudaMalloc(&out, n * a->amp_bytes());
+    if (e != cudaSuccess) {
+        return cuda_fail(e, "cudaMalloc(compose)");
+    }
+    SV_TRY(cross_wait(a, b));
+    const uint64_t startMask = (1ULL << start) - 1U;
+    const uint64_t midMask = ((1ULL << b->nq) - 1U) << start;
+    const uint64_t endMask = (n - 1U) & ~(startMask | midMask);
+    const unsigned grid = stream_grid(a->dev, n, 256);
+    DISPATCH_PREC(a, (k_compose<float><<<grid, 256, 0, a->stream>>>((float2*)out, (const float2*)a->amps, (const float2*)b->amps, n, startMask, midMask, endMask, start, b->nq)),
+        (k_compose<double><<<grid, 256, 0, a->stream>>>((double2*)out, (const double2*)a->amps, (const double2*)b->amps, n, startMask, midMask, endMask, start, b->nq)));
+    e = cudaGetLastError();
+    a->stats.kernel_launches++;
+    if (e != cudaSuccess) {
+        cudaFree(out);
+        return cuda_fail(e, "compose kernel");
+    }
+    SV_TRY(cross_wait(b, a));
+    free_amps(a); // synchronises a's stream first
+    a->amps = out;
+    a->nq = nq;
+    return B200SV_OK;
+}
+
+int b200sv_dispose_perm(b200sv_t s, int start, int length, uint64_t perm)
+{
+    SV_ENTER(s);
+    if (start < 0 || length < 0 || start + length > s->nq) {
+        return einval("Dispose range is out-of-bounds!");
+    }
+    if (!length) {
+        return B200SV_OK;
+    }
+    if (s->external) {
+        return einval("Dispose on an external buffer");
+    }
+    SV_TRY(flush_queue(s));
+    const int nl = s->nq - length;
+    if (!s->amps) {
+        s->nq = nl;
+        return B200SV_OK;
+    }
+    const uint64_t rem = 1ULL << nl;
+    void* out = nullptr;
+    cudaError_t e = cudaMalloc(&out, rem * s->amp_bytes());
+    if (e != cudaSuccess) {
+        return cuda_fail(e, "cudaMalloc(dispose)");
+    }
+    const unsigned grid = stream_grid(s->dev, rem, 256);
+    const uint64_t skipMask = (1ULL << start) - 1U;
+    DISPATCH_PREC(s, (k_dispose_perm<float><<<grid, 256, 0, s->stream>>>((float2*)out, (const float2*)s->amps, rem, skipMask, length, perm << start)),
+        (k_dispose_perm<double><<<grid, 256, 0, s->stream>>>((double2*)out, (const double2*)s->amps, rem, skipMask, length, perm << start)));
+    e = cudaGetLastError();
+    s->stats.kernel_launches++;
+    if (e != cudaSuccess) {
+        cudaFree(out);
+        return cuda_fail(e, "dispose kernel");
+    }
+    free_amps(s);
+    s->amps = out;
+    s->nq = nl; // (the reference sets qubitCount 1 when nl==0, state.cpp:1741-1745; the adapter handles that)
+    return B200SV_OK;
+}
+
+int b200sv_decompose(b200sv_t s, int start, int length, b200sv_t dest)
+{
+    SV_ENTER(s);
+    if (start < 0 || length < 0 || start + length > s->nq) {
+        return einval("DecomposeDispose range is out-of-bounds!");
+    }
+    if (!length) {
+        return B200SV_OK;
+    }
+    if (s->external || (dest && dest->external)) {
+        return einval("Decompose on an external buffer");
+    }
+    if (dest && (dest->prec != s->prec || dest->nq != length)) {
+        return einval("Decompose: destination size/precision mismatch");
+    }
+    SV_TRY(flush_queue(s));
+    if (dest) {
+        DevGuard g2(dest->dev);
+        dest->queue.clear();
+    }
+    const int nl = s->nq - length;
+    if (!s->amps) {
+        s->nq = nl;
+        if (dest) {
+            SV_TRY(b200sv_zero(dest));
+        }
+        return B200SV_OK;
+    }
+    if (!nl) {
+        // hand the buffer over (reference state.cpp:1572-1579)
+        if (dest) {
+            if (dest->dev != s->dev) {
+                SV_TRY(b200sv_copy_page(dest, s, 0, 0, s->dim()));
+                free_amps(s);
+            } else {
+                SV_CUDA(cudaStreamSynchronize(s->stream));
+                free_amps(dest);
+                dest->amps = s->amps;
+                s->amps = nullptr;
+            }
+        } else {
+            free_amps(s);
+        }
+        s->nq = 0;
+        return B200SV_OK;
+    }
+    const uint64_t n = s->dim();
+    const uint64_t partPower = 1ULL << length, remPower = 1ULL << nl;
+    const double floorv = (s->prec == 32) ? 1.7763568394002505e-15 : 6.310887241768095e-30; // amplitudeFloor = REAL1_EPSILON (qrack_types.hpp:206,209)
+    double* acc = nullptr;
+    const size_t accN = 2 * remPower + 2 * partPower;
+    cudaError_t e = cudaMalloc(&acc, accN * sizeof(double));
+    if (e != cudaSuccess) {
+        return cuda_fail(e, "cudaMalloc(decompose marginals)");
+    }
+    cudaMemsetAsync(acc, 0, accN * sizeof(double), s->stream);
+    double* remProb = acc;
+    double* remAngle = acc + remPower;
+    double* partProb = dest ? acc + 2 * remPower : nullptr;
+    double* partAngle = dest ? acc + 2 * remPower + partPower : nullptr;
+    const int partShared = dest && partPower <= 2048;
+    const size_t shm = partShared ? 2 * partPower * sizeof(double) : 0;
+    const unsigned grid = std::min<unsigned>(stream_grid(s->dev, n, 256), (unsigned)sm_count(s->dev) * 8U);
+    DISPATCH_PREC(s, (k_decompose_marginals<float><<<grid, 256, shm, s->stream>>>((const float2*)s->amps, n, start, length, (float)floorv, remProb, remAngle, partProb, partAngle, partShared)),
+        (k_decompose_marginals<double><<<grid, 256, shm, s->stream>>>((const double2*)s->amps, n, start, length, floorv, remProb, remAngle, partProb, partAngle, partShared)));
+    s->stats.kernel_launches++;
+    void* nout = nullptr;
+    e = cudaMalloc(&nout, remPower * s->amp_bytes());
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(s->stream);
+        cudaFree(acc);
+        return cuda_fail(e, "cudaMalloc(decompose remainder)");
+    }
+    {
+        const unsigned g2 = stream_grid(s->dev, remPower, 256);
+        DISPATCH_PREC(s, (k_polar_rebuild<float><<<g2, 256, 0, s->stream>>>((float2*)nout, remPower, remProb, remAngle, (float)floorv)),
+            (k_polar_rebuild<double><<<g2, 256, 0, s->stream>>>((double2*)nout, remPower, remProb, remAngle, floorv)));
+        s->stats.kernel_launches++;
+    }
+    int rc = B200SV_OK;
+    if (dest) {
+        // build the part state on s's device, then move it if dest lives elsewhere
+        void* pout = nullptr;
+        e = cudaMalloc(&pout, partPower * s->amp_bytes());
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, "cudaMalloc(decompose part)");
+        } else {
+            const unsigned g3 = stream_grid(s->dev, partPower, 256);
+            DISPATCH_PREC(s, (k_polar_rebuild<float><<<g3, 256, 0, s->stream>>>((float2*)pout, partPower, partProb, partAngle, (float)floorv)),
+                (k_polar_rebuild<double><<<g3, 256, 0, s->stream>>>((double2*)pout, partPower, partProb, partAngle, floorv)));
+            s->stats.kernel_launches++;
+            cudaStreamSynchronize(s->stream);
+            if (dest->dev == s->dev) {
+                free_amps(dest);
+                dest->amps = pout;
+            } else {
+                DevGuard g4(dest->dev);
+                rc = alloc_amps(dest, false);
+                if (rc == B200SV_OK) {
+                    e = cudaMemcpyPeer(dest->amps, dest->dev, pout, s->dev, partPower * s->amp_bytes());
+                    if (e != cudaSuccess) {
+                        rc = cuda_fail(e, "decompose peer copy");
+                    }
+                }
+                cudaFree(pout);
+            }
+        }
+    }
+    e = cudaStreamSynchronize(s->stream);
+    cudaFree(acc);
+    if (e != cudaSuccess && rc == B200SV_OK) {
+        rc = cuda_fail(e, "decompose");
+    }
+    if (rc != B200SV_OK) {
+        cudaFree(nout);
+        return rc;
+    }
+    free_amps(s);
+    s->amps = nout;
+    s->nq = nl;
+    return B200SV_OK;
+}
+
+// ---- stats / timing ---------------------------------------------------------------------------------------------------
+
+int b200sv_get_stats(b200sv_t s, b200sv_stats* out)
+{
+    if (!s || !out) {
+        return einval("null argument");
+    }
+    *out = s->stats;
+    return B200SV_OK;
+}
+int b200sv_reset_stats(b200sv_t s)
+{
+    if (!s) {
+        return einval("null argument");
+    }
+    memset(&s->stats, 0, sizeof(s->stats));
+    return B200SV_OK;
+}
+
+int b200sv_timer_begin(b200sv_t s)
+{
+    SV_ENTER(s);
+    SV_TRY(flush_queue(s));
+    SV_CUDA(cudaEventRecord(s->ev0, s->stream));
+    return B200SV_OK;
+}
+int b200sv_timer_end(b200sv_t s, double* ms)
+{
+    SV_ENTER(s);
+    if (!ms) {
+        return einval("null out pointer");
+    }
+    SV_TRY(flush_queue(s));
+    SV_CUDA(cudaEventRecord(s->ev1, s->stream));
+    SV_CUDA(cudaEventSynchronize(s->ev1));
+    float f = 0;
+    SV_CUDA(cudaEventElapsedTime(&f, s->ev0, s->ev1));
+    *ms = f;
+    return B200SV_OK;
+}
+
+int b200sv_flush_l2(b200sv_t s, uint64_t bytes)
+{
+    SV_ENTER(s);
+    bytes = (bytes + 15U) & ~15ULL;
+    if (s->flush_bytes < bytes) {
+        if (s->d_flush) {
+            cudaFree(s->d_flush);
+            s->d_flush = nullptr;
+            s->flush_bytes = 0;
+        }
+        SV_CUDA(cudaMalloc(&s->d_flush, bytes));
+        s->flush_bytes = bytes;
+    }
+    const uint64_t n16 = bytes / 16;
+    k_fill_bytes<<<stream_grid(s->dev, n16, 256), 256, 0, s->stream>>>((uint4*)s->d_flush, n16, 0x5a5a5a5aU);
+    SV_CUDA(cudaGetLastError());
+    return B200SV_OK;
+}
+
+} // extern "C"

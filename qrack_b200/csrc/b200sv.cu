@@ -927,6 +927,7 @@ int b200sv_destroy(b200sv_t s)
     }
     DevGuard g(s->dev);
     cudaStreamSynchronize(s->stream);
+    fused_release(s);
     free_amps(s);
     if (s->d_scratch) {
         cudaFree(s->d_scratch);
@@ -1044,6 +1045,7 @@ int b200sv_set_device(b200sv_t s, int device)
     }
     SV_TRY(flush_queue(s));
     SV_CUDA(cudaStreamSynchronize(s->stream));
+    fused_release(s); // the sweep-program arena lives on the old device
     // build the new-device resources, then move the buffer with a peer copy
     b200sv_t n = nullptr;
     SV_TRY(b200sv_create(device, s->nq, s->prec, &n));
@@ -2285,6 +2287,15 @@ int b200sv_timer_end(b200sv_t s, double* ms)
     SV_CUDA(cudaEventElapsedTime(&f, s->ev0, s->ev1));
     *ms = f;
     return B200SV_OK;
+}
+
+int b200sv_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks, const int* kinds,
+    int* n_sweeps, int* n_passes)
+{
+    if (n_gates < 0 || (n_gates && (!targets || !cmasks || !kinds)) || !n_sweeps || !n_passes) {
+        return einval("plan_dry_run: bad arguments");
+    }
+    return fused_plan_dry_run(n_qubits, precision, n_gates, targets, cmasks, kinds, n_sweeps, n_passes);
 }
 
 int b200sv_flush_l2(b200sv_t s, uint64_t bytes)

@@ -120,6 +120,9 @@ int sm_count(int dev);
 // fused.cu
 int fused_flush(State* s);
 bool fused_accepts(const State* s, const GateOp& g);
+void fused_release(State* s);
+int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks, const int* kinds,
+    int* n_sweeps, int* n_passes);
 
 } // namespace b200sv
 

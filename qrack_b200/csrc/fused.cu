@@ -17,6 +17,8 @@
 #include "sv_common.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -24,42 +26,46 @@ namespace b200sv {
 
 constexpr int MAX_HIGH = 8;
 constexpr int MAX_PASS = 12;
-constexpr int MAX_OPS = 64;
-constexpr int MAX_NA = 32; // register amplitudes per sub-block
+constexpr int MAX_OPS = 96;
+constexpr int MAX_NCH = 16; // register chunks per sub-block (RB <= 4)
+constexpr int MAX_NA = 32;  // register amplitudes per sub-block
 
-enum { OP_GENERAL = 0, OP_REALM = 1, OP_XSWAP = 2, OP_PHASE = 3 };
+// device op codes: kind * 5 + jr (dense, so the dispatch compiles to a jump table); bit 8 = has a sub-block predicate
+enum { K_HAD = 0, K_XSWAP = 1, K_GEN_U = 2, K_GEN_P = 3, K_PHREG1 = 4, K_PHUNI = 5, K_PHGEN = 6 };
+constexpr uint32_t CODE_HAS_SB = 0x100U;
+// host (scheduler) op kinds
+enum { OP_GENERAL = 0, OP_HAD = 1, OP_XSWAP = 2, OP_PHASE = 3 };
 
 template <typename R> struct DevOp {
     uint64_t omask, oval; // predicate on the tile's global base index (qubits outside the tile)
-    uint32_t lmaskSb, lvalSb; // predicate on the sub-block base (tile-local amplitude index bits outside the register set)
-    uint32_t emask;           // bit e set: register amplitude e satisfies the register-resident part of the controls
-    int kind;
-    int jr; // register-bit index of the target (OP_PHASE: unused)
-    int pad;
+    // --- one 16-byte group, fetched with a single LDS.128 ---
+    uint32_t code;    // kind * 5 + jr [| CODE_HAS_SB]
+    uint32_t emask;   // bit e set: register amplitude e satisfies the register-resident part of the controls
+    uint32_t lmaskSb; // predicate on the sub-block base (tile-local amplitude bits outside the register set)
+    uint32_t lvalSb;
     R m[8];
 };
 
 struct DevPass {
     int opBegin, opEnd;
-    int nsb;                 // number of sub-block index bits
-    unsigned char sbit[16];  // sub-block index bit i -> tile chunk bit
-    unsigned short roffc[MAX_NA]; // register chunk e -> tile chunk offset
+    int nsb;                       // number of sub-block index bits
+    int nIt;                       // sub-blocks per thread
+    unsigned char sbit[16];        // sub-block index bit i -> tile chunk bit
+    unsigned short pswzB[MAX_NCH]; // register chunk e -> swizzled byte offset inside the tile
+    unsigned short itoffC[16];     // iteration -> chunk-index contribution of the sub-block bits above the thread id
 };
 
 struct DevSweep {
-    int nHigh;        // high qubits in the tile
-    int lowAmpBits;   // L: low qubits in the tile
-    int kc;           // tile chunk bits actually used (<= KC)
+    int nHigh;      // high qubits in the tile
+    int lowAmpBits; // L: low qubits in the tile
+    int kc;         // tile chunk bits actually used (<= KC)
     int nPass;
     int nOps;
-    int pad[3];
+    int hasScale;
+    double scale;   // deferred scalar of the un-normalised Hadamard butterflies, applied once in the last pass
     uint64_t highLow[MAX_HIGH]; // (2^q - 1) for push_apart of the tile base, ascending
     uint64_t highPow[MAX_HIGH]; // 2^q
     DevPass pass[MAX_PASS];
-};
-
-template <typename R> struct Apc {
-    static constexpr int v = 16 / (2 * sizeof(R)); // amplitudes per 16-byte chunk: fp32 2, fp64 1
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p)
@@ -73,93 +79,240 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4 v)
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// TMA SWIZZLE_128B layout on 16-byte chunks: chunk index bits [0..2] ^= bits [3..5]
-__device__ __forceinline__ uint32_t swz(uint32_t c) { return c ^ ((c >> 3) & 7U); }
+// TMA SWIZZLE_128B layout on 16-byte chunks: chunk index bits [0..2] ^= bits [3..5] (XOR-linear in the index)
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t c) { return c ^ ((c >> 3) & 7U); }
 
-template <int JR, int NA, typename C, typename R>
-__device__ __forceinline__ void app_general(C (&a)[NA], const R* __restrict__ m, uint32_t em)
+// ---------------------------------------------------------------------------------------------------------
+// register representation of amplitudes.
+//   fp32: one amplitude = one 64-bit register pair (re, im) driven with Blackwell's packed FADD2/FMUL2/FFMA2
+//         (PTX add/mul/fma.rn.f32x2): a complex multiply by a constant is 2 instructions, a Hadamard butterfly 2.
+//   fp64: plain double2 with DFMA.
+// ---------------------------------------------------------------------------------------------------------
+typedef unsigned long long ull;
+__device__ __forceinline__ ull pk(float lo, float hi)
 {
-    const C m0 = mk<R>(m[0], m[1]), m1 = mk<R>(m[2], m[3]), m2 = mk<R>(m[4], m[5]), m3 = mk<R>(m[6], m[7]);
-#pragma unroll
-    for (int e = 0; e < NA; ++e) {
-        if (!(e & (1 << JR))) {
-            if (em & (1U << e)) {
-                const C x = a[e], y = a[e | (1 << JR)];
-                a[e] = cmad2(m0, x, m1, y);
-                a[e | (1 << JR)] = cmad2(m2, x, m3, y);
-            }
-        }
-    }
+    ull r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
-template <int JR, int NA, typename C, typename R>
-__device__ __forceinline__ void app_realm(C (&a)[NA], const R* __restrict__ m, uint32_t em)
+__device__ __forceinline__ ull swp64(ull v)
 {
-    const R m0 = m[0], m1 = m[2], m2 = m[4], m3 = m[6];
-#pragma unroll
-    for (int e = 0; e < NA; ++e) {
-        if (!(e & (1 << JR))) {
-            if (em & (1U << e)) {
-                const C x = a[e], y = a[e | (1 << JR)];
-                a[e] = mk<R>(m0 * x.x + m1 * y.x, m0 * x.y + m1 * y.y);
-                a[e | (1 << JR)] = mk<R>(m2 * x.x + m3 * y.x, m2 * x.y + m3 * y.y);
-            }
-        }
-    }
+    float lo, hi;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return pk(hi, lo);
 }
-template <int JR, int NA, typename C> __device__ __forceinline__ void app_xswap(C (&a)[NA], uint32_t em)
+__device__ __forceinline__ ull f2add(ull a, ull b)
 {
-#pragma unroll
-    for (int e = 0; e < NA; ++e) {
-        if (!(e & (1 << JR))) {
-            if (em & (1U << e)) {
-                const C x = a[e];
-                a[e] = a[e | (1 << JR)];
-                a[e | (1 << JR)] = x;
-            }
-        }
-    }
+    ull r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ ull f2mul(ull a, ull b)
+{
+    ull r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ ull f2fma(ull a, ull b, ull c)
+{
+    ull r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
 }
 
-template <int NA, typename C, typename R> struct TargetDispatch {
-    static __device__ __forceinline__ void run(C (&a)[NA], int kind, int jr, const R* m, uint32_t em)
+template <typename R> struct AmpOps;
+template <> struct AmpOps<float> {
+    typedef ull A;
+    typedef ulonglong2 Chunk; // 16 bytes = 2 amplitudes
+    static constexpr int APC = 2;
+    struct Ph {
+        ull xx, ny; // (x, x), (-y, y)
+    };
+    static __device__ __forceinline__ Ph mkph(float x, float y) { return Ph{ pk(x, x), pk(-y, y) }; }
+    static __device__ __forceinline__ A mulc(A a, const Ph& p) { return f2fma(a, p.xx, f2mul(swp64(a), p.ny)); }
+    static __device__ __forceinline__ A macc(A a, const Ph& p, A acc) { return f2fma(a, p.xx, f2fma(swp64(a), p.ny, acc)); }
+    static __device__ __forceinline__ void had(A& x, A& y)
     {
-#define SV_CASE(J)                                                                                                     \
-    case J:                                                                                                            \
-        if ((1 << J) < NA) {                                                                                           \
-            if (kind == OP_GENERAL)                                                                                    \
-                app_general<((1 << J) < NA ? J : 0), NA, C, R>(a, m, em);                                              \
-            else if (kind == OP_REALM)                                                                                 \
-                app_realm<((1 << J) < NA ? J : 0), NA, C, R>(a, m, em);                                                \
-            else                                                                                                       \
-                app_xswap<((1 << J) < NA ? J : 0), NA, C>(a, em);                                                      \
-        }                                                                                                              \
-        break;
-        switch (jr) {
-            SV_CASE(0)
-            SV_CASE(1)
-            SV_CASE(2)
-            SV_CASE(3)
-            SV_CASE(4)
-        default:
-            break;
-        }
-#undef SV_CASE
+        x = f2add(x, y);
+        y = f2fma(y, pk(-2.0f, -2.0f), x);
+    }
+    static __device__ __forceinline__ A scale(A a, float s) { return f2mul(a, pk(s, s)); }
+    static __device__ __forceinline__ void get(const Chunk& c, A* a)
+    {
+        a[0] = c.x;
+        a[1] = c.y;
+    }
+    static __device__ __forceinline__ Chunk put(const A* a)
+    {
+        Chunk c;
+        c.x = a[0];
+        c.y = a[1];
+        return c;
     }
 };
+template <> struct AmpOps<double> {
+    typedef double2 A;
+    typedef double2 Chunk; // 16 bytes = 1 amplitude
+    static constexpr int APC = 1;
+    struct Ph {
+        double x, y;
+    };
+    static __device__ __forceinline__ Ph mkph(double x, double y) { return Ph{ x, y }; }
+    static __device__ __forceinline__ A mulc(A a, const Ph& p) { return make_double2(a.x * p.x - a.y * p.y, a.x * p.y + a.y * p.x); }
+    static __device__ __forceinline__ A macc(A a, const Ph& p, A acc)
+    {
+        return make_double2(fma(a.x, p.x, fma(-a.y, p.y, acc.x)), fma(a.x, p.y, fma(a.y, p.x, acc.y)));
+    }
+    static __device__ __forceinline__ void had(A& x, A& y)
+    {
+        x.x += y.x;
+        x.y += y.y;
+        y.x = fma(y.x, -2.0, x.x);
+        y.y = fma(y.y, -2.0, x.y);
+    }
+    static __device__ __forceinline__ A scale(A a, double s) { return make_double2(a.x * s, a.y * s); }
+    static __device__ __forceinline__ void get(const Chunk& c, A* a) { a[0] = c; }
+    static __device__ __forceinline__ Chunk put(const A* a) { return a[0]; }
+};
+
+template <typename R> struct Apc {
+    static constexpr int v = AmpOps<R>::APC;
+};
+
+// ---- in-register gate bodies: JR = register-bit index of the target ------------------------------------------------
+template <typename R, int JR, int NA> __device__ __forceinline__ void app_had(typename AmpOps<R>::A (&a)[NA])
+{
+#pragma unroll
+    for (int e = 0; e < NA; ++e) {
+        if (!(e & (1 << JR))) {
+            AmpOps<R>::had(a[e], a[e | (1 << JR)]);
+        }
+    }
+}
+template <typename R, int JR, int NA, bool PRED>
+__device__ __forceinline__ void app_general(typename AmpOps<R>::A (&a)[NA], const R* __restrict__ m, uint32_t em)
+{
+    typedef AmpOps<R> O;
+    typedef typename O::A A;
+    const typename O::Ph m0 = O::mkph(m[0], m[1]), m1 = O::mkph(m[2], m[3]), m2 = O::mkph(m[4], m[5]), m3 = O::mkph(m[6], m[7]);
+#pragma unroll
+    for (int e = 0; e < NA; ++e) {
+        if (!(e & (1 << JR))) {
+            const A x = a[e], y = a[e | (1 << JR)];
+            const A nx = O::macc(y, m1, O::mulc(x, m0));
+            const A ny = O::macc(y, m3, O::mulc(x, m2));
+            if (PRED) {
+                const bool p = (em >> e) & 1U;
+                a[e] = p ? nx : x;
+                a[e | (1 << JR)] = p ? ny : y;
+            } else {
+                a[e] = nx;
+                a[e | (1 << JR)] = ny;
+            }
+        }
+    }
+}
+template <typename R, int JR, int NA> __device__ __forceinline__ void app_xswap(typename AmpOps<R>::A (&a)[NA], uint32_t em)
+{
+    typedef typename AmpOps<R>::A A;
+#pragma unroll
+    for (int e = 0; e < NA; ++e) {
+        if (!(e & (1 << JR))) {
+            const bool p = (em >> e) & 1U;
+            const A x = a[e], y = a[e | (1 << JR)];
+            a[e] = p ? y : x;
+            a[e | (1 << JR)] = p ? x : y;
+        }
+    }
+}
+template <typename R, int JR, int NA>
+__device__ __forceinline__ void app_phase_reg(typename AmpOps<R>::A (&a)[NA], const typename AmpOps<R>::Ph& ph)
+{
+#pragma unroll
+    for (int e = 0; e < NA; ++e) {
+        if (e & (1 << JR)) {
+            a[e] = AmpOps<R>::mulc(a[e], ph);
+        }
+    }
+}
+
+template <typename R, int NA>
+__device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const DevOp<R>& op, uint32_t xsb)
+{
+    typedef AmpOps<R> O;
+    const uint4 hd = *reinterpret_cast<const uint4*>(&op.code);
+    bool tp = true;
+    if (hd.x & CODE_HAS_SB) {
+        tp = (xsb & hd.z) == hd.w;
+    }
+    const uint32_t em = tp ? hd.y : 0U;
+#define SV_J(J) (((1 << (J)) < NA) ? (J) : 0)
+#define SV_CASES(J)                                                                                                    \
+    case K_HAD * 5 + J:                                                                                             \
+        app_had<R, SV_J(J), NA>(a);                                                                                    \
+        break;                                                                                                         \
+    case K_XSWAP * 5 + J:                                                                                           \
+        app_xswap<R, SV_J(J), NA>(a, em);                                                                              \
+        break;                                                                                                         \
+    case K_GEN_U * 5 + J:                                                                                           \
+        app_general<R, SV_J(J), NA, false>(a, op.m, em);                                                               \
+        break;                                                                                                         \
+    case K_GEN_P * 5 + J:                                                                                           \
+        app_general<R, SV_J(J), NA, true>(a, op.m, em);                                                                \
+        break;                                                                                                         \
+    case K_PHREG1 * 5 + J:                                                                                          \
+        if (tp) {                                                                                                      \
+            app_phase_reg<R, SV_J(J), NA>(a, O::mkph(op.m[0], op.m[1]));                                               \
+        }                                                                                                              \
+        break;
+    switch (hd.x & 0xffU) {
+        SV_CASES(0)
+        SV_CASES(1)
+        SV_CASES(2)
+        SV_CASES(3)
+        SV_CASES(4)
+    case K_PHUNI * 5:
+        if (tp) {
+            const typename O::Ph ph = O::mkph(op.m[0], op.m[1]);
+#pragma unroll
+            for (int e = 0; e < NA; ++e) {
+                a[e] = O::mulc(a[e], ph);
+            }
+        }
+        break;
+    case K_PHGEN * 5: {
+        const typename O::Ph ph = O::mkph(op.m[0], op.m[1]);
+#pragma unroll
+        for (int e = 0; e < NA; ++e) {
+            const typename O::A v = O::mulc(a[e], ph);
+            a[e] = ((em >> e) & 1U) ? v : a[e];
+        }
+    } break;
+    default:
+        break;
+    }
+#undef SV_CASES
+#undef SV_J
+}
 
 template <typename R, int KC, int RB, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
     k_fused_sweep(typename Cx<R>::type* __restrict__ psi, const unsigned char* __restrict__ prog, uint32_t progBytes, uint64_t nTiles)
 {
     typedef typename Cx<R>::type C;
-    constexpr int APC = Apc<R>::v;
+    typedef AmpOps<R> O;
+    typedef typename O::A A;
+    typedef typename O::Chunk Chunk;
+    constexpr int APC = O::APC;
     constexpr int NCH = 1 << RB;
     constexpr int NA = NCH * APC;
-    static_assert(NA <= MAX_NA, "register sub-block too large");
+    static_assert(NA <= MAX_NA && NCH <= MAX_NCH, "register sub-block too large");
     extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* tileB = smem;
     uint4* tile = reinterpret_cast<uint4*>(smem);
     unsigned char* sprog = smem + ((size_t)16 << KC);
-    __shared__ uint64_t rowOff[1 << 8];
+    __shared__ uint64_t rowOff[1 << MAX_HIGH];
+    __shared__ uint32_t activeW[4];
 
     const int tid = threadIdx.x;
     for (uint32_t i = tid; i < progBytes / 16; i += NT) {
@@ -183,12 +336,23 @@ __global__ void __launch_bounds__(NT, MINB)
         rowOff[r] = off;
     }
     __syncthreads();
+    const uint32_t nSub = nChunk >> RB;
+    const R fscale = (R)sw.scale;
+    const int nOps = sw.nOps;
 
     for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
         uint64_t base = t << sw.lowAmpBits;
         for (int h = 0; h < sw.nHigh; ++h) {
             const uint64_t lo = base & sw.highLow[h];
             base = ((base ^ lo) << 1) | lo;
+        }
+        // which ops act on this tile at all (predicates on qubits outside the tile are uniform per tile)
+        if (tid < 128) {
+            const bool act = (tid < nOps) && ((base & ops[tid < nOps ? tid : 0].omask) == ops[tid < nOps ? tid : 0].oval);
+            const uint32_t bal = __ballot_sync(0xffffffffU, act);
+            if ((tid & 31) == 0) {
+                activeW[tid >> 5] = bal;
+            }
         }
         // ---- load: global -> swizzled smem ----------------------------------------------------------------------
         for (uint32_t c0 = tid; c0 < nChunk; c0 += NT * 8) {
@@ -213,40 +377,60 @@ __global__ void __launch_bounds__(NT, MINB)
         // ---- passes ----------------------------------------------------------------------------------------------
         for (int p = 0; p < sw.nPass; ++p) {
             const DevPass& ps = sw.pass[p];
-            const uint32_t nSub = nChunk >> RB;
-            for (uint32_t s = tid; s < nSub; s += NT) {
-                uint32_t sbc = 0;
-                for (int i = 0; i < ps.nsb; ++i) {
-                    sbc |= ((s >> i) & 1U) << ps.sbit[i];
+            uint32_t po[NCH];
+#pragma unroll
+            for (int e = 0; e < NCH; ++e) {
+                po[e] = ps.pswzB[e];
+            }
+            uint32_t dep = 0;
+            {
+                const int nb = ps.nsb < 8 ? ps.nsb : 8;
+                for (int i = 0; i < nb; ++i) {
+                    dep |= ((tid >> i) & 1U) << ps.sbit[i];
                 }
-                C a[NA];
+            }
+            // active ops of this pass as (up to 4) 32-bit words
+            uint32_t pm[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int lo = ps.opBegin - 32 * w, hi = ps.opEnd - 32 * w;
+                uint32_t m = activeW[w];
+                m = (lo > 0) ? ((lo >= 32) ? 0U : (m & (0xffffffffU << lo))) : m;
+                m = (hi < 32) ? ((hi <= 0) ? 0U : (m & (0xffffffffU >> (32 - hi)))) : m;
+                pm[w] = m;
+            }
+            const bool lastPass = (p == sw.nPass - 1) && sw.hasScale;
+            for (int it = 0; it < ps.nIt; ++it) {
+                if ((uint32_t)(it * NT + tid) >= nSub) {
+                    break;
+                }
+                const uint32_t sbc = dep | ps.itoffC[it];
+                const uint32_t swb = swz(sbc) << 4;
+                A a[NA];
 #pragma unroll
                 for (int e = 0; e < NCH; ++e) {
-                    const uint4 v = tile[swz(sbc | ps.roffc[e])];
-                    *reinterpret_cast<uint4*>(&a[e * APC]) = v;
+                    const Chunk c = *reinterpret_cast<const Chunk*>(tileB + (swb ^ po[e]));
+                    O::get(c, &a[e * APC]);
                 }
                 const uint32_t xsb = sbc * APC;
-                for (int o = ps.opBegin; o < ps.opEnd; ++o) {
-                    const DevOp<R>& op = ops[o];
-                    if ((base & op.omask) != op.oval) {
-                        continue;
+#pragma unroll 1
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t m = (w == 0) ? pm[0] : ((w == 1) ? pm[1] : ((w == 2) ? pm[2] : pm[3]));
+                    while (m) {
+                        const int o = 32 * w + __ffs(m) - 1;
+                        m &= m - 1U;
+                        exec_op<R, NA>(a, ops[o], xsb);
                     }
-                    const uint32_t em = ((xsb & op.lmaskSb) == op.lvalSb) ? op.emask : 0U;
-                    if (op.kind == OP_PHASE) {
-                        const C ph = mk<R>(op.m[0], op.m[1]);
+                }
+                if (lastPass) {
 #pragma unroll
-                        for (int e = 0; e < NA; ++e) {
-                            if (em & (1U << e)) {
-                                a[e] = cmul<C>(ph, a[e]);
-                            }
-                        }
-                    } else {
-                        TargetDispatch<NA, C, R>::run(a, op.kind, op.jr, op.m, em);
+                    for (int e = 0; e < NA; ++e) {
+                        a[e] = O::scale(a[e], fscale);
                     }
                 }
 #pragma unroll
                 for (int e = 0; e < NCH; ++e) {
-                    tile[swz(sbc | ps.roffc[e])] = *reinterpret_cast<const uint4*>(&a[e * APC]);
+                    *reinterpret_cast<Chunk*>(tileB + (swb ^ po[e])) = O::put(&a[e * APC]);
                 }
             }
             __syncthreads();
@@ -312,10 +496,11 @@ static void lower_queue(const std::vector<GateOp>& q, std::vector<HostOp>& out)
         h.cmask = g.cmask;
         h.cval = g.cval;
         memcpy(h.m, g.m, sizeof(h.m));
+        const bool allReal = (g.m[1] == 0.0 && g.m[3] == 0.0 && g.m[5] == 0.0 && g.m[7] == 0.0);
         if (g.kind == 2 && g.m[2] == 1.0 && g.m[3] == 0.0 && g.m[4] == 1.0 && g.m[5] == 0.0) {
             h.kind = OP_XSWAP;
-        } else if (g.m[1] == 0.0 && g.m[3] == 0.0 && g.m[5] == 0.0 && g.m[7] == 0.0) {
-            h.kind = OP_REALM;
+        } else if (!g.cmask && allReal && g.m[0] > 0.0 && g.m[0] == g.m[2] && g.m[0] == g.m[4] && g.m[6] == -g.m[0]) {
+            h.kind = OP_HAD; // c * [[1,1],[1,-1]]: butterfly now, the scalar c is applied once per sweep
         } else {
             h.kind = OP_GENERAL;
         }
@@ -331,11 +516,14 @@ struct TileCfg {
     int L;    // low (contiguous) amplitude bits
     int kA;   // tile amplitude bits actually used
     int H;    // capacity of high qubits
+    int NT;   // threads per CTA
+    int maxOps; // ops per sweep (bounded by the shared-memory program area: 3 CTAs/SM must fit)
 };
 
-static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref)
+static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref, int NT = 256)
 {
     TileCfg c;
+    c.NT = NT;
     c.n = n;
     c.apcLog = (prec == 32) ? 1 : 0;
     c.KC = KC;
@@ -347,6 +535,7 @@ static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref)
         c.L = c.kA; // whole state is one tile
     }
     c.H = c.kA - c.L;
+    c.maxOps = (prec == 32) ? MAX_OPS : (MAX_OPS * 2) / 3;
     return c;
 }
 
@@ -401,7 +590,7 @@ static void plan_sweep(std::vector<HostOp>& pending, const TileCfg& cfg, SweepPl
     uint64_t inTile = (cfg.L >= 64) ? ~0ULL : (bitq(cfg.L) - 1U);
     int freeHigh = cfg.H;
     std::vector<HostOp> sel;
-    greedy_select(pending, sel, MAX_OPS, 2048, [&](const HostOp& op) {
+    greedy_select(pending, sel, (size_t)cfg.maxOps, 2048, [&](const HostOp& op) {
         if (op.tq < 0 || (inTile & bitq(op.tq))) {
             return true;
         }
@@ -489,7 +678,10 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
     }
     const int kc = ds->kc;
     const int APC = 1 << cfg.apcLog;
-    const int NA = (1 << cfg.RB) * APC;
+    const int NCH = 1 << cfg.RB;
+    const int NA = NCH * APC;
+    const int NT = cfg.NT;
+    double scale = 1.0;
     int o = 0;
     for (int p = 0; p < ds->nPass; ++p) {
         const PassPlan& pp = sp.passes[p];
@@ -531,28 +723,43 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
         for (size_t i = 0; i < sb.size(); ++i) {
             dp.sbit[i] = (unsigned char)sb[i];
         }
+        const uint32_t nSub = 1U << dp.nsb;
+        dp.nIt = (int)std::max<uint32_t>(1U, nSub / (uint32_t)NT);
+        int tidBits = 0;
+        while ((1 << tidBits) < NT) {
+            ++tidBits;
+        }
+        for (int it = 0; it < dp.nIt && it < 16; ++it) {
+            uint32_t off = 0;
+            for (int i = tidBits; i < dp.nsb; ++i) {
+                if ((it >> (i - tidBits)) & 1) {
+                    off |= 1U << sb[i];
+                }
+            }
+            dp.itoffC[it] = (unsigned short)off;
+        }
         // register chunk offsets and per-register-amplitude tile-local amplitude offsets
         uint32_t roffA[MAX_NA];
         uint32_t regAmpMask = cfg.apcLog ? 1U : 0U;
         for (int cb : rb) {
             regAmpMask |= 1U << (cb + cfg.apcLog);
         }
-        for (int e = 0; e < (1 << cfg.RB); ++e) {
+        for (int e = 0; e < NCH; ++e) {
             uint32_t off = 0;
             for (int b = 0; b < cfg.RB; ++b) {
                 if ((e >> b) & 1) {
                     off |= 1U << rb[b];
                 }
             }
-            dp.roffc[e] = (unsigned short)off;
+            dp.pswzB[e] = (unsigned short)(swz(off) << 4);
             for (int w = 0; w < APC; ++w) {
                 roffA[e * APC + w] = (off << cfg.apcLog) | (uint32_t)w;
             }
         }
+        const uint32_t fullE = (NA >= 32) ? 0xffffffffU : ((1U << NA) - 1U);
         dp.opBegin = o;
         for (const HostOp& hop : pp.ops) {
             DevOp<R>& d = dops[o++];
-            d.kind = hop.kind;
             d.omask = hop.cmask & ~tileMask;
             d.oval = hop.cval & ~tileMask;
             // tile-local predicate
@@ -575,24 +782,47 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
                 }
             }
             d.emask = em;
-            d.jr = 0;
-            if (hop.tq >= 0) {
-                const int tb = tile_bit(cfg, sp.highQ, hop.tq);
-                // register-bit index of the target: position among the register amplitude bits
+            const bool uncond = (em == fullE && d.lmaskSb == 0);
+            auto reg_index = [&](int tb) {
                 int jr = 0;
                 for (int b = 0; b < tb; ++b) {
                     if (regAmpMask & (1U << b)) {
                         ++jr;
                     }
                 }
-                d.jr = jr;
-            }
+                return jr;
+            };
             for (int k = 0; k < 8; ++k) {
                 d.m[k] = (R)hop.m[k];
             }
+            uint32_t kind = 0, jr = 0;
+            if (hop.kind == OP_PHASE) {
+                const int nreg = __builtin_popcount(lmr);
+                if (nreg == 0) {
+                    kind = K_PHUNI;
+                } else if (nreg == 1 && lvr == lmr) {
+                    kind = K_PHREG1;
+                    jr = (uint32_t)reg_index(__builtin_ctz(lmr));
+                } else {
+                    kind = K_PHGEN;
+                }
+            } else {
+                jr = (uint32_t)reg_index(tile_bit(cfg, sp.highQ, hop.tq));
+                if (hop.kind == OP_HAD) {
+                    kind = K_HAD;
+                    scale *= hop.m[0];
+                } else if (hop.kind == OP_XSWAP) {
+                    kind = K_XSWAP;
+                } else {
+                    kind = uncond ? K_GEN_U : K_GEN_P;
+                }
+            }
+            d.code = (kind * 5U + jr) | (d.lmaskSb ? CODE_HAS_SB : 0U);
         }
         dp.opEnd = o;
     }
+    ds->scale = scale;
+    ds->hasScale = (scale != 1.0) ? 1 : 0;
     return bytes;
 }
 
@@ -671,6 +901,43 @@ static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes
     return B200SV_OK;
 }
 
+// tuning knobs (env B200SV_FUSED="RB,L32,L64"): register chunk bits per pass and the contiguous-run length (low tile bits)
+struct FusedKnobs {
+    int RB = 3;
+    int L32 = 7;
+    int L64 = 6;
+};
+static const FusedKnobs& knobs()
+{
+    static FusedKnobs k = [] {
+        FusedKnobs v;
+        const char* e = getenv("B200SV_FUSED");
+        if (e) {
+            int rb = 0, l32 = 0, l64 = 0;
+            const int got = sscanf(e, "%d,%d,%d", &rb, &l32, &l64);
+            if (got >= 1 && (rb == 3 || rb == 4)) {
+                v.RB = rb;
+            }
+            if (got >= 2 && l32 >= 5 && l32 <= 9) {
+                v.L32 = l32;
+            }
+            if (got >= 3 && l64 >= 4 && l64 <= 8) {
+                v.L64 = l64;
+            }
+        }
+        return v;
+    }();
+    return k;
+}
+constexpr int FUSED_KC = 12;
+constexpr int FUSED_NT = 256;
+
+static TileCfg state_cfg(int nq, int prec)
+{
+    const FusedKnobs& k = knobs();
+    return make_cfg(nq, prec, FUSED_KC, k.RB, prec == 32 ? k.L32 : k.L64, FUSED_NT);
+}
+
 int fused_flush(State* s)
 {
     if (s->queue.empty()) {
@@ -682,13 +949,12 @@ int fused_flush(State* s)
     }
     std::vector<HostOp> pending;
     lower_queue(s->queue, pending);
+    const size_t nGates = s->queue.size();
     s->queue.clear();
     if (pending.empty()) {
         return B200SV_OK;
     }
-    constexpr int KC = 12, RB = 3, NT = 256, MINB = 3;
-    const int Lpref = (s->prec == 32) ? 7 : 6;
-    const TileCfg cfg = make_cfg(s->nq, s->prec, KC, RB, Lpref);
+    const TileCfg cfg = state_cfg(s->nq, s->prec);
     Arena* ar = get_arena(s);
     if (!ar->done) {
         SV_CUDA(cudaEventCreateWithFlags(&ar->done, cudaEventDisableTiming));
@@ -696,7 +962,6 @@ int fused_flush(State* s)
     // build every sweep of this flush
     std::vector<unsigned char> buf;
     std::vector<std::pair<size_t, size_t>> segs; // (offset, bytes)
-    std::vector<size_t> nops;
     while (!pending.empty()) {
         SweepPlan sp;
         plan_sweep(pending, cfg, sp);
@@ -707,7 +972,6 @@ int fused_flush(State* s)
         const size_t off = buf.size();
         const size_t bytes = (s->prec == 32) ? encode_sweep<float>(sp, cfg, buf) : encode_sweep<double>(sp, cfg, buf);
         segs.push_back({ off, bytes });
-        nops.push_back(sp.nOps);
     }
     if (ar->pending) {
         SV_CUDA(cudaEventSynchronize(ar->done));
@@ -726,16 +990,26 @@ int fused_flush(State* s)
     SV_CUDA(cudaMemcpyAsync(ar->dev, ar->host, buf.size(), cudaMemcpyHostToDevice, s->stream));
     const uint64_t nTiles = s->dim() >> cfg.kA;
     for (size_t i = 0; i < segs.size(); ++i) {
+        const unsigned char* dp = ar->dev + segs[i].first;
+        const uint32_t pb = (uint32_t)segs[i].second;
         if (s->prec == 32) {
-            SV_TRY((launch_sweep<float, KC, RB, NT, MINB>(s, ar->dev + segs[i].first, (uint32_t)segs[i].second, nTiles)));
+            if (cfg.RB == 4) {
+                SV_TRY((launch_sweep<float, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, nTiles)));
+            } else {
+                SV_TRY((launch_sweep<float, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, nTiles)));
+            }
         } else {
-            SV_TRY((launch_sweep<double, KC, RB, NT, MINB>(s, ar->dev + segs[i].first, (uint32_t)segs[i].second, nTiles)));
+            if (cfg.RB == 4) {
+                SV_TRY((launch_sweep<double, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, nTiles)));
+            } else {
+                SV_TRY((launch_sweep<double, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, nTiles)));
+            }
         }
         s->stats.kernel_launches++;
         s->stats.fused_sweeps++;
-        s->stats.fused_gates += nops[i];
         s->stats.bytes_swept += 2ULL * s->dim() * s->amp_bytes();
     }
+    s->stats.fused_gates += nGates;
     SV_CUDA(cudaEventRecord(ar->done, s->stream));
     ar->pending = true;
     return B200SV_OK;
@@ -769,8 +1043,7 @@ int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targ
     }
     std::vector<HostOp> pending;
     lower_queue(q, pending);
-    constexpr int KC = 12, RB = 3;
-    const TileCfg cfg = make_cfg(n_qubits, precision, KC, RB, precision == 32 ? 7 : 6);
+    const TileCfg cfg = state_cfg(n_qubits, precision);
     int sweeps = 0, passes = 0;
     while (!pending.empty()) {
         SweepPlan sp;

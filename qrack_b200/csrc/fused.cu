@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(NT, MINB)
     unsigned char* sprog = smem + ((size_t)16 << KC);
     __shared__ uint64_t rowOff[1 << MAX_HIGH];
     __shared__ uint32_t activeW[4];
+    __shared__ uint64_t uOff[(1 << KC) / NT];
 
     const int tid = threadIdx.x;
     for (uint32_t i = tid; i < progBytes / 16; i += NT) {
@@ -336,6 +337,18 @@ __global__ void __launch_bounds__(NT, MINB)
         rowOff[r] = off;
     }
     __syncthreads();
+    // Thread `tid` moves chunks c = tid + NT*u.  Because NT is a power of two, the global offset of chunk c separates
+    // into a per-thread part and a per-iteration (uniform) part, and the swizzled smem slot is swz(tid) + NT*u.
+    constexpr int NU = (1 << KC) / NT; // chunks per thread for a full tile
+    if (tid < NU) {
+        const uint32_t cu = (uint32_t)tid * NT;
+        uOff[tid] = (cu < nChunk) ? rowOff[cu >> lcb] + (uint64_t)(cu & colMask) * APC : 0;
+    }
+    const uint32_t nU = (nChunk >= (uint32_t)NT) ? (nChunk / NT) : 1U; // iterations actually needed
+    const bool mover = (uint32_t)tid < nChunk;
+    const uint64_t tOff = mover ? rowOff[(uint32_t)tid >> lcb] + (uint64_t)((uint32_t)tid & colMask) * APC : 0;
+    unsigned char* const tSlot = tileB + ((size_t)swz((uint32_t)tid) << 4);
+    __syncthreads();
     const uint32_t nSub = nChunk >> RB;
     const R fscale = (R)sw.scale;
     const int nOps = sw.nOps;
@@ -355,21 +368,25 @@ __global__ void __launch_bounds__(NT, MINB)
             }
         }
         // ---- load: global -> swizzled smem ----------------------------------------------------------------------
-        for (uint32_t c0 = tid; c0 < nChunk; c0 += NT * 8) {
-            uint4 v[8];
+        if (mover) {
+            const uint4* gp = reinterpret_cast<const uint4*>(psi + base + tOff);
+            if (nU == NU) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t c = c0 + u * NT;
-                if (c < nChunk) {
-                    const C* g = psi + base + rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC;
-                    v[u] = ld_stream(reinterpret_cast<const uint4*>(g));
+                for (int u0 = 0; u0 < NU; u0 += 8) {
+                    uint4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        v[u] = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const C*>(gp) + uOff[u0 + u]));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        *reinterpret_cast<uint4*>(tSlot + (size_t)(u0 + u) * NT * 16) = v[u];
+                    }
                 }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t c = c0 + u * NT;
-                if (c < nChunk) {
-                    tile[swz(c)] = v[u];
+            } else {
+                for (uint32_t u = 0; u < nU; ++u) {
+                    *reinterpret_cast<uint4*>(tSlot + (size_t)u * NT * 16) =
+                        ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const C*>(gp) + uOff[u]));
                 }
             }
         }
@@ -399,6 +416,7 @@ __global__ void __launch_bounds__(NT, MINB)
                 m = (hi < 32) ? ((hi <= 0) ? 0U : (m & (0xffffffffU >> (32 - hi)))) : m;
                 pm[w] = m;
             }
+            const int wBegin = ps.opBegin >> 5, wEnd = (ps.opEnd > ps.opBegin) ? ((ps.opEnd - 1) >> 5) : (wBegin - 1);
             const bool lastPass = (p == sw.nPass - 1) && sw.hasScale;
             for (int it = 0; it < ps.nIt; ++it) {
                 if ((uint32_t)(it * NT + tid) >= nSub) {
@@ -414,7 +432,7 @@ __global__ void __launch_bounds__(NT, MINB)
                 }
                 const uint32_t xsb = sbc * APC;
 #pragma unroll 1
-                for (int w = 0; w < 4; ++w) {
+                for (int w = wBegin; w <= wEnd; ++w) {
                     uint32_t m = (w == 0) ? pm[0] : ((w == 1) ? pm[1] : ((w == 2) ? pm[2] : pm[3]));
                     while (m) {
                         const int o = 32 * w + __ffs(m) - 1;
@@ -436,13 +454,18 @@ __global__ void __launch_bounds__(NT, MINB)
             __syncthreads();
         }
         // ---- store: swizzled smem -> global ------------------------------------------------------------------------
-        for (uint32_t c0 = tid; c0 < nChunk; c0 += NT * 8) {
+        if (mover) {
+            uint4* gp = reinterpret_cast<uint4*>(psi + base + tOff);
+            if (nU == NU) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t c = c0 + u * NT;
-                if (c < nChunk) {
-                    C* g = psi + base + rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC;
-                    st_stream(reinterpret_cast<uint4*>(g), tile[swz(c)]);
+                for (int u = 0; u < NU; ++u) {
+                    st_stream(reinterpret_cast<uint4*>(reinterpret_cast<C*>(gp) + uOff[u]),
+                        *reinterpret_cast<const uint4*>(tSlot + (size_t)u * NT * 16));
+                }
+            } else {
+                for (uint32_t u = 0; u < nU; ++u) {
+                    st_stream(reinterpret_cast<uint4*>(reinterpret_cast<C*>(gp) + uOff[u]),
+                        *reinterpret_cast<const uint4*>(tSlot + (size_t)u * NT * 16));
                 }
             }
         }

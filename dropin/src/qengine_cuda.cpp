@@ -1,0 +1,893 @@
+// qengine_cuda.cpp — Qrack::QEngineCUDA on the B200-native core (see dropin/include/qengine_cuda.hpp).
+//
+// Host-side semantics follow QEngineCPU, the parity oracle (reference src/qengine/state.cpp, utility.cpp); every
+// method cites the lines it mirrors.  All amplitude work happens behind include/b200sv.h.
+#include "qengine_cuda.hpp"
+
+#include "b200sv.h"
+#include "qengine_cpu.hpp"
+#include "qengine_gpu_util.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace Qrack {
+
+static const int kPrecision = (int)(8U * sizeof(real1));
+
+void QEngineCUDA::Check(int rc) const
+{
+    if (rc == B200SV_OK) {
+        return;
+    }
+    const std::string msg = std::string("QEngineCUDA(b200sv): ") + b200sv_last_error();
+    if (rc == B200SV_EINVAL) {
+        throw std::invalid_argument(msg);
+    }
+    if (rc == B200SV_ENOMEM) {
+        throw bad_alloc(msg);
+    }
+    throw std::runtime_error(msg);
+}
+
+QEngineCUDAPtr QEngineCUDA::Cast(QInterfacePtr p, const char* what) const
+{
+    QEngineCUDAPtr c = std::dynamic_pointer_cast<QEngineCUDA>(p);
+    if (!c) {
+        throw std::invalid_argument(std::string("QEngineCUDA::") + what + " argument is not a QEngineCUDA!");
+    }
+    return c;
+}
+
+QEngineCUDA::QEngineCUDA(bitLenInt qBitCount, const bitCapInt& initState, qrack_rand_gen_ptr rgp, const complex& phaseFac,
+    bool doNorm, bool randomGlobalPhase, bool useHostMem, int64_t devID, bool useHardwareRNG, bool ignored,
+    real1_f norm_thresh, std::vector<int64_t> ignored2, bitLenInt ignored4, real1_f ignored3)
+    : QEngine(qBitCount, rgp, doNorm, randomGlobalPhase, useHostMem, useHardwareRNG, norm_thresh)
+    , sv(nullptr)
+    , deviceID(devID)
+    , svCountSynced(false)
+{
+    if (deviceID < 0) {
+        deviceID = (int64_t)CUDAEngine::Instance().GetDefaultDeviceID();
+    }
+    Check(b200sv_create((int)deviceID, (int)qBitCount, kPrecision, &sv));
+    if (!qubitCount) {
+        runningNorm = ZERO_R1; // reference QEngineCPU ctor -> ZeroAmplitudes(), state.cpp:50-54
+        return;
+    }
+    // reference state.cpp:56-63
+    const complex ph = (phaseFac == CMPLX_DEFAULT_ARG) ? GetNonunitaryPhase() : phaseFac;
+    Check(b200sv_set_permutation(sv, (uint64_t)(bitCapIntOcl)initState, (double)real(ph), (double)imag(ph)));
+}
+
+QEngineCUDA::~QEngineCUDA()
+{
+    if (sv) {
+        b200sv_destroy(sv);
+        sv = nullptr;
+    }
+}
+
+void QEngineCUDA::SetDevice(int64_t dID)
+{
+    if (dID < 0) {
+        dID = (int64_t)CUDAEngine::Instance().GetDefaultDeviceID();
+    }
+    Check(b200sv_set_device(sv, (int)dID));
+    deviceID = dID;
+}
+
+bitCapIntOcl QEngineCUDA::GetMaxSize()
+{
+    return CUDAEngine::Instance().GetDeviceContextPtr(deviceID)->GetMaxAlloc() / sizeof(complex);
+}
+
+void QEngineCUDA::ResizeZero(bitLenInt qb)
+{
+    b200sv_state* n = nullptr;
+    Check(b200sv_create((int)deviceID, (int)qb, kPrecision, &n));
+    if (sv) {
+        b200sv_destroy(sv);
+    }
+    sv = n;
+}
+
+/// QEngine::SetQubitCount is how QPager::MakeEngine (src/qpager.cpp:287-296) and QEngine::Decompose
+/// (qengine.hpp:287-293) size an EMPTY engine.  After Compose/Decompose the core already has the new width.
+void QEngineCUDA::SetQubitCount(bitLenInt qb)
+{
+    QEngine::SetQubitCount(qb);
+    if (svCountSynced) {
+        svCountSynced = false;
+        return;
+    }
+    int have = 0;
+    Check(b200sv_qubit_count(sv, &have));
+    if (have != (int)qb) {
+        ResizeZero(qb);
+    }
+}
+
+void QEngineCUDA::SyncQubitCount()
+{
+    int have = 0;
+    Check(b200sv_qubit_count(sv, &have));
+    svCountSynced = true;
+    SetQubitCount((bitLenInt)have);
+}
+
+void QEngineCUDA::Finish() { Check(b200sv_finish(sv)); }
+bool QEngineCUDA::isFinished()
+{
+    Check(b200sv_flush(sv));
+    return true;
+}
+
+// ---- page / buffer ops (reference state.cpp:66-185) -------------------------------------------------------------------
+
+void QEngineCUDA::ZeroAmplitudes()
+{
+    Check(b200sv_zero(sv));
+    runningNorm = ZERO_R1;
+}
+
+bool QEngineCUDA::IsZeroAmplitude()
+{
+    int z = 0;
+    Check(b200sv_is_zero(sv, &z));
+    return z != 0;
+}
+
+void QEngineCUDA::CopyStateVec(QEnginePtr src)
+{
+    if (qubitCount != src->GetQubitCount()) {
+        throw std::invalid_argument("QEngineCUDA::CopyStateVec argument size differs from this!");
+    }
+    if (src->IsZeroAmplitude()) {
+        return ZeroAmplitudes();
+    }
+    QEngineCUDAPtr c = std::dynamic_pointer_cast<QEngineCUDA>(src);
+    if (c) {
+        Check(b200sv_copy_state(sv, c->sv));
+    } else {
+        // e.g. QHybrid switching from QEngineCPU (src/qhybrid.cpp:45-57): stage through the host
+        std::unique_ptr<complex[]> tmp(new complex[maxQPowerOcl]);
+        src->GetQuantumState(tmp.get());
+        Check(b200sv_set_state(sv, tmp.get()));
+    }
+    runningNorm = (real1)src->GetRunningNorm();
+}
+
+void QEngineCUDA::GetAmplitudePage(complex* pagePtr, bitCapIntOcl offset, bitCapIntOcl length)
+{
+    if (isBadPermRange(offset, length, maxQPowerOcl)) {
+        throw std::invalid_argument("QEngineCUDA::GetAmplitudePage range is out-of-bounds!");
+    }
+    Check(b200sv_get_page(sv, pagePtr, offset, length));
+}
+
+void QEngineCUDA::SetAmplitudePage(const complex* pagePtr, bitCapIntOcl offset, bitCapIntOcl length)
+{
+    if (isBadPermRange(offset, length, maxQPowerOcl)) {
+        throw std::invalid_argument("QEngineCUDA::SetAmplitudePage range is out-of-bounds!");
+    }
+    Check(b200sv_set_page(sv, pagePtr, offset, length));
+    if (doNormalize) {
+        runningNorm = REAL1_DEFAULT_ARG;
+    }
+}
+
+void QEngineCUDA::SetAmplitudePage(QEnginePtr pageEnginePtr, bitCapIntOcl srcOffset, bitCapIntOcl dstOffset, bitCapIntOcl length)
+{
+    if (isBadPermRange(dstOffset, length, maxQPowerOcl)) {
+        throw std::invalid_argument("QEngineCUDA::SetAmplitudePage source range is out-of-bounds!");
+    }
+    QEngineCUDAPtr c = std::dynamic_pointer_cast<QEngineCUDA>(pageEnginePtr);
+    if (c) {
+        if (isBadPermRange(srcOffset, length, c->maxQPowerOcl)) {
+            throw std::invalid_argument("QEngineCUDA::SetAmplitudePage source range is out-of-bounds!");
+        }
+        Check(b200sv_copy_page(sv, c->sv, srcOffset, dstOffset, length));
+    } else {
+        std::unique_ptr<complex[]> tmp(new complex[length]);
+        pageEnginePtr->GetAmplitudePage(tmp.get(), srcOffset, length);
+        Check(b200sv_set_page(sv, tmp.get(), dstOffset, length));
+    }
+    runningNorm = REAL1_DEFAULT_ARG;
+}
+
+void QEngineCUDA::ShuffleBuffers(QEnginePtr engine)
+{
+    if (qubitCount != engine->GetQubitCount()) {
+        throw std::invalid_argument("QEngineCUDA::ShuffleBuffers argument size differs from this!");
+    }
+    QEngineCUDAPtr c = Cast(engine, "ShuffleBuffers");
+    Check(b200sv_shuffle(sv, c->sv));
+    runningNorm = REAL1_DEFAULT_ARG;
+    c->runningNorm = REAL1_DEFAULT_ARG;
+}
+
+QEnginePtr QEngineCUDA::CloneEmpty()
+{
+    // reference utility.cpp:36-44
+    QEngineCUDAPtr c = std::make_shared<QEngineCUDA>(0U, ZERO_BCI, rand_generator, ONE_CMPLX, doNormalize, randGlobalPhase,
+        useHostRam, deviceID, !hardware_rand_generator ? false : true, false, (real1_f)amplitudeFloor);
+    c->SetQubitCount(qubitCount);
+    return c;
+}
+
+QInterfacePtr QEngineCUDA::Clone()
+{
+    // reference utility.cpp:17-34
+    QEngineCUDAPtr c = std::dynamic_pointer_cast<QEngineCUDA>(CloneEmpty());
+    if (!IsZeroAmplitude()) {
+        Check(b200sv_copy_state(c->sv, sv));
+    }
+    c->runningNorm = runningNorm;
+    return c;
+}
+
+// ---- state access (reference state.cpp:187-351) -----------------------------------------------------------------------
+
+void QEngineCUDA::SetQuantumState(const complex* inputState)
+{
+    Check(b200sv_set_state(sv, inputState));
+    runningNorm = REAL1_DEFAULT_ARG;
+}
+
+void QEngineCUDA::GetQuantumState(complex* outputState)
+{
+    if (doNormalize) {
+        NormalizeState();
+    }
+    Check(b200sv_get_state(sv, outputState));
+}
+
+void QEngineCUDA::GetProbs(real1* outputProbs)
+{
+    if (doNormalize) {
+        NormalizeState();
+    }
+    Check(b200sv_get_probs(sv, outputProbs));
+}
+
+complex QEngineCUDA::GetAmplitude(const bitCapInt& perm)
+{
+    if (perm >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::GetAmplitude argument out-of-bounds!");
+    }
+    double re = 0, im = 0;
+    Check(b200sv_get_amplitude(sv, (uint64_t)(bitCapIntOcl)perm, &re, &im));
+    return complex((real1)re, (real1)im);
+}
+
+void QEngineCUDA::SetAmplitude(const bitCapInt& perm, const complex& amp)
+{
+    if (perm >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::SetAmplitude argument out-of-bounds!");
+    }
+    if (IsZeroAmplitude() && !norm(amp)) {
+        return;
+    }
+    if (runningNorm != REAL1_DEFAULT_ARG) {
+        runningNorm += norm(amp) - norm(GetAmplitude(perm));
+    }
+    Check(b200sv_set_amplitude(sv, (uint64_t)(bitCapIntOcl)perm, (double)real(amp), (double)imag(amp)));
+}
+
+void QEngineCUDA::SetPermutation(const bitCapInt& perm, const complex& phaseFac)
+{
+    // reference state.cpp:228-254
+    complex phase;
+    if (phaseFac == CMPLX_DEFAULT_ARG) {
+        if (randGlobalPhase) {
+            const real1_f angle = Rand() * 2 * (real1_f)PI_R1;
+            phase = complex((real1)cos(angle), (real1)sin(angle));
+        } else {
+            phase = ONE_CMPLX;
+        }
+    } else {
+        phase = phaseFac / (real1)abs(phaseFac);
+    }
+    Check(b200sv_set_permutation(sv, (uint64_t)(bitCapIntOcl)perm, (double)real(phase), (double)imag(phase)));
+    runningNorm = ONE_R1;
+}
+
+// ---- the gate hot path -----------------------------------------------------------------------------------------------
+
+void QEngineCUDA::Apply2x2(bitCapInt offset1, bitCapInt offset2, const complex* mtrx, bitLenInt bitCount,
+    bitCapInt const* qPowersSorted, bool doCalcNorm, real1_f nrm_thresh)
+{
+    // host part of QEngineCPU::Apply2x2, reference state.cpp:392-431 and :514-531
+    if (IsZeroAmplitude()) {
+        return;
+    }
+    if ((offset1 >= maxQPower) || (offset2 >= maxQPower)) {
+        throw std::invalid_argument(
+            "QEngineCUDA::Apply2x2 offset1 and offset2 parameters must be within allocated qubit bounds!");
+    }
+    uint64_t pows[64];
+    for (bitLenInt i = 0U; i < bitCount; ++i) {
+        if (qPowersSorted[i] >= maxQPower) {
+            throw std::invalid_argument(
+                "QEngineCUDA::Apply2x2 parameter qPowsSorted array values must be within allocated qubit bounds!");
+        }
+        if (i && (qPowersSorted[i - 1U] == qPowersSorted[i])) {
+            throw std::invalid_argument("QEngineCUDA::Apply2x2 parameter qPowSorted array values cannot be "
+                                        "duplicated (for control and target qubits)!");
+        }
+        pows[i] = (uint64_t)(bitCapIntOcl)qPowersSorted[i];
+    }
+    const bool doApplyNorm = doNormalize && (bitCount == 1U) && (runningNorm > ZERO_R1);
+    doCalcNorm &= doApplyNorm || (runningNorm <= ZERO_R1);
+    const real1 nrm = doApplyNorm ? ONE_R1 / (real1)sqrt(runningNorm) : ONE_R1;
+    if (doCalcNorm) {
+        runningNorm = ONE_R1;
+    }
+    const real1_f thresh = (nrm_thresh < ZERO_R1) ? (real1_f)amplitudeFloor : nrm_thresh;
+    double m8[8];
+    for (int k = 0; k < 4; ++k) {
+        m8[2 * k] = (double)real(mtrx[k]);
+        m8[2 * k + 1] = (double)imag(mtrx[k]);
+    }
+    double normOut = 0;
+    Check(b200sv_apply2x2(sv, (uint64_t)(bitCapIntOcl)offset1, (uint64_t)(bitCapIntOcl)offset2, m8, (int)bitCount, pows,
+        (double)nrm, doCalcNorm ? (double)thresh : 0.0, doCalcNorm ? &normOut : nullptr));
+    if (doApplyNorm) {
+        runningNorm = ONE_R1;
+    }
+    if (doCalcNorm) {
+        runningNorm = (real1)normOut;
+        if (runningNorm <= FP_NORM_EPSILON) {
+            ZeroAmplitudes();
+        }
+    }
+}
+
+void QEngineCUDA::ApplyM(const bitCapInt& regMask, const bitCapInt& result, const complex& nrm)
+{
+    if (IsZeroAmplitude()) {
+        return;
+    }
+    Check(b200sv_apply_m(sv, (uint64_t)(bitCapIntOcl)regMask, (uint64_t)(bitCapIntOcl)result, (double)real(nrm), (double)imag(nrm)));
+    runningNorm = ONE_R1;
+}
+
+void QEngineCUDA::XMask(const bitCapInt& mask)
+{
+    // reference state.cpp:965-1007
+    if (mask >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::XMask mask out-of-bounds!");
+    }
+    if (IsZeroAmplitude() || (bi_compare_0(mask) == 0)) {
+        return;
+    }
+    if (isPowerOfTwo(mask)) {
+        return X(log2(mask));
+    }
+    Check(b200sv_xmask(sv, (uint64_t)(bitCapIntOcl)mask));
+}
+
+void QEngineCUDA::PhaseParity(real1_f radians, const bitCapInt& mask)
+{
+    // reference state.cpp:1009-1054
+    if (mask >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::PhaseParity mask out-of-bounds!");
+    }
+    if (IsZeroAmplitude() || (bi_compare_0(mask) == 0)) {
+        return;
+    }
+    if (isPowerOfTwo(mask)) {
+        const complex phaseFac = std::polar(ONE_R1, (real1)(radians / 2));
+        return Phase(ONE_CMPLX / phaseFac, phaseFac, log2(mask));
+    }
+    Check(b200sv_phase_parity(sv, (double)radians, (uint64_t)(bitCapIntOcl)mask));
+}
+
+void QEngineCUDA::PhaseRootNMask(bitLenInt n, const bitCapInt& mask)
+{
+    // reference state.cpp:1056-1092
+    if (mask >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::PhaseRootNMask mask out-of-bounds!");
+    }
+    if (IsZeroAmplitude() || !n || (bi_compare_0(mask) == 0)) {
+        return;
+    }
+    if (n == 1U) {
+        return ZMask(mask);
+    }
+    const real1_f radians = -PI_R1 / pow2Ocl(n - 1U);
+    if (isPowerOfTwo(mask)) {
+        return Phase(ONE_CMPLX, std::polar(ONE_R1, (real1)radians), log2(mask));
+    }
+    Check(b200sv_phase_root_n_mask(sv, (int)n, (uint64_t)(bitCapIntOcl)mask));
+}
+
+void QEngineCUDA::UniformlyControlledSingleBit(const std::vector<bitLenInt>& controls, bitLenInt qubitIndex, const complex* mtrxs,
+    const std::vector<bitCapInt>& mtrxSkipPowers, const bitCapInt& mtrxSkipValueMask)
+{
+    // reference state.cpp:1094-1198
+    if (IsZeroAmplitude()) {
+        return;
+    }
+    if (controls.empty()) {
+        return Mtrx(mtrxs + ((bitCapIntOcl)mtrxSkipValueMask * 4U), qubitIndex);
+    }
+    if (qubitIndex >= qubitCount) {
+        throw std::invalid_argument("QEngineCUDA::UniformlyControlledSingleBit qubitIndex is out-of-bounds!");
+    }
+    ThrowIfQbIdArrayIsBad(controls, qubitCount, "QEngineCUDA::UniformlyControlledSingleBit control is out-of-bounds!");
+    std::vector<int> ctrl(controls.begin(), controls.end());
+    std::vector<uint64_t> skip(mtrxSkipPowers.size());
+    for (size_t i = 0; i < skip.size(); ++i) {
+        skip[i] = (uint64_t)(bitCapIntOcl)mtrxSkipPowers[i];
+    }
+    const size_t nMtrx = (size_t)4U << (controls.size() + mtrxSkipPowers.size());
+    std::vector<double> m(2U * nMtrx);
+    for (size_t i = 0; i < nMtrx; ++i) {
+        m[2 * i] = (double)real(mtrxs[i]);
+        m[2 * i + 1] = (double)imag(mtrxs[i]);
+    }
+    const real1 nrm = (runningNorm > ZERO_R1) ? ONE_R1 / (real1)sqrt(runningNorm) : ONE_R1;
+    const bool useNrm = doNormalize && ((ONE_R1 - nrm) > FP_NORM_EPSILON);
+    Check(b200sv_uniformly_controlled(sv, (int)ctrl.size(), ctrl.data(), (int)qubitIndex, m.data(), (int)skip.size(), skip.data(),
+        (uint64_t)(bitCapIntOcl)mtrxSkipValueMask, useNrm ? (double)nrm : 1.0));
+    if (doNormalize) {
+        runningNorm = ONE_R1;
+    }
+}
+
+void QEngineCUDA::UniformParityRZ(const bitCapInt& mask, real1_f angle)
+{
+    if (mask >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::UniformParityRZ mask out-of-bounds!");
+    }
+    if (IsZeroAmplitude()) {
+        return;
+    }
+    Check(b200sv_uniform_parity_rz(sv, 0U, (uint64_t)(bitCapIntOcl)mask, (double)angle));
+}
+
+void QEngineCUDA::CUniformParityRZ(const std::vector<bitLenInt>& controls, const bitCapInt& mask, real1_f angle)
+{
+    if (controls.empty()) {
+        return UniformParityRZ(mask, angle);
+    }
+    if (mask >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::CUniformParityRZ mask out-of-bounds!");
+    }
+    ThrowIfQbIdArrayIsBad(controls, qubitCount, "QEngineCUDA::CUniformParityRZ control is out-of-bounds!");
+    if (IsZeroAmplitude()) {
+        return;
+    }
+    uint64_t cm = 0;
+    for (const bitLenInt& c : controls) {
+        cm |= pow2Ocl(c);
+    }
+    Check(b200sv_uniform_parity_rz(sv, cm, (uint64_t)(bitCapIntOcl)mask, (double)angle));
+}
+
+// ---- probabilities / measurement (reference state.cpp:1751-2107) ---------------------------------------------------
+
+real1_f QEngineCUDA::Prob(bitLenInt qubit)
+{
+    if (qubit >= qubitCount) {
+        throw std::invalid_argument("QEngineCUDA::Prob qubit index parameter must be within allocated qubit bounds!");
+    }
+    if (doNormalize) {
+        NormalizeState();
+    }
+    if (IsZeroAmplitude()) {
+        return ZERO_R1_F;
+    }
+    double out = 0;
+    const uint64_t p = pow2Ocl(qubit);
+    Check(b200sv_prob_mask(sv, p, p, &out));
+    return clampProb((real1_f)(real1)out);
+}
+
+real1_f QEngineCUDA::CtrlOrAntiProb(bool controlState, bitLenInt control, bitLenInt target)
+{
+    if (IsZeroAmplitude()) {
+        return ZERO_R1_F;
+    }
+    real1_f controlProb = Prob(control);
+    if (!controlState) {
+        controlProb = ONE_R1 - controlProb;
+    }
+    if (controlProb <= FP_NORM_EPSILON) {
+        return ZERO_R1;
+    }
+    if ((ONE_R1 - controlProb) <= FP_NORM_EPSILON) {
+        return Prob(target);
+    }
+    if (target >= qubitCount) {
+        throw std::invalid_argument(
+            "QEngineCUDA::CtrlOrAntiProb target index parameter must be within allocated qubit bounds!");
+    }
+    double out = 0;
+    const uint64_t cp = pow2Ocl(control), tp = pow2Ocl(target);
+    Check(b200sv_prob_mask(sv, cp | tp, (controlState ? cp : 0U) | tp, &out));
+    return clampProb((real1_f)((real1)out / (real1)controlProb));
+}
+
+real1_f QEngineCUDA::ProbReg(bitLenInt start, bitLenInt length, const bitCapInt& permutation)
+{
+    if (doNormalize) {
+        NormalizeState();
+    }
+    if (IsZeroAmplitude()) {
+        return ZERO_R1_F;
+    }
+    double out = 0;
+    Check(b200sv_prob_mask(sv, bitRegMaskOcl(start, length), (uint64_t)(bitCapIntOcl)permutation << start, &out));
+    return clampProb((real1_f)(real1)out);
+}
+
+real1_f QEngineCUDA::ProbMask(const bitCapInt& mask, const bitCapInt& permutation)
+{
+    if (mask >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::ProbMask mask out-of-bounds!");
+    }
+    if (doNormalize) {
+        NormalizeState();
+    }
+    if (IsZeroAmplitude()) {
+        return ZERO_R1_F;
+    }
+    double out = 0;
+    Check(b200sv_prob_mask(sv, (uint64_t)(bitCapIntOcl)mask, (uint64_t)(bitCapIntOcl)permutation, &out));
+    return clampProb((real1_f)(real1)out);
+}
+
+void QEngineCUDA::ProbMaskAll(const bitCapInt& mask, real1* probsArray)
+{
+    if (mask >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::ProbMaskAll mask out-of-bounds!");
+    }
+    if (doNormalize) {
+        NormalizeState();
+    }
+    Check(b200sv_prob_mask_all(sv, (uint64_t)(bitCapIntOcl)mask, probsArray));
+}
+
+void QEngineCUDA::ProbRegAll(bitLenInt start, bitLenInt length, real1* probsArray)
+{
+    ProbMaskAll(bitCapInt(bitRegMaskOcl(start, length)), probsArray);
+}
+
+real1_f QEngineCUDA::ProbParity(const bitCapInt& mask)
+{
+    if (mask >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::ProbParity mask out-of-bounds!");
+    }
+    if (doNormalize) {
+        NormalizeState();
+    }
+    if (IsZeroAmplitude() || (bi_compare_0(mask) == 0)) {
+        return ZERO_R1_F;
+    }
+    double out = 0;
+    Check(b200sv_prob_parity(sv, (uint64_t)(bitCapIntOcl)mask, &out));
+    return clampProb((real1_f)(real1)out);
+}
+
+bool QEngineCUDA::ForceMParity(const bitCapInt& mask, bool result, bool doForce)
+{
+    if (mask >= maxQPower) {
+        throw std::invalid_argument("QEngineCUDA::ForceMParity mask out-of-bounds!");
+    }
+    if (IsZeroAmplitude() || (bi_compare_0(mask) == 0)) {
+        return false;
+    }
+    if (!doForce) {
+        result = (Rand() <= ProbParity(mask));
+    }
+    double kept = 0;
+    Check(b200sv_collapse_parity(sv, (uint64_t)(bitCapIntOcl)mask, result ? 1 : 0, &kept));
+    runningNorm = (real1)kept;
+    if (!doNormalize) {
+        NormalizeState();
+    }
+    return result;
+}
+
+bitCapInt QEngineCUDA::MAll()
+{
+    // QEngineCPU::MAll (state.cpp:2026-2050) with the cumulative search done on the device
+    const real1_f rnd = Rand();
+    if (doNormalize) {
+        NormalizeState();
+    }
+    uint64_t perm = 0;
+    Check(b200sv_sample(sv, (double)rnd, &perm));
+    SetPermutation(bitCapInt(perm));
+    return bitCapInt(perm);
+}
+
+real1_f QEngineCUDA::GetExpectation(bitLenInt valueStart, bitLenInt valueLength)
+{
+    double avg = 0, tot = 0;
+    Check(b200sv_expectation(sv, (int)valueStart, (int)valueLength, &avg));
+    Check(b200sv_norm(sv, 0.0, &tot));
+    return (tot > 0) ? (real1_f)(avg / tot) : (real1_f)avg;
+}
+
+// ---- structure (reference state.cpp:1271-1748, utility.cpp:54-68) --------------------------------------------------
+
+bitLenInt QEngineCUDA::Compose(QEngineCUDAPtr toCopy) { return Compose(toCopy, qubitCount); }
+
+bitLenInt QEngineCUDA::Compose(QEngineCUDAPtr toCopy, bitLenInt start)
+{
+    if (start > qubitCount) {
+        throw std::invalid_argument("QEngineCUDA::Compose start index is out-of-bounds!");
+    }
+    if (!toCopy->qubitCount) {
+        return start;
+    }
+    if (!qubitCount) {
+        // reference state.cpp:1286-1297
+        ResizeZero(toCopy->qubitCount);
+        QEngine::SetQubitCount(toCopy->qubitCount);
+        if (!toCopy->IsZeroAmplitude()) {
+            Check(b200sv_copy_state(sv, toCopy->sv));
+        }
+        runningNorm = toCopy->runningNorm;
+        return 0U;
+    }
+    if (doNormalize) {
+        NormalizeState();
+    }
+    if (toCopy->doNormalize) {
+        toCopy->NormalizeState();
+    }
+    Check(b200sv_compose(sv, toCopy->sv, (int)start));
+    SyncQubitCount();
+    if (IsZeroAmplitude()) {
+        runningNorm = ZERO_R1;
+    }
+    return start;
+}
+
+void QEngineCUDA::Decompose(bitLenInt start, QInterfacePtr destination)
+{
+    QEngineCUDAPtr dest = Cast(destination, "Decompose");
+    const bitLenInt length = dest->GetQubitCount();
+    if (isBadBitRange(start, length, qubitCount)) {
+        throw std::invalid_argument("QEngineCUDA::DecomposeDispose range is out-of-bounds!");
+    }
+    if (!length) {
+        return;
+    }
+    if (doNormalize) {
+        NormalizeState();
+    }
+    Check(b200sv_decompose(sv, (int)start, (int)length, dest->sv));
+    SyncQubitCount();
+    dest->runningNorm = dest->IsZeroAmplitude() ? ZERO_R1 : ONE_R1;
+}
+
+void QEngineCUDA::Dispose(bitLenInt start, bitLenInt length)
+{
+    if (isBadBitRange(start, length, qubitCount)) {
+        throw std::invalid_argument("QEngineCUDA::DecomposeDispose range is out-of-bounds!");
+    }
+    if (!length) {
+        return;
+    }
+    if (doNormalize) {
+        NormalizeState();
+    }
+    Check(b200sv_decompose(sv, (int)start, (int)length, nullptr));
+    SyncQubitCount();
+}
+
+void QEngineCUDA::Dispose(bitLenInt start, bitLenInt length, const bitCapInt& disposedPerm)
+{
+    if (isBadBitRange(start, length, qubitCount)) {
+        throw std::invalid_argument("QEngineCUDA::Dispose range is out-of-bounds!");
+    }
+    if (!length) {
+        return;
+    }
+    if (doNormalize) {
+        NormalizeState();
+    }
+    Check(b200sv_dispose_perm(sv, (int)start, (int)length, (uint64_t)(bitCapIntOcl)disposedPerm));
+    SyncQubitCount();
+}
+
+bitLenInt QEngineCUDA::Allocate(bitLenInt start, bitLenInt length)
+{
+    if (start > qubitCount) {
+        throw std::invalid_argument("QEngineCUDA::Allocate argument is out-of-bounds!");
+    }
+    if (!length) {
+        return start;
+    }
+    QEngineCUDAPtr nQubits = std::make_shared<QEngineCUDA>(length, ZERO_BCI, rand_generator, ONE_CMPLX, doNormalize,
+        randGlobalPhase, useHostRam, deviceID, !hardware_rand_generator ? false : true, false, (real1_f)amplitudeFloor);
+    return Compose(nQubits, start);
+}
+
+// ---- norm (reference state.cpp:2109-2268) ------------------------------------------------------------------------------
+
+real1_f QEngineCUDA::SumSqrDiff(QInterfacePtr toCompare)
+{
+    if (!toCompare) {
+        return ONE_R1_F;
+    }
+    if (this == toCompare.get()) {
+        return ZERO_R1_F;
+    }
+    if (qubitCount != toCompare->GetQubitCount()) {
+        return ONE_R1_F;
+    }
+    QEngineCUDAPtr o = Cast(toCompare, "SumSqrDiff");
+    if (doNormalize) {
+        NormalizeState();
+    }
+    if (o->doNormalize) {
+        o->NormalizeState();
+    }
+    if (IsZeroAmplitude() && o->IsZeroAmplitude()) {
+        return ZERO_R1_F;
+    }
+    if (IsZeroAmplitude()) {
+        o->UpdateRunningNorm();
+        return (real1_f)o->runningNorm;
+    }
+    if (o->IsZeroAmplitude()) {
+        UpdateRunningNorm();
+        return (real1_f)runningNorm;
+    }
+    double re = 0, im = 0;
+    Check(b200sv_inner(sv, o->sv, &re, &im));
+    return ONE_R1_F - clampProb((real1_f)norm(complex((real1)re, (real1)im)));
+}
+
+void QEngineCUDA::NormalizeState(real1_f nrm_f, real1_f norm_thresh_f, real1_f phaseArg)
+{
+    if (IsZeroAmplitude()) {
+        return;
+    }
+    if ((runningNorm == REAL1_DEFAULT_ARG) && (nrm_f == REAL1_DEFAULT_ARG)) {
+        UpdateRunningNorm();
+    }
+    real1 nrm = (real1)nrm_f;
+    real1 norm_thresh = (real1)norm_thresh_f;
+    if (nrm < ZERO_R1) {
+        nrm = runningNorm;
+    }
+    if (nrm <= FP_NORM_EPSILON) {
+        return ZeroAmplitudes();
+    }
+    if ((abs(ONE_R1 - nrm) <= FP_NORM_EPSILON) && ((phaseArg * phaseArg) <= FP_NORM_EPSILON)) {
+        return;
+    }
+    if (norm_thresh < ZERO_R1) {
+        norm_thresh = amplitudeFloor;
+    }
+    Check(b200sv_normalize(sv, (double)nrm, (double)norm_thresh, (double)phaseArg));
+    runningNorm = ONE_R1;
+}
+
+void QEngineCUDA::UpdateRunningNorm(real1_f norm_thresh)
+{
+    if (IsZeroAmplitude()) {
+        runningNorm = ZERO_R1;
+        return;
+    }
+    if (norm_thresh < ZERO_R1) {
+        norm_thresh = (real1_f)amplitudeFloor;
+    }
+    double out = 0;
+    Check(b200sv_norm(sv, (double)norm_thresh, &out));
+    runningNorm = (real1)out;
+    if (runningNorm <= FP_NORM_EPSILON) {
+        ZeroAmplitudes();
+    }
+}
+
+// ---- QAlu: host round trip through the reference's own QEngineCPU (out of the hot path) -------------------------------
+
+// QEngineCPU keeps INCDECSC protected; expose it for the round trip
+struct CpuAlu : public QEngineCPU {
+    using QEngineCPU::QEngineCPU;
+#if ENABLE_ALU
+    using QEngineCPU::INCDECSC;
+#endif
+};
+
+void QEngineCUDA::ViaCpu(CpuFn fn)
+{
+    if (IsZeroAmplitude()) {
+        return;
+    }
+    QInterfacePtr cpu = std::make_shared<CpuAlu>(qubitCount, ZERO_BCI, rand_generator, ONE_CMPLX, doNormalize,
+        randGlobalPhase, false, -1, !hardware_rand_generator ? false : true, false, (real1_f)amplitudeFloor);
+    std::unique_ptr<complex[]> tmp(new complex[maxQPowerOcl]);
+    GetQuantumState(tmp.get());
+    cpu->SetQuantumState(tmp.get());
+    fn(cpu);
+    cpu->GetQuantumState(tmp.get());
+    SetQuantumState(tmp.get());
+}
+
+#if ENABLE_ALU
+#define VIA_ALU(call) ViaCpu([&](QInterfacePtr q) { std::dynamic_pointer_cast<CpuAlu>(q)->call; })
+void QEngineCUDA::PhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length)
+{
+    VIA_ALU(PhaseFlipIfLess(greaterPerm, start, length));
+}
+void QEngineCUDA::CPhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length, bitLenInt flagIndex)
+{
+    VIA_ALU(CPhaseFlipIfLess(greaterPerm, start, length, flagIndex));
+}
+void QEngineCUDA::INCDECSC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt carryIndex)
+{
+    VIA_ALU(INCDECSC(toMod, start, length, carryIndex));
+}
+void QEngineCUDA::INCDECSC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt overflowIndex, bitLenInt carryIndex)
+{
+    VIA_ALU(INCDECSC(toMod, start, length, overflowIndex, carryIndex));
+}
+void QEngineCUDA::MUL(const bitCapInt& toMul, bitLenInt start, bitLenInt carryStart, bitLenInt length)
+{
+    VIA_ALU(MUL(toMul, start, carryStart, length));
+}
+void QEngineCUDA::DIV(const bitCapInt& toDiv, bitLenInt start, bitLenInt carryStart, bitLenInt length)
+{
+    VIA_ALU(DIV(toDiv, start, carryStart, length));
+}
+void QEngineCUDA::POWModNOut(const bitCapInt& base, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length)
+{
+    VIA_ALU(POWModNOut(base, modN, inStart, outStart, length));
+}
+void QEngineCUDA::CMUL(const bitCapInt& toMul, bitLenInt start, bitLenInt carryStart, bitLenInt length,
+    const std::vector<bitLenInt>& controls)
+{
+    VIA_ALU(CMUL(toMul, start, carryStart, length, controls));
+}
+void QEngineCUDA::CDIV(const bitCapInt& toDiv, bitLenInt start, bitLenInt carryStart, bitLenInt length,
+    const std::vector<bitLenInt>& controls)
+{
+    VIA_ALU(CDIV(toDiv, start, carryStart, length, controls));
+}
+void QEngineCUDA::CPOWModNOut(const bitCapInt& base, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart,
+    bitLenInt length, const std::vector<bitLenInt>& controls)
+{
+    VIA_ALU(CPOWModNOut(base, modN, inStart, outStart, length, controls));
+}
+bitCapInt QEngineCUDA::IndexedLDA(bitLenInt indexStart, bitLenInt indexLength, bitLenInt valueStart, bitLenInt valueLength,
+    const unsigned char* values, bool resetValue)
+{
+    bitCapInt r = ZERO_BCI;
+    ViaCpu([&](QInterfacePtr q) {
+        r = std::dynamic_pointer_cast<CpuAlu>(q)->IndexedLDA(indexStart, indexLength, valueStart, valueLength, values, resetValue);
+    });
+    return r;
+}
+bitCapInt QEngineCUDA::IndexedADC(bitLenInt indexStart, bitLenInt indexLength, bitLenInt valueStart, bitLenInt valueLength,
+    bitLenInt carryIndex, const unsigned char* values)
+{
+    bitCapInt r = ZERO_BCI;
+    ViaCpu([&](QInterfacePtr q) {
+        r = std::dynamic_pointer_cast<CpuAlu>(q)->IndexedADC(indexStart, indexLength, valueStart, valueLength, carryIndex, values);
+    });
+    return r;
+}
+bitCapInt QEngineCUDA::IndexedSBC(bitLenInt indexStart, bitLenInt indexLength, bitLenInt valueStart, bitLenInt valueLength,
+    bitLenInt carryIndex, const unsigned char* values)
+{
+    bitCapInt r = ZERO_BCI;
+    ViaCpu([&](QInterfacePtr q) {
+        r = std::dynamic_pointer_cast<CpuAlu>(q)->IndexedSBC(indexStart, indexLength, valueStart, valueLength, carryIndex, values);
+    });
+    return r;
+}
+void QEngineCUDA::Hash(bitLenInt start, bitLenInt length, const unsigned char* values) { VIA_ALU(Hash(start, length, values)); }
+#undef VIA_ALU
+#endif
+
+} // namespace Qrack

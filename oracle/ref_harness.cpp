@@ -39,6 +39,19 @@ static QInterfacePtr make_reg(bitLenInt n, uint64_t perm)
         const int qpp = atoi(g_engine.c_str() + 6);
         q = CreateQuantumInterface({ QINTERFACE_QPAGER, QINTERFACE_CPU }, n, ZERO_BCI, rng, ONE_CMPLX, false, false,
             false, -1, false, false, REAL1_EPSILON, std::vector<int64_t>{}, (bitLenInt)qpp);
+#if ENABLE_CUDA
+    } else if (g_engine == "cuda") {
+        // the QEngineCUDA slot (dropin/): same factory call, different enum
+        q = CreateQuantumInterface(QINTERFACE_CUDA, n, ZERO_BCI, rng, ONE_CMPLX, false, false, false, -1, false);
+    } else if (g_engine.rfind("pager-cuda:", 0) == 0) {
+        const int qpp = atoi(g_engine.c_str() + 11);
+        q = CreateQuantumInterface({ QINTERFACE_QPAGER, QINTERFACE_CUDA }, n, ZERO_BCI, rng, ONE_CMPLX, false, false,
+            false, -1, false, false, REAL1_EPSILON, std::vector<int64_t>{}, (bitLenInt)qpp);
+    } else if (g_engine == "hybrid") {
+        q = CreateQuantumInterface(QINTERFACE_HYBRID, n, ZERO_BCI, rng, ONE_CMPLX, false, false, false, -1, false);
+    } else if (g_engine == "qunit-cuda") {
+        q = CreateQuantumInterface({ QINTERFACE_QUNIT, QINTERFACE_CUDA }, n, ZERO_BCI, rng, ONE_CMPLX, false, false, false, -1, false);
+#endif
     } else {
         q = CreateQuantumInterface(QINTERFACE_CPU, n, ZERO_BCI, rng, ONE_CMPLX, false, false, false, -1, false);
     }

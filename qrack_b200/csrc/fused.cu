@@ -30,20 +30,36 @@ constexpr int MAX_OPS = 96;
 constexpr int MAX_NCH = 16; // register chunks per sub-block (RB <= 4)
 constexpr int MAX_NA = 32;  // register amplitudes per sub-block
 
-// device op codes: kind * 5 + jr (dense, so the dispatch compiles to a jump table); bit 8 = has a sub-block predicate
+// device op codes.  Single-gate ops: kind * 5 + jr (jr = register-bit index of the target).  Bundles: K_LAYER (several
+// uncontrolled non-diagonal 1-qubit gates on distinct register bits) and K_PHGROUP (any number of diagonal gates whose
+// predicate touches at most one register bit).  bit 8 = has a sub-block predicate; bits 16..31 = payload offset (16-B units).
 enum { K_HAD = 0, K_XSWAP = 1, K_GEN_U = 2, K_GEN_P = 3, K_PHREG1 = 4, K_PHUNI = 5, K_PHGEN = 6 };
+constexpr uint32_t OPC_LAYER = 40U;
+constexpr uint32_t OPC_SCALE = 41U; // multiply every amplitude by the per-tile scalar (outer phases x Hadamard scale)
 constexpr uint32_t CODE_HAS_SB = 0x100U;
 // host (scheduler) op kinds
 enum { OP_GENERAL = 0, OP_HAD = 1, OP_XSWAP = 2, OP_PHASE = 3 };
 
-template <typename R> struct DevOp {
+template <typename R> struct alignas(16) DevOp {
     uint64_t omask, oval; // predicate on the tile's global base index (qubits outside the tile)
     // --- one 16-byte group, fetched with a single LDS.128 ---
-    uint32_t code;    // kind * 5 + jr [| CODE_HAS_SB]
-    uint32_t emask;   // bit e set: register amplitude e satisfies the register-resident part of the controls
+    uint32_t code;    // opcode | CODE_HAS_SB
+    uint32_t emask;   // single ops: bit e set = register amplitude e satisfies the register-resident controls
+                      // OPC_LAYER: mask of register bits that get a Hadamard butterfly
     uint32_t lmaskSb; // predicate on the sub-block base (tile-local amplitude bits outside the register set)
     uint32_t lvalSb;
-    R m[8];
+    R m[8];           // inline, so that its loads do not wait for the header
+};
+// member of a K_PHGROUP: predicate on the sub-block base only (tile-local bits outside the register set)
+template <typename R> struct DevPhaseMember;
+template <> struct DevPhaseMember<float> { // 16 bytes
+    uint32_t lmaskSb, lvalSb;
+    float ph[2];
+};
+template <> struct DevPhaseMember<double> { // 32 bytes
+    uint32_t lmaskSb, lvalSb;
+    double ph[2];
+    double pad;
 };
 
 struct DevPass {
@@ -55,14 +71,18 @@ struct DevPass {
     unsigned short itoffC[16];     // iteration -> chunk-index contribution of the sub-block bits above the thread id
 };
 
-struct DevSweep {
+struct alignas(16) DevSweep {
     int nHigh;      // high qubits in the tile
     int lowAmpBits; // L: low qubits in the tile
     int kc;         // tile chunk bits actually used (<= KC)
     int nPass;
     int nOps;
     int hasScale;
-    double scale;   // deferred scalar of the un-normalised Hadamard butterflies, applied once in the last pass
+    double scale;
+    int poolOff;  // byte offset of the payload pool from the start of the program
+    int nOuter;   // outer-only phases (DevOuterPhase records at outerOff)
+    int outerOff;
+    int pad2;   // deferred scalar of the un-normalised Hadamard butterflies, applied once in the last pass
     uint64_t highLow[MAX_HIGH]; // (2^q - 1) for push_apart of the tile base, ascending
     uint64_t highPow[MAX_HIGH]; // 2^q
     DevPass pass[MAX_PASS];
@@ -137,6 +157,13 @@ template <> struct AmpOps<float> {
         y = f2fma(y, pk(-2.0f, -2.0f), x);
     }
     static __device__ __forceinline__ A scale(A a, float s) { return f2mul(a, pk(s, s)); }
+    static __device__ __forceinline__ A unit() { return pk(1.0f, 0.0f); }
+    static __device__ __forceinline__ Ph toph(A a)
+    {
+        float x, y;
+        asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+        return mkph(x, y);
+    }
     static __device__ __forceinline__ void get(const Chunk& c, A* a)
     {
         a[0] = c.x;
@@ -171,6 +198,8 @@ template <> struct AmpOps<double> {
         y.y = fma(y.y, -2.0, x.y);
     }
     static __device__ __forceinline__ A scale(A a, double s) { return make_double2(a.x * s, a.y * s); }
+    static __device__ __forceinline__ A unit() { return make_double2(1.0, 0.0); }
+    static __device__ __forceinline__ Ph toph(A a) { return Ph{ a.x, a.y }; }
     static __device__ __forceinline__ void get(const Chunk& c, A* a) { a[0] = c; }
     static __device__ __forceinline__ Chunk put(const A* a) { return a[0]; }
 };
@@ -237,10 +266,12 @@ __device__ __forceinline__ void app_phase_reg(typename AmpOps<R>::A (&a)[NA], co
 }
 
 template <typename R, int NA>
-__device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const DevOp<R>& op, uint32_t xsb)
+__device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const DevOp<R>& op, uint32_t xsb, const R* __restrict__ tileScale)
 {
     typedef AmpOps<R> O;
+    typedef typename O::A A;
     const uint4 hd = *reinterpret_cast<const uint4*>(&op.code);
+    const R* m = op.m;
     bool tp = true;
     if (hd.x & CODE_HAS_SB) {
         tp = (xsb & hd.z) == hd.w;
@@ -248,24 +279,44 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
     const uint32_t em = tp ? hd.y : 0U;
 #define SV_J(J) (((1 << (J)) < NA) ? (J) : 0)
 #define SV_CASES(J)                                                                                                    \
-    case K_HAD * 5 + J:                                                                                             \
+    case K_HAD * 5 + J:                                                                                                \
         app_had<R, SV_J(J), NA>(a);                                                                                    \
         break;                                                                                                         \
-    case K_XSWAP * 5 + J:                                                                                           \
+    case K_XSWAP * 5 + J:                                                                                              \
         app_xswap<R, SV_J(J), NA>(a, em);                                                                              \
         break;                                                                                                         \
-    case K_GEN_U * 5 + J:                                                                                           \
-        app_general<R, SV_J(J), NA, false>(a, op.m, em);                                                               \
+    case K_GEN_U * 5 + J:                                                                                              \
+        app_general<R, SV_J(J), NA, false>(a, m, em);                                                                  \
         break;                                                                                                         \
-    case K_GEN_P * 5 + J:                                                                                           \
-        app_general<R, SV_J(J), NA, true>(a, op.m, em);                                                                \
+    case K_GEN_P * 5 + J:                                                                                              \
+        app_general<R, SV_J(J), NA, true>(a, m, em);                                                                   \
         break;                                                                                                         \
-    case K_PHREG1 * 5 + J:                                                                                          \
+    case K_PHREG1 * 5 + J:                                                                                             \
         if (tp) {                                                                                                      \
-            app_phase_reg<R, SV_J(J), NA>(a, O::mkph(op.m[0], op.m[1]));                                               \
+            app_phase_reg<R, SV_J(J), NA>(a, O::mkph(m[0], m[1]));                                                     \
         }                                                                                                              \
         break;
     switch (hd.x & 0xffU) {
+    case OPC_LAYER: {
+        // Hadamard butterflies on several register bits in one dispatch (hd.y = mask of register bits)
+#define SV_LAYER_BIT(J)                                                                                                \
+    if (((1 << (J)) < NA) && ((hd.y >> (J)) & 1U)) {                                                                   \
+        app_had<R, SV_J(J), NA>(a);                                                                                    \
+    }
+        SV_LAYER_BIT(0)
+        SV_LAYER_BIT(1)
+        SV_LAYER_BIT(2)
+        SV_LAYER_BIT(3)
+        SV_LAYER_BIT(4)
+#undef SV_LAYER_BIT
+    } break;
+    case OPC_SCALE: {
+        const typename O::Ph sc = O::mkph(tileScale[0], tileScale[1]);
+#pragma unroll
+        for (int e = 0; e < NA; ++e) {
+            a[e] = O::mulc(a[e], sc);
+        }
+    } break;
         SV_CASES(0)
         SV_CASES(1)
         SV_CASES(2)
@@ -273,7 +324,7 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         SV_CASES(4)
     case K_PHUNI * 5:
         if (tp) {
-            const typename O::Ph ph = O::mkph(op.m[0], op.m[1]);
+            const typename O::Ph ph = O::mkph(m[0], m[1]);
 #pragma unroll
             for (int e = 0; e < NA; ++e) {
                 a[e] = O::mulc(a[e], ph);
@@ -281,10 +332,10 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         }
         break;
     case K_PHGEN * 5: {
-        const typename O::Ph ph = O::mkph(op.m[0], op.m[1]);
+        const typename O::Ph ph = O::mkph(m[0], m[1]);
 #pragma unroll
         for (int e = 0; e < NA; ++e) {
-            const typename O::A v = O::mulc(a[e], ph);
+            const A v = O::mulc(a[e], ph);
             a[e] = ((em >> e) & 1U) ? v : a[e];
         }
     } break;
@@ -294,6 +345,14 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
 #undef SV_CASES
 #undef SV_J
 }
+
+// outer-only diagonal gate (every qubit of its predicate lies outside the tile): uniform per tile, folded into one
+// per-tile complex scalar that is applied together with the deferred Hadamard scale in the last pass
+template <typename R> struct DevOuterPhase {
+    uint64_t omask, oval;
+    R ph[2];
+    R pad[(sizeof(R) == 4) ? 2 : 2];
+};
 
 template <typename R, int KC, int RB, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
@@ -307,13 +366,13 @@ __global__ void __launch_bounds__(NT, MINB)
     constexpr int NCH = 1 << RB;
     constexpr int NA = NCH * APC;
     static_assert(NA <= MAX_NA && NCH <= MAX_NCH, "register sub-block too large");
+    static_assert(NT >= 128, "the per-tile preamble uses warps 0..3");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* tileB = smem;
-    uint4* tile = reinterpret_cast<uint4*>(smem);
     unsigned char* sprog = smem + ((size_t)16 << KC);
-    __shared__ uint64_t rowOff[1 << MAX_HIGH];
-    __shared__ uint32_t activeW[4];
     __shared__ uint64_t uOff[(1 << KC) / NT];
+    __shared__ uint32_t ballots[4];
+    __shared__ R tileScale[2];
 
     const int tid = threadIdx.x;
     for (uint32_t i = tid; i < progBytes / 16; i += NT) {
@@ -326,7 +385,9 @@ __global__ void __launch_bounds__(NT, MINB)
     const uint32_t nChunk = 1U << kc;
     const int lcb = sw.lowAmpBits - (APC == 2 ? 1 : 0); // low (contiguous) chunk bits
     const uint32_t colMask = (1U << lcb) - 1U;
-    // global amplitude offset of each chunk row (depends only on the sweep's high qubits)
+    // global amplitude offset of each chunk row (depends only on the sweep's high qubits); the tile area is free
+    // scratch until the first load
+    uint64_t* rowOff = reinterpret_cast<uint64_t*>(smem);
     for (uint32_t r = tid; r < (nChunk >> lcb); r += NT) {
         uint64_t off = 0;
         for (int h = 0; h < sw.nHigh; ++h) {
@@ -350,8 +411,9 @@ __global__ void __launch_bounds__(NT, MINB)
     unsigned char* const tSlot = tileB + ((size_t)swz((uint32_t)tid) << 4);
     __syncthreads();
     const uint32_t nSub = nChunk >> RB;
-    const R fscale = (R)sw.scale;
     const int nOps = sw.nOps;
+    const int nOuter = sw.nOuter;
+    const DevOuterPhase<R>* outer = reinterpret_cast<const DevOuterPhase<R>*>(sprog + sw.outerOff);
 
     for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
         uint64_t base = t << sw.lowAmpBits;
@@ -359,12 +421,36 @@ __global__ void __launch_bounds__(NT, MINB)
             const uint64_t lo = base & sw.highLow[h];
             base = ((base ^ lo) << 1) | lo;
         }
-        // which ops act on this tile at all (predicates on qubits outside the tile are uniform per tile)
-        if (tid < 128) {
-            const bool act = (tid < nOps) && ((base & ops[tid < nOps ? tid : 0].omask) == ops[tid < nOps ? tid : 0].oval);
+        // ---- per-tile preamble (consumed after the load's barrier) -----------------------------------------------
+        // warps 0..2: which ops act on this tile (predicates on qubits outside the tile are uniform per tile)
+        // warp 3   : product of the outer-only phases that fire for this tile, times the deferred Hadamard scale
+        if (tid < 96) {
+            const DevOp<R>& aop = ops[tid < nOps ? tid : 0];
+            const bool act = (tid < nOps) && ((base & aop.omask) == aop.oval);
             const uint32_t bal = __ballot_sync(0xffffffffU, act);
             if ((tid & 31) == 0) {
-                activeW[tid >> 5] = bal;
+                ballots[tid >> 5] = bal;
+            }
+        } else if (tid < 128) {
+            R fx = (R)1, fy = (R)0;
+            for (int i = tid - 96; i < nOuter; i += 32) {
+                const DevOuterPhase<R>& op = outer[i];
+                if ((base & op.omask) == op.oval) {
+                    const R nx = fx * op.ph[0] - fy * op.ph[1];
+                    fy = fx * op.ph[1] + fy * op.ph[0];
+                    fx = nx;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const R ox = __shfl_xor_sync(0xffffffffU, fx, d), oy = __shfl_xor_sync(0xffffffffU, fy, d);
+                const R nx = fx * ox - fy * oy;
+                fy = fx * oy + fy * ox;
+                fx = nx;
+            }
+            if (tid == 96) {
+                tileScale[0] = fx * (R)sw.scale;
+                tileScale[1] = fy * (R)sw.scale;
             }
         }
         // ---- load: global -> swizzled smem ----------------------------------------------------------------------
@@ -406,18 +492,17 @@ __global__ void __launch_bounds__(NT, MINB)
                     dep |= ((tid >> i) & 1U) << ps.sbit[i];
                 }
             }
-            // active ops of this pass as (up to 4) 32-bit words
-            uint32_t pm[4];
+            // active ops of this pass as (up to 3) 32-bit words
+            uint32_t pm[3];
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < 3; ++w) {
                 const int lo = ps.opBegin - 32 * w, hi = ps.opEnd - 32 * w;
-                uint32_t m = activeW[w];
+                uint32_t m = ballots[w];
                 m = (lo > 0) ? ((lo >= 32) ? 0U : (m & (0xffffffffU << lo))) : m;
                 m = (hi < 32) ? ((hi <= 0) ? 0U : (m & (0xffffffffU >> (32 - hi)))) : m;
                 pm[w] = m;
             }
             const int wBegin = ps.opBegin >> 5, wEnd = (ps.opEnd > ps.opBegin) ? ((ps.opEnd - 1) >> 5) : (wBegin - 1);
-            const bool lastPass = (p == sw.nPass - 1) && sw.hasScale;
             for (int it = 0; it < ps.nIt; ++it) {
                 if ((uint32_t)(it * NT + tid) >= nSub) {
                     break;
@@ -433,17 +518,11 @@ __global__ void __launch_bounds__(NT, MINB)
                 const uint32_t xsb = sbc * APC;
 #pragma unroll 1
                 for (int w = wBegin; w <= wEnd; ++w) {
-                    uint32_t m = (w == 0) ? pm[0] : ((w == 1) ? pm[1] : ((w == 2) ? pm[2] : pm[3]));
+                    uint32_t m = (w == 0) ? pm[0] : ((w == 1) ? pm[1] : pm[2]);
                     while (m) {
                         const int o = 32 * w + __ffs(m) - 1;
                         m &= m - 1U;
-                        exec_op<R, NA>(a, ops[o], xsb);
-                    }
-                }
-                if (lastPass) {
-#pragma unroll
-                    for (int e = 0; e < NA; ++e) {
-                        a[e] = O::scale(a[e], fscale);
+                        exec_op<R, NA>(a, ops[o], xsb, tileScale);
                     }
                 }
 #pragma unroll
@@ -541,6 +620,7 @@ struct TileCfg {
     int H;    // capacity of high qubits
     int NT;   // threads per CTA
     int maxOps; // ops per sweep (bounded by the shared-memory program area: 3 CTAs/SM must fit)
+    int bundle; // bit 0: LAYER bundles, bit 1: PHGROUP bundles
 };
 
 static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref, int NT = 256)
@@ -558,7 +638,8 @@ static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref, int NT = 256
         c.L = c.kA; // whole state is one tile
     }
     c.H = c.kA - c.L;
-    c.maxOps = (prec == 32) ? MAX_OPS : (MAX_OPS * 2) / 3;
+    c.maxOps = MAX_OPS;
+    c.bundle = 3;
     return c;
 }
 
@@ -681,34 +762,44 @@ static int tile_bit(const TileCfg& cfg, const std::vector<int>& highQ, int q)
     return -1;
 }
 
+// Encoded size limits of one sweep program (must fit beside the tile in shared memory with 3 CTAs/SM)
+constexpr size_t MAX_PROG_BYTES = 7168;
+
 template <typename R> static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<unsigned char>& buf)
 {
-    const size_t start = buf.size();
-    const size_t bytes = ((sizeof(DevSweep) + sp.nOps * sizeof(DevOp<R>)) + 15U) & ~(size_t)15U;
-    buf.resize(start + bytes, 0);
-    DevSweep* ds = reinterpret_cast<DevSweep*>(buf.data() + start);
-    DevOp<R>* dops = reinterpret_cast<DevOp<R>*>(buf.data() + start + sizeof(DevSweep));
-    ds->nHigh = (int)sp.highQ.size();
-    ds->lowAmpBits = cfg.L;
-    ds->kc = cfg.kA - cfg.apcLog;
-    ds->nPass = (int)sp.passes.size();
-    ds->nOps = (int)sp.nOps;
-    uint64_t tileMask = bitq(cfg.L) - 1U;
-    for (int h = 0; h < ds->nHigh; ++h) {
-        ds->highLow[h] = bitq(sp.highQ[h]) - 1U;
-        ds->highPow[h] = bitq(sp.highQ[h]);
-        tileMask |= bitq(sp.highQ[h]);
-    }
-    const int kc = ds->kc;
+    const int kc = cfg.kA - cfg.apcLog;
     const int APC = 1 << cfg.apcLog;
     const int NCH = 1 << cfg.RB;
     const int NA = NCH * APC;
     const int NT = cfg.NT;
+    int JRN = 0;
+    while ((1 << JRN) < NA) {
+        ++JRN;
+    }
+    DevSweep ds;
+    memset(&ds, 0, sizeof(ds));
+    std::vector<DevOp<R>> dops;
+    std::vector<unsigned char> pool;
+    std::vector<DevOuterPhase<R>> outerList;
+    auto pool_alloc = [&](size_t bytes) {
+        const size_t off = pool.size();
+        pool.resize(off + ((bytes + 15U) & ~(size_t)15U), 0);
+        return off;
+    };
+    ds.nHigh = (int)sp.highQ.size();
+    ds.lowAmpBits = cfg.L;
+    ds.kc = kc;
+    ds.nPass = (int)sp.passes.size();
+    uint64_t tileMask = bitq(cfg.L) - 1U;
+    for (int h = 0; h < ds.nHigh; ++h) {
+        ds.highLow[h] = bitq(sp.highQ[h]) - 1U;
+        ds.highPow[h] = bitq(sp.highQ[h]);
+        tileMask |= bitq(sp.highQ[h]);
+    }
     double scale = 1.0;
-    int o = 0;
-    for (int p = 0; p < ds->nPass; ++p) {
+    for (int p = 0; p < ds.nPass; ++p) {
         const PassPlan& pp = sp.passes[p];
-        DevPass& dp = ds->pass[p];
+        DevPass& dp = ds.pass[p];
         // register chunk bits: targets first, then fill from the top with unused chunk bits
         std::vector<int> rb;
         uint32_t used = 0;
@@ -780,13 +871,19 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
             }
         }
         const uint32_t fullE = (NA >= 32) ? 0xffffffffU : ((1U << NA) - 1U);
-        dp.opBegin = o;
-        for (const HostOp& hop : pp.ops) {
-            DevOp<R>& d = dops[o++];
-            d.omask = hop.cmask & ~tileMask;
-            d.oval = hop.cval & ~tileMask;
-            // tile-local predicate
-            uint32_t lmask = 0, lval = 0;
+        auto reg_index = [&](int tb) {
+            int jr = 0;
+            for (int b = 0; b < tb; ++b) {
+                if (regAmpMask & (1U << b)) {
+                    ++jr;
+                }
+            }
+            return jr;
+        };
+        // tile-local predicate of a host op: (lmask, lval) over tile amplitude bits
+        auto local_pred = [&](const HostOp& hop, uint32_t& lmask, uint32_t& lval) {
+            lmask = 0;
+            lval = 0;
             for (uint64_t m = hop.cmask & tileMask; m; m &= m - 1U) {
                 const int q = __builtin_ctzll(m);
                 const int tb = tile_bit(cfg, sp.highQ, q);
@@ -795,9 +892,105 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
                     lval |= 1U << tb;
                 }
             }
+        };
+        // ---- bundle state ----
+        struct LayerMember {
+            int kind; // 1 HAD, 2 GEN
+            double m[8];
+        };
+        LayerMember layer[5];
+        bool layerUsed[5] = { false, false, false, false, false };
+        int layerCount = 0;
+        struct GroupMember {
+            int cls; // 0 scalar, 1+b register bit b
+            DevPhaseMember<R> d;
+        };
+        std::vector<GroupMember> group;
+        uint64_t ndq = 0; // qubits with a non-diagonal layer member in the open bundle
+        uint64_t dq = 0;  // qubits used diagonally by a group member in the open bundle
+        auto close_bundle = [&]() {
+            if (layerCount) {
+                DevOp<R> d;
+                memset(&d, 0, sizeof(d));
+                uint32_t kinds = 0;
+                for (int b = 0; b < JRN; ++b) {
+                    if (layerUsed[b]) {
+                        kinds |= 1U << b;
+                    }
+                }
+                d.emask = kinds;
+                d.code = OPC_LAYER;
+                dops.push_back(d);
+            }
+            layerCount = 0;
+            for (bool& u : layerUsed) {
+                u = false;
+            }
+            group.clear();
+            ndq = 0;
+            dq = 0;
+        };
+        dp.opBegin = (int)dops.size();
+        for (const HostOp& hop : pp.ops) {
+            uint32_t lmask, lval;
+            local_pred(hop, lmask, lval);
+            const uint32_t lmr = lmask & regAmpMask, lvr = lval & regAmpMask;
+            if (hop.kind == OP_PHASE) {
+                if (!(hop.cmask & tileMask)) {
+                    // every qubit of the predicate is outside the tile: uniform per tile, commutes with the whole sweep
+                    DevOuterPhase<R> op;
+                    memset(&op, 0, sizeof(op));
+                    op.omask = hop.cmask;
+                    op.oval = hop.cval;
+                    op.ph[0] = (R)hop.m[0];
+                    op.ph[1] = (R)hop.m[1];
+                    outerList.push_back(op);
+                    continue;
+                }
+                const int nreg = __builtin_popcount(lmr);
+                if (false && !(hop.cmask & ~tileMask) && (nreg == 0 || (nreg == 1 && lvr == lmr))) {
+                    // purely tile-local predicate touching at most one register bit: group member
+                    if (hop.cmask & ndq) {
+                        close_bundle();
+                    }
+                    if (group.size() >= 200) {
+                        close_bundle();
+                    }
+                    GroupMember g;
+                    memset(&g, 0, sizeof(g));
+                    g.cls = nreg ? 1 + reg_index(__builtin_ctz(lmr)) : 0;
+                    g.d.lmaskSb = lmask & ~regAmpMask;
+                    g.d.lvalSb = lval & ~regAmpMask;
+                    g.d.ph[0] = (R)hop.m[0];
+                    g.d.ph[1] = (R)hop.m[1];
+                    group.push_back(g);
+                    dq |= hop.cmask;
+                    continue;
+                }
+            } else if ((cfg.bundle & 1) && !hop.cmask && hop.kind == OP_HAD) {
+                // uncontrolled non-diagonal 1-qubit gate: layer member
+                const int jr = reg_index(tile_bit(cfg, sp.highQ, hop.tq));
+                if ((bitq(hop.tq) & (ndq | dq)) || layerUsed[jr]) {
+                    close_bundle();
+                }
+                layer[jr].kind = (hop.kind == OP_HAD) ? 1 : 2;
+                memcpy(layer[jr].m, hop.m, sizeof(hop.m));
+                layerUsed[jr] = true;
+                ++layerCount;
+                ndq |= bitq(hop.tq);
+                if (hop.kind == OP_HAD) {
+                    scale *= hop.m[0];
+                }
+                continue;
+            }
+            // everything else is a single op and closes the open bundle
+            close_bundle();
+            DevOp<R> d;
+            memset(&d, 0, sizeof(d));
+            d.omask = hop.cmask & ~tileMask;
+            d.oval = hop.cval & ~tileMask;
             d.lmaskSb = lmask & ~regAmpMask;
             d.lvalSb = lval & ~regAmpMask;
-            const uint32_t lmr = lmask & regAmpMask, lvr = lval & regAmpMask;
             uint32_t em = 0;
             for (int e = 0; e < NA; ++e) {
                 if ((roffA[e] & lmr) == lvr) {
@@ -806,15 +999,6 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
             }
             d.emask = em;
             const bool uncond = (em == fullE && d.lmaskSb == 0);
-            auto reg_index = [&](int tb) {
-                int jr = 0;
-                for (int b = 0; b < tb; ++b) {
-                    if (regAmpMask & (1U << b)) {
-                        ++jr;
-                    }
-                }
-                return jr;
-            };
             for (int k = 0; k < 8; ++k) {
                 d.m[k] = (R)hop.m[k];
             }
@@ -841,12 +1025,72 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
                 }
             }
             d.code = (kind * 5U + jr) | (d.lmaskSb ? CODE_HAS_SB : 0U);
+            dops.push_back(d);
         }
-        dp.opEnd = o;
+        close_bundle();
+        if (p == ds.nPass - 1 && (scale != 1.0 || !outerList.empty())) {
+            DevOp<R> d;
+            memset(&d, 0, sizeof(d));
+            d.code = OPC_SCALE;
+            dops.push_back(d);
+        }
+        dp.opEnd = (int)dops.size();
     }
-    ds->scale = scale;
-    ds->hasScale = (scale != 1.0) ? 1 : 0;
+    ds.scale = scale;
+    ds.hasScale = (scale != 1.0 || !outerList.empty()) ? 1 : 0;
+    ds.nOps = (int)dops.size();
+    ds.nOuter = (int)outerList.size();
+    const size_t opsBytes = ((dops.size() * sizeof(DevOp<R>)) + 15U) & ~(size_t)15U;
+    const size_t outerBytes = ((outerList.size() * sizeof(DevOuterPhase<R>)) + 15U) & ~(size_t)15U;
+    ds.poolOff = (int)(sizeof(DevSweep) + opsBytes);
+    ds.outerOff = (int)(sizeof(DevSweep) + opsBytes + pool.size());
+    const size_t start = buf.size();
+    const size_t bytes = ((sizeof(DevSweep) + opsBytes + pool.size() + outerBytes) + 15U) & ~(size_t)15U;
+    buf.resize(start + bytes, 0);
+    memcpy(buf.data() + start, &ds, sizeof(ds));
+    if (!dops.empty()) {
+        memcpy(buf.data() + start + sizeof(DevSweep), dops.data(), dops.size() * sizeof(DevOp<R>));
+    }
+    if (!pool.empty()) {
+        memcpy(buf.data() + start + ds.poolOff, pool.data(), pool.size());
+    }
+    if (!outerList.empty()) {
+        memcpy(buf.data() + start + ds.outerOff, outerList.data(), outerList.size() * sizeof(DevOuterPhase<R>));
+    }
     return bytes;
+}
+
+// Plan + encode ONE sweep from the head of `pending`.  Planning works on a bounded window (the scheduler never looks
+// further ahead than that), and retries with fewer ops if the encoded program would not fit beside the tile.
+constexpr size_t PLAN_WINDOW = 1024;
+static int plan_and_encode(std::vector<HostOp>& pending, const TileCfg& cfg0, int prec, std::vector<unsigned char>& buf, size_t* bytesOut,
+    size_t* nOpsOut, int* nPassOut)
+{
+    const size_t wsz = std::min(pending.size(), PLAN_WINDOW);
+    TileCfg cfg = cfg0;
+    for (;;) {
+        std::vector<HostOp> window(pending.begin(), pending.begin() + wsz);
+        SweepPlan sp;
+        plan_sweep(window, cfg, sp);
+        if (!sp.nOps) {
+            set_error("fused scheduler made no progress");
+            return B200SV_ESTATE;
+        }
+        const size_t mark = buf.size();
+        const size_t bytes = (prec == 32) ? encode_sweep<float>(sp, cfg, buf) : encode_sweep<double>(sp, cfg, buf);
+        if (bytes > MAX_PROG_BYTES && cfg.maxOps > 4) {
+            buf.resize(mark);
+            cfg.maxOps /= 2;
+            continue;
+        }
+        // commit: the window's leftovers go back in front of the untouched tail
+        window.insert(window.end(), pending.begin() + wsz, pending.end());
+        pending.swap(window);
+        *bytesOut = bytes;
+        *nOpsOut = sp.nOps;
+        *nPassOut = (int)sp.passes.size();
+        return B200SV_OK;
+    }
 }
 
 // per-state program arena (device + pinned host), guarded by an event
@@ -914,7 +1158,7 @@ static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes
     static unsigned long long attr_set_mask = 0; // per device: the attribute is per-context
     if (!(attr_set_mask & (1ULL << s->dev))) {
         SV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (int)(((size_t)16 << KC) + sizeof(DevSweep) + MAX_OPS * sizeof(DevOp<R>) + 16)));
+            (int)(((size_t)16 << KC) + MAX_PROG_BYTES)));
         attr_set_mask |= 1ULL << s->dev;
     }
     const uint64_t maxGrid = (uint64_t)sm_count(s->dev) * MINB;
@@ -926,9 +1170,10 @@ static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes
 
 // tuning knobs (env B200SV_FUSED="RB,L32,L64"): register chunk bits per pass and the contiguous-run length (low tile bits)
 struct FusedKnobs {
-    int RB = 3;
-    int L32 = 7;
+    int RB = 4;   // measured on B200 (profiles/r1_tuning.md): RB=4/L=6 beats RB=3/L=7 by ~12% on the 30-qubit H/T/CNOT circuit
+    int L32 = 6;
     int L64 = 6;
+    int bundle = 3; // bit 0: LAYER bundles, bit 1: PHGROUP bundles
 };
 static const FusedKnobs& knobs()
 {
@@ -936,8 +1181,11 @@ static const FusedKnobs& knobs()
         FusedKnobs v;
         const char* e = getenv("B200SV_FUSED");
         if (e) {
-            int rb = 0, l32 = 0, l64 = 0;
-            const int got = sscanf(e, "%d,%d,%d", &rb, &l32, &l64);
+            int rb = 0, l32 = 0, l64 = 0, bn = 3;
+            const int got = sscanf(e, "%d,%d,%d,%d", &rb, &l32, &l64, &bn);
+            if (got >= 4) {
+                v.bundle = bn;
+            }
             if (got >= 1 && (rb == 3 || rb == 4)) {
                 v.RB = rb;
             }
@@ -958,7 +1206,9 @@ constexpr int FUSED_NT = 256;
 static TileCfg state_cfg(int nq, int prec)
 {
     const FusedKnobs& k = knobs();
-    return make_cfg(nq, prec, FUSED_KC, k.RB, prec == 32 ? k.L32 : k.L64, FUSED_NT);
+    TileCfg c = make_cfg(nq, prec, FUSED_KC, k.RB, prec == 32 ? k.L32 : k.L64, FUSED_NT);
+    c.bundle = k.bundle;
+    return c;
 }
 
 int fused_flush(State* s)
@@ -986,14 +1236,10 @@ int fused_flush(State* s)
     std::vector<unsigned char> buf;
     std::vector<std::pair<size_t, size_t>> segs; // (offset, bytes)
     while (!pending.empty()) {
-        SweepPlan sp;
-        plan_sweep(pending, cfg, sp);
-        if (!sp.nOps) {
-            set_error("fused scheduler made no progress");
-            return B200SV_ESTATE;
-        }
         const size_t off = buf.size();
-        const size_t bytes = (s->prec == 32) ? encode_sweep<float>(sp, cfg, buf) : encode_sweep<double>(sp, cfg, buf);
+        size_t bytes = 0, nops = 0;
+        int npass = 0;
+        SV_TRY(plan_and_encode(pending, cfg, s->prec, buf, &bytes, &nops, &npass));
         segs.push_back({ off, bytes });
     }
     if (ar->pending) {
@@ -1068,14 +1314,14 @@ int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targ
     lower_queue(q, pending);
     const TileCfg cfg = state_cfg(n_qubits, precision);
     int sweeps = 0, passes = 0;
+    std::vector<unsigned char> buf;
     while (!pending.empty()) {
-        SweepPlan sp;
-        plan_sweep(pending, cfg, sp);
-        if (!sp.nOps) {
-            return B200SV_ESTATE;
-        }
+        size_t bytes = 0, nops = 0;
+        int npass = 0;
+        buf.clear();
+        SV_TRY(plan_and_encode(pending, cfg, precision, buf, &bytes, &nops, &npass));
         ++sweeps;
-        passes += (int)sp.passes.size();
+        passes += npass;
     }
     *n_sweeps = sweeps;
     *n_passes = passes;

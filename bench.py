@@ -81,7 +81,7 @@ def gate_calls(text):
     for _, t in qscript.parse(text):
         if t[0] in ("qubits", "TIC", "TOC"):
             continue
-        calls.append((t[0], tuple(int(x) for x in t[1:])))
+        calls.append((t[0], tuple((float(x) if ("." in x or "e" in x) else int(x)) for x in t[1:])))
     return calls
 
 
@@ -148,15 +148,26 @@ def main():
     ap.add_argument("--fusion", type=int, default=1)
     ap.add_argument("--cpu-sample-gates", type=int, default=45)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="htcnot", choices=["htcnot", "qft", "qv"],
+                    help="htcnot = BASELINE configs[1] (default, the headline); qft = configs[2]; qv = configs[3]-style layers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     n, depth, prec = args.qubits, args.depth, args.precision
     amp_bytes = 8 if prec == 32 else 16
-    text = qscript.random_htcnot(n, depth, seed=args.seed, timed=False)
+    if args.workload == "qft":
+        text = qscript.qft(n, seed=11, timed=False)
+    elif args.workload == "qv":
+        text = qscript.quantum_volume(n, depth=depth, seed=33, timed=False)
+    else:
+        text = qscript.random_htcnot(n, depth, seed=args.seed, timed=False)
     calls = gate_calls(text)
     gates = len(calls)
-    workload = "%d-qubit random circuit (H/T/CNOT, depth %d, %d gates), fp%d amplitudes" % (n, depth, gates, prec)
+    if args.workload == "qft":
+        gates = sum(1 for c in calls if c[0] == "H") + n + n * (n - 1) // 2  # init H's + QFT's own H and CPhaseRootN gates
+    workload = {"htcnot": "%d-qubit random circuit (H/T/CNOT, depth %d, %d gates), fp%d amplitudes" % (n, depth, gates, prec),
+                "qft": "%d-qubit QFT (%d H + %d controlled-phase), fp%d amplitudes" % (n, n, n * (n - 1) // 2, prec),
+                "qv": "%d-qubit quantum-volume layers (AI + CNOT matching, depth %d, %d gates), fp%d" % (n, depth, gates, prec)}[args.workload]
     dtype = "f32" if prec == 32 else "f64"
 
     if args.impl == "reference":

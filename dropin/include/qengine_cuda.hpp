@@ -30,6 +30,12 @@ protected:
     void SyncQubitCount();
     QEngineCUDAPtr Cast(QInterfacePtr p, const char* what) const;
 
+    /// QInterface::TryDecompose (src/qinterface/qinterface.cpp:836-853) adopts another instance's state through this
+    /// protected hook; the reference engines share the buffer (include/qengine_cpu.hpp:47-55), here it is a device copy.
+    using QEngine::Copy;
+    void Copy(QInterfacePtr orig) { Copy(std::dynamic_pointer_cast<QEngineCUDA>(orig)); }
+    void Copy(QEngineCUDAPtr orig);
+
     typedef std::function<void(QInterfacePtr)> CpuFn;
     /// ALU members are outside the hot path: round-trip through a temporary QEngineCPU.
     void ViaCpu(CpuFn fn);

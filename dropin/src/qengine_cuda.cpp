@@ -60,6 +60,21 @@ QEngineCUDA::QEngineCUDA(bitLenInt qBitCount, const bitCapInt& initState, qrack_
     Check(b200sv_set_permutation(sv, (uint64_t)(bitCapIntOcl)initState, (double)real(ph), (double)imag(ph)));
 }
 
+void QEngineCUDA::Copy(QEngineCUDAPtr orig)
+{
+    QEngine::Copy(std::dynamic_pointer_cast<QEngine>(orig));
+    int have = 0;
+    Check(b200sv_qubit_count(sv, &have));
+    if (have != (int)qubitCount) {
+        ResizeZero(qubitCount);
+    }
+    if (orig->IsZeroAmplitude()) {
+        Check(b200sv_zero(sv));
+    } else {
+        Check(b200sv_copy_state(sv, orig->sv));
+    }
+}
+
 QEngineCUDA::~QEngineCUDA()
 {
     if (sv) {

@@ -1173,6 +1173,7 @@ struct FusedKnobs {
     int RB = 4;   // measured on B200 (profiles/r1_tuning.md): RB=4/L=6 beats RB=3/L=7 by ~12% on the 30-qubit H/T/CNOT circuit
     int L32 = 6;
     int L64 = 6;
+    int RB64 = 3; // fp64: 8 double2 amplitudes per sub-block keep 3 CTAs/SM resident
     int bundle = 3; // bit 0: LAYER bundles, bit 1: PHGROUP bundles
 };
 static const FusedKnobs& knobs()
@@ -1181,10 +1182,13 @@ static const FusedKnobs& knobs()
         FusedKnobs v;
         const char* e = getenv("B200SV_FUSED");
         if (e) {
-            int rb = 0, l32 = 0, l64 = 0, bn = 3;
-            const int got = sscanf(e, "%d,%d,%d,%d", &rb, &l32, &l64, &bn);
+            int rb = 0, l32 = 0, l64 = 0, bn = 3, rb64 = 0;
+            const int got = sscanf(e, "%d,%d,%d,%d,%d", &rb, &l32, &l64, &bn, &rb64);
             if (got >= 4) {
                 v.bundle = bn;
+            }
+            if (got >= 5 && (rb64 == 3 || rb64 == 4)) {
+                v.RB64 = rb64;
             }
             if (got >= 1 && (rb == 3 || rb == 4)) {
                 v.RB = rb;
@@ -1206,7 +1210,7 @@ constexpr int FUSED_NT = 256;
 static TileCfg state_cfg(int nq, int prec)
 {
     const FusedKnobs& k = knobs();
-    TileCfg c = make_cfg(nq, prec, FUSED_KC, k.RB, prec == 32 ? k.L32 : k.L64, FUSED_NT);
+    TileCfg c = make_cfg(nq, prec, FUSED_KC, prec == 32 ? k.RB : k.RB64, prec == 32 ? k.L32 : k.L64, FUSED_NT);
     c.bundle = k.bundle;
     return c;
 }

@@ -29,6 +29,19 @@ from qrack_b200 import qscript  # noqa: E402
 METRIC = "gates/sec at 30q random circuit; Apply2x2 HBM GB/s vs roofline"
 
 
+def measured_traffic(kernel_bytes_per_launch):
+    """dram__bytes_read+write per launch of the fused sweep from the committed `ncu --set full` capture
+    (profiles/r1_fused_v6_ncu_full.json, 28 qubits), scaled to this run's state size."""
+    p = os.path.join(ROOT, "profiles", "r1_fused_v6_ncu_full.json")
+    try:
+        j = json.load(open(p))
+        l = j["launches"][0]
+        per28 = (float(l["dram__bytes_read.sum"]) + float(l["dram__bytes_write.sum"])) * 1e9
+        return per28 / (2.0 * (1 << 28) * 8) * kernel_bytes_per_launch
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -273,7 +286,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "includes": "SetPermutation + host gate submission through the C ABI + Prob(q) for every qubit"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "fused sweep" if stats["fused_sweeps"] else "k_apply2x2",
+                         "traffic": (measured_traffic(swept / max(1, launches)) if stats["fused_sweeps"] else None), "peak_source": peak_src, "kernel": "fused sweep" if stats["fused_sweeps"] else "k_apply2x2",
                          "bytes_per_launch": swept / max(1, launches), "ms_per_launch": kernel_ms,
                          "algorithmic_gbs": (alg / 1e9) / (ms_total / 1e3), "fused_sweeps": int(stats["fused_sweeps"]),
                          "fused_gates": int(stats["fused_gates"])},

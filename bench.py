@@ -212,8 +212,25 @@ def main():
     rank, world, local, dist = dist_setup(args.gpus)
     from qrack_b200 import QEngineCUDA
 
-    q = QEngineCUDA(n, 0, random.Random(1), 1.0 + 0j, False, False, deviceId=local, precision=prec)
-    q.be.set_fusion(args.fusion)
+    sharded = world > 1
+    if sharded:
+        # ONE state vector of n = qubits + log2(N) qubits sharded over the N GPUs (weak scaling: 2^qubits amplitudes per GPU)
+        import torch
+        from qrack_b200.sharded import QEngineSharded, cuda_engine_factory
+        k = world.bit_length() - 1
+        n = args.qubits + k
+        text = {"qft": lambda: qscript.qft(n, seed=11, timed=False),
+                "qv": lambda: qscript.quantum_volume(n, depth=depth, seed=33, timed=False),
+                "htcnot": lambda: qscript.random_htcnot(n, depth, seed=args.seed, timed=False)}[args.workload]()
+        calls = gate_calls(text)
+        gates = len(calls)
+        workload = "%d-qubit %s circuit (%d gates), fp%d amplitudes, 2^%d amplitudes per GPU" % (n, args.workload, gates, prec, args.qubits)
+        os.environ["B200SV_FUSED"] = os.environ.get("B200SV_FUSED", "")
+        q = QEngineSharded(n, 0, random.Random(1), 1.0 + 0j, precision=prec, dist=dist, world=world, rank=rank,
+                           device=torch.device("cuda", local), make_engine=cuda_engine_factory(local, prec))
+    else:
+        q = QEngineCUDA(n, 0, random.Random(1), 1.0 + 0j, False, False, deviceId=local, precision=prec)
+        q.be.set_fusion(args.fusion)
 
     def replay():
         for name, a in calls:
@@ -225,7 +242,10 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-timed arm: state resident in HBM, CUDA events on the engine's stream -------------------------
+    def get_stats():
+        return q.be.shard.stats() if sharded else q.be.stats()
+
+    # ---- device-timed arm: state resident in HBM, CUDA events on the stream the kernels run on --------------------
     for _ in range(args.warmup):
         q.SetPermutation(0, 1.0 + 0j)
         replay()
@@ -233,16 +253,33 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ms_steps = []
-    q.be.reset_stats()
+    ex0 = q.be.exchanges if sharded else 0
+    stats0 = get_stats()
+    if not sharded:
+        q.be.reset_stats()
+        stats0 = {k: 0 for k in stats0}
     barrier()
     for _ in range(args.steps):
         q.SetPermutation(0, 1.0 + 0j)
         q.Finish()
-        q.be.timer_begin()
-        replay()
-        ms_steps.append(q.be.timer_end())
+        if sharded:
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()          # the local engines run on torch's current stream (b200sv_set_stream), like NCCL
+            replay()
+            q.be.flush()
+            q.be.loc.be.flush()
+            e1.record()
+            e1.synchronize()
+            ms_steps.append(e0.elapsed_time(e1))
+        else:
+            q.be.timer_begin()
+            replay()
+            ms_steps.append(q.be.timer_end())
     barrier()
-    stats = q.be.stats()
+    stats1 = get_stats()
+    stats = {k: stats1[k] - stats0.get(k, 0) for k in stats1}
+    exchanges = (q.be.exchanges - ex0) if sharded else 0
     # ---- end-to-end arm: public API, host submission + init + result read inside the timed region -----------
     h2d = gates * (8 * 8 + 8 * 4)  # per gate: 8 doubles of matrix + offsets/powers words crossing the C ABI
     d2h = n * 8
@@ -264,7 +301,7 @@ def main():
         t = torch.tensor([ms_total, e2e_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, e2e_total = t.tolist()
-    total_gates = gates * args.steps * world  # replicas: every rank replays the whole circuit on its own state
+    total_gates = gates * args.steps  # one circuit on one (possibly sharded) state vector: whole-job gate count
     value = total_gates / (ms_total / 1e3)
     e2e_value = total_gates / e2e_total
 
@@ -275,13 +312,17 @@ def main():
         kernel_ms = ms_total / max(1, launches) * 1.0
         achieved = (swept / 1e9) / (ms_total / 1e3) if ms_total > 0 else 0.0
         alg = algorithmic_bytes(calls, n, amp_bytes) * args.steps
+        if sharded:
+            swept = swept  # bytes swept by rank 0's local kernels; the roofline entry is per GPU
         line = {
             "metric": METRIC, "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic",
             "config": {"workload": workload, "l2_policy": "state vector (%.1f GiB) is far larger than the 126 MB L2" %
                        ((1 << n) * amp_bytes / 2 ** 30), "fusion": args.fusion,
-                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world},
+                       "parallelism": "1 GPU" if world == 1 else
+                       "1 state vector sharded over %d GPUs (top %d qubits = rank), all-to-all qubit exchange" % (world, world.bit_length() - 1),
+                       "exchanges_per_step": (exchanges / max(1, args.steps)) if sharded else 0},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "includes": "SetPermutation + host gate submission through the C ABI + Prob(q) for every qubit"},

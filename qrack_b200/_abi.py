@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200sv_set_device": [H, c_int],
     "b200sv_device_ptr": [H, POINTER(c_void_p)],
     "b200sv_create_external": [c_int, c_int, c_int, c_void_p, POINTER(H)],
+    "b200sv_set_stream": [H, c_void_p],
     "b200sv_set_permutation": [H, c_uint64, c_double, c_double],
     "b200sv_zero": [H],
     "b200sv_is_zero": [H, POINTER(c_int)],
@@ -134,7 +135,10 @@ def check(lib, rc: int):
     raise RuntimeError("b200sv error %d: %s" % (rc, msg))
 
 
-def create(lib, device: int, n_qubits: int, precision: int):
+def create(lib, device: int, n_qubits: int, precision: int, external_ptr: int = 0):
     h = c_void_p()
-    check(lib, lib.b200sv_create(device, n_qubits, precision, ctypes.byref(h)))
+    if external_ptr:
+        check(lib, lib.b200sv_create_external(device, n_qubits, precision, c_void_p(external_ptr), ctypes.byref(h)))
+    else:
+        check(lib, lib.b200sv_create(device, n_qubits, precision, ctypes.byref(h)))
     return h

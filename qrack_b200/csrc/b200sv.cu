@@ -941,7 +941,9 @@ int b200sv_destroy(b200sv_t s)
     cudaEventDestroy(s->ev0);
     cudaEventDestroy(s->ev1);
     cudaEventDestroy(s->evx);
-    cudaStreamDestroy(s->stream);
+    if (s->ownStream) {
+        cudaStreamDestroy(s->stream);
+    }
     delete s;
     return B200SV_OK;
 }
@@ -968,6 +970,24 @@ int b200sv_device(b200sv_t s, int* d)
         return einval("null argument");
     }
     *d = s->dev;
+    return B200SV_OK;
+}
+
+int b200sv_set_stream(b200sv_t s, void* stream)
+{
+    SV_ENTER(s);
+    SV_TRY(flush_queue(s));
+    SV_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->ownStream) {
+        cudaStreamDestroy(s->stream);
+    }
+    if (stream) {
+        s->stream = (cudaStream_t)stream;
+        s->ownStream = false;
+    } else {
+        SV_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        s->ownStream = true;
+    }
     return B200SV_OK;
 }
 
@@ -1073,6 +1093,7 @@ int b200sv_set_device(b200sv_t s, int device)
     free_amps(s);
     std::swap(s->amps, n->amps);
     std::swap(s->stream, n->stream);
+    std::swap(s->ownStream, n->ownStream);
     std::swap(s->d_scratch, n->d_scratch);
     std::swap(s->h_scratch, n->h_scratch);
     std::swap(s->scratch_doubles, n->scratch_doubles);

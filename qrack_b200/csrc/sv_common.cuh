@@ -84,6 +84,7 @@ struct State {
     void* amps = nullptr; // device buffer (nullptr == the zero state)
     bool external = false;
     cudaStream_t stream = nullptr;
+    bool ownStream = true;
     double* d_scratch = nullptr; // small device scratch for reductions
     size_t scratch_doubles = 0;
     double* h_scratch = nullptr; // pinned host mirror

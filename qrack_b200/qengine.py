@@ -876,7 +876,7 @@ class QEngineHost:
 class _CudaBackend:
     """Backend primitives over libb200sv.so (include/b200sv.h).  One b200sv handle."""
 
-    def __init__(self, n_qubits: int, precision: int, device: int):
+    def __init__(self, n_qubits: int, precision: int, device: int, external_ptr: int = 0):
         from . import _abi
         self.abi = _abi
         self.lib = _abi.load()
@@ -884,7 +884,12 @@ class _CudaBackend:
         self.cplx = np.complex64 if precision == 32 else np.complex128
         self.real = np.float32 if precision == 32 else np.float64
         self.device = max(device, 0)
-        self.h = _abi.create(self.lib, self.device, n_qubits, precision)
+        self.h = _abi.create(self.lib, self.device, n_qubits, precision, external_ptr)
+
+    def set_stream(self, cuda_stream: int):
+        """run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0 restores a private one"""
+        import ctypes
+        self._ck(self.lib.b200sv_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
 
     def __del__(self):
         try:
@@ -1083,6 +1088,17 @@ class QEngineCUDA(QEngineHost):
 
     def _make_backend(self, n_qubits: int):
         return _CudaBackend(n_qubits, self.precision, self.deviceId)
+
+    @classmethod
+    def over_buffer(cls, device_ptr: int, n_qubits: int, device: int, precision: int = 32, rgp=None):
+        """Engine over an externally owned device buffer of 2^n amplitudes (e.g. a torch tensor's data_ptr()).  The
+        buffer is used as is (no initialisation) and never freed by the library."""
+        q = cls(0, 0, rgp, 1.0 + 0j, False, False, deviceId=device, precision=precision)
+        q.be.lib.b200sv_destroy(q.be.h)
+        q.be.h = q.be.abi.create(q.be.lib, q.be.device, n_qubits, precision, device_ptr)
+        q.qubitCount = n_qubits
+        q.runningNorm = REAL1_DEFAULT_ARG
+        return q
 
     def SetDevice(self, dID: int):
         import ctypes

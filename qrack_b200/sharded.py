@@ -1,0 +1,408 @@
+"""One-process-per-GPU sharding of one state vector: the B200 analogue of the reference's ``QPager``.
+
+Partition (reference ``include/qpager.hpp:60-69``, ``src/qpager.cpp:57-67``): with ``W = 2^k`` ranks the top ``k`` index
+bits are the rank, every rank holds one page of ``2^(n-k)`` amplitudes.  What differs from QPager is how a gate on a
+device-index ("meta") qubit is served.  QPager does swap–compute–swap with two half-page ``ShuffleBuffers`` per gate
+(``src/qpager.cpp:425-432``); here the engine keeps a *logical→physical qubit map* and, when a non-diagonal gate needs a
+qubit that currently lives in the rank bits, does **one all-to-all that exchanges all k rank bits with the top k local
+bits** (each rank keeps 1/W of its page and ships the rest over NVLink/NVSwitch — NCCL ``all_to_all_single``), choosing
+the qubits that become the new rank bits with Belady's rule over the queued gate list (farthest next non-diagonal use).
+Everything else needs no data motion: gates on local qubits run on the local engine (the fused sweep), diagonal gates on
+rank-bit qubits are per-rank scalars or predicated local phases, controls on rank-bit qubits just select which ranks run
+(QPager's meta-controlled cases, ``src/qpager.cpp:452-593``), scalars (Prob, norms) are one ``all_reduce``.
+
+``QEngineSharded`` derives from ``QEngineHost`` — the same gate dispatch mirror as ``QEngineCUDA`` — and supplies a
+backend whose primitives are distributed, so every ``QInterface``-named method (H, T, CNOT, QFT, Prob, ForceM, …) works
+unchanged on top of it.  The local engine and the communicator are injected: ``QEngineCUDA`` over a torch CUDA buffer +
+NCCL on the GPU box; the oracle restatement over a torch CPU buffer + gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import math
+import random
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from .qengine import QEngineHost, REAL1_DEFAULT_ARG
+
+
+def _bits(mask: int):
+    q = 0
+    while mask:
+        if mask & 1:
+            yield q
+        mask >>= 1
+        q += 1
+
+
+class ShardBuffers:
+    """Two page-sized torch buffers (real view, interleaved re/im) + the local engine bound to the active one."""
+
+    def __init__(self, n_local: int, precision: int, device, make_engine: Callable):
+        import torch
+        self.torch = torch
+        self.nl = n_local
+        self.precision = precision
+        self.rdtype = torch.float32 if precision == 32 else torch.float64
+        self.device = device
+        self.buf = torch.zeros(2 << n_local, dtype=self.rdtype, device=device)
+        self.scratch = torch.empty(2 << n_local, dtype=self.rdtype, device=device)
+        self.make_engine = make_engine
+        self.engine = make_engine(self.buf, n_local)
+        self.retired_stats = {}
+
+    def _retire(self):
+        st = getattr(self.engine.be, "stats", None)
+        if st is not None:
+            for k, v in st().items():
+                self.retired_stats[k] = self.retired_stats.get(k, 0) + v
+
+    def stats(self) -> dict:
+        """kernel/launch counters of every local engine this page has had (a new one is bound after each exchange)"""
+        out = dict(self.retired_stats)
+        st = getattr(self.engine.be, "stats", None)
+        if st is not None:
+            for k, v in st().items():
+                out[k] = out.get(k, 0) + v
+        return out
+
+    def swap(self):
+        """the exchange wrote into `scratch`: make it the live page"""
+        self.engine.Finish()
+        self._retire()
+        self.buf, self.scratch = self.scratch, self.buf
+        self.engine = self.make_engine(self.buf, self.nl)
+
+
+def cuda_engine_factory(device_index: int, precision: int = 32):
+    """local engine = QEngineCUDA over the torch buffer, running on torch's current stream"""
+    def make(buf, n_local):
+        import torch
+        from .qengine import QEngineCUDA
+        q = QEngineCUDA.over_buffer(buf.data_ptr(), n_local, device_index, precision, random.Random(1))
+        q.be.set_stream(torch.cuda.current_stream(torch.device("cuda", device_index)).cuda_stream)
+        return q
+    return make
+
+
+class _Gate:
+    __slots__ = ("t", "cmask", "cval", "m", "diag")
+
+    def __init__(self, t, cmask, cval, m):
+        self.t, self.cmask, self.cval, self.m = t, cmask, cval, m
+        self.diag = (m[1] == 0 and m[2] == 0)
+
+
+class _ShardedBackend:
+    """Backend primitives (see qengine.QEngineHost) over W ranks; indices and masks arrive in LOGICAL qubit order."""
+
+    def __init__(self, n_qubits: int, precision: int, shard: Optional[ShardBuffers], dist, world: int, rank: int):
+        self.n = n_qubits
+        self.precision = precision
+        self.dist = dist
+        self.world = world
+        self.rank = rank
+        self.k = int(round(math.log2(world))) if world > 1 else 0
+        assert (1 << self.k) == world, "world size must be a power of two"
+        self.nl = n_qubits - self.k
+        self.shard = shard
+        self.cplx = np.complex64 if precision == 32 else np.complex128
+        self.real = np.float32 if precision == 32 else np.float64
+        self.perm = list(range(n_qubits))  # logical qubit -> physical index bit (>= nl: rank bit)
+        self.pending: List[_Gate] = []
+        self.exchanges = 0
+        self.exchange_bytes = 0
+        self.local_swaps = 0
+
+    # ---- helpers ------------------------------------------------------------------------------------------------
+    @property
+    def loc(self):
+        return self.shard.engine
+
+    def _pmask(self, mask: int) -> int:
+        out = 0
+        for q in _bits(mask):
+            out |= 1 << self.perm[q]
+        return out
+
+    def _pindex(self, idx: int) -> int:
+        out = 0
+        for q in _bits(idx):
+            out |= 1 << self.perm[q]
+        return out
+
+    def _split(self, pmask: int):
+        lm = pmask & ((1 << self.nl) - 1)
+        return lm, pmask >> self.nl
+
+    def _allreduce(self, vals: Sequence[float]) -> List[float]:
+        if self.world == 1:
+            return list(vals)
+        torch = self.shard.torch
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.shard.device)
+        self.dist.all_reduce(t)
+        return t.tolist()
+
+    # ---- lifecycle / trivial --------------------------------------------------------------------------------------
+    def resize_zero(self, n):
+        raise NotImplementedError("sharded states have a fixed width")
+
+    def finish(self):
+        self.flush()
+        self.loc.Finish()
+
+    def is_zero(self) -> bool:
+        return False
+
+    def zero(self):
+        self.pending.clear()
+        self.shard.buf.zero_()
+
+    def set_permutation(self, perm: int, phase: complex):
+        self.pending.clear()
+        self.perm = list(range(self.n))
+        self.loc.Finish()
+        self.shard.buf.zero_()
+        if (perm >> self.nl) == self.rank:
+            self.loc.SetAmplitude(perm & ((1 << self.nl) - 1), phase)
+        self.loc.runningNorm = REAL1_DEFAULT_ARG
+
+    # ---- gates ------------------------------------------------------------------------------------------------------
+    def apply2x2(self, off1, off2, mtrx, pows, nrm, thresh, calc_norm):
+        if calc_norm or nrm != 1.0:
+            raise NotImplementedError("doNormalize is not supported on the sharded engine (QPager forces it off too)")
+        pmask = 0
+        for p in pows:
+            pmask |= p
+        diff = off1 ^ off2
+        if diff and not (diff & (diff - 1)):
+            t = diff.bit_length() - 1
+            m = list(mtrx)
+            if off1 & diff:  # off1 holds the |1> branch
+                m = [m[3], m[2], m[1], m[0]]
+            self.pending.append(_Gate(t, pmask & ~diff, off1 & ~diff, m))
+            return None
+        if bin(diff).count("1") == 2 and pmask == diff and mtrx[0] == 0 and mtrx[3] == 0 and mtrx[1] == 1 and mtrx[2] == 1:
+            # uncontrolled Swap: relabel, no data motion (QPager::Swap does the same for meta qubits)
+            self.flush()
+            a, b = [q for q in _bits(diff)]
+            self.perm[a], self.perm[b] = self.perm[b], self.perm[a]
+            return None
+        raise NotImplementedError("two-target Apply2x2 forms (ISwap/SqrtSwap/CSwap) are not sharded; decompose them")
+
+    def xmask(self, mask):
+        for q in _bits(mask):
+            self.pending.append(_Gate(q, 0, 0, [0j, 1 + 0j, 1 + 0j, 0j]))
+
+    def phase_parity(self, radians, mask):
+        self.flush()
+        lm, gm = self._split(self._pmask(mask))
+        sign = -1.0 if (bin(self.rank & gm).count("1") & 1) else 1.0
+        if lm:
+            self.loc.PhaseParity(sign * radians, lm)
+        else:  # all qubits are rank bits: a per-rank scalar, e^{+i r/2} for odd parity, e^{-i r/2} for even (state.cpp:1035-1051)
+            ang = (radians / 2) if sign < 0 else -(radians / 2)
+            ph = complex(math.cos(ang), math.sin(ang))
+            self.loc.Mtrx([ph, 0j, 0j, ph], 0)
+
+    def phase_root_n_mask(self, n, mask):
+        self.flush()
+        lm, gm = self._split(self._pmask(mask))
+        steps = bin(self.rank & gm).count("1")
+        if lm:
+            self.loc.PhaseRootNMask(n, lm)
+        if steps:
+            rad = -math.pi / (1 << (n - 1)) * steps
+            ph = complex(math.cos(rad), math.sin(rad))
+            self.loc.Mtrx([ph, 0j, 0j, ph], 0)
+
+    def apply_m(self, mask, result, nrm: complex):
+        self.flush()
+        lm, gm = self._split(self._pmask(mask))
+        lr, gr = self._split(self._pindex(result))
+        if (self.rank & gm) != gr:
+            self.loc.Finish()
+            self.shard.buf.zero_()
+        elif lm:
+            self.loc.be.apply_m(lm, lr, nrm)
+        else:
+            self.loc.Mtrx([nrm, 0j, 0j, nrm], 0)
+
+    # ---- reductions -------------------------------------------------------------------------------------------------
+    def prob_mask(self, mask, perm) -> float:
+        self.flush()
+        lm, gm = self._split(self._pmask(mask))
+        lr, gr = self._split(self._pindex(perm))
+        v = 0.0
+        if (self.rank & gm) == gr:
+            v = self.loc.be.prob_mask(lm, lr) if lm else self.loc.be.norm(0.0)
+        return self._allreduce([v])[0]
+
+    def prob_parity(self, mask) -> float:
+        self.flush()
+        lm, gm = self._split(self._pmask(mask))
+        odd_rank = bin(self.rank & gm).count("1") & 1
+        tot = self.loc.be.norm(0.0)
+        podd = self.loc.be.prob_parity(lm) if lm else 0.0
+        return self._allreduce([(tot - podd) if odd_rank else podd])[0]
+
+    def norm(self, thresh) -> float:
+        self.flush()
+        return self._allreduce([self.loc.be.norm(thresh)])[0]
+
+    def normalize(self, nrm, thresh, phase_arg):
+        self.flush()
+        self.loc.be.normalize(nrm, thresh, phase_arg)
+
+    def get_amplitude(self, perm: int) -> complex:
+        self.flush()
+        p = self._pindex(perm)
+        a = 0j
+        if (p >> self.nl) == self.rank:
+            a = self.loc.GetAmplitude(p & ((1 << self.nl) - 1))
+        re, im = self._allreduce([a.real, a.imag])
+        return complex(re, im)
+
+    def set_amplitude(self, perm: int, amp: complex):
+        self.flush()
+        p = self._pindex(perm)
+        if (p >> self.nl) == self.rank:
+            self.loc.SetAmplitude(p & ((1 << self.nl) - 1), amp)
+
+    def get_state(self) -> np.ndarray:
+        """full state in LOGICAL order on every rank (tests / small n only)"""
+        self.flush()
+        self.loc.Finish()
+        torch = self.shard.torch
+        local = self.shard.buf
+        if self.world > 1:
+            parts = [torch.empty_like(local) for _ in range(self.world)]
+            self.dist.all_gather(parts, local)
+            full = torch.cat(parts)
+        else:
+            full = local
+        phys = full.cpu().numpy().view(self.cplx)
+        # phys index bit perm[q] holds logical qubit q: transpose the 2^n tensor accordingly
+        t = phys.reshape([2] * self.n)  # axis 0 = most significant physical bit (n-1)
+        axes = [self.n - 1 - self.perm[q] for q in range(self.n - 1, -1, -1)]
+        return np.ascontiguousarray(t.transpose(axes)).reshape(-1)
+
+    def get_probs(self):
+        s = self.get_state()
+        return (s.real.astype(self.real) ** 2 + s.imag.astype(self.real) ** 2).astype(self.real)
+
+    # ---- scheduling -------------------------------------------------------------------------------------------------
+    def flush(self):
+        ops, self.pending = self.pending, []
+        i = 0
+        while i < len(ops):
+            g = ops[i]
+            if self.perm[g.t] < self.nl or g.diag:
+                self._run_local(g)
+                i += 1
+                continue
+            self._exchange(ops, i)
+        return
+
+    def _run_local(self, g: _Gate):
+        nl = self.nl
+        ctrls, cperm = [], 0
+        for c in _bits(g.cmask):
+            pc = self.perm[c]
+            want = (g.cval >> c) & 1
+            if pc >= nl:
+                if ((self.rank >> (pc - nl)) & 1) != want:
+                    return  # a rank-bit control that is not satisfied on this rank: nothing to do
+            else:
+                if want:
+                    cperm |= 1 << len(ctrls)
+                ctrls.append(pc)
+        pt = self.perm[g.t]
+        if pt < nl:
+            self.loc.UCMtrx(ctrls, g.m, pt, cperm)
+            return
+        # diagonal gate on a rank-bit qubit: this rank sees one diagonal entry
+        d = g.m[3] if ((self.rank >> (pt - nl)) & 1) else g.m[0]
+        if d == 1:
+            return
+        if ctrls:
+            tq = next(q for q in range(nl) if q not in ctrls)
+            self.loc.UCMtrx(ctrls, [d, 0j, 0j, d], tq, cperm)
+        else:
+            self.loc.Mtrx([d, 0j, 0j, d], 0)
+
+    def _exchange(self, ops: List[_Gate], i: int):
+        """make every rank-bit qubit local: all k rank bits <-> top k local bits, victims chosen by Belady's rule"""
+        k, nl, n = self.k, self.nl, self.n
+        inv = {p: q for q, p in enumerate(self.perm)}  # physical bit -> logical qubit
+        far = {}
+        horizon = len(ops)
+        for q in range(n):
+            if self.perm[q] < nl:
+                far[q] = horizon + 1
+        for j in range(i, len(ops)):
+            g = ops[j]
+            if not g.diag and g.t in far and far[g.t] > horizon:
+                far[g.t] = j
+        # k local logical qubits with the farthest next non-diagonal use (ties: higher physical position = cheaper)
+        victims = sorted(far.keys(), key=lambda q: (-far[q], -self.perm[q]))[:k]
+        top = list(range(nl - k, nl))
+        # step A: bring the victims to the top k local positions with local swaps
+        need = [v for v in victims if self.perm[v] < nl - k]
+        free_top = [p for p in top if inv[p] not in victims]
+        for v, p in zip(need, free_top):
+            pv = self.perm[v]
+            other = inv[p]
+            self.loc.Swap(pv, p)
+            self.local_swaps += 1
+            self.perm[v], self.perm[other] = p, pv
+            inv[p], inv[pv] = v, other
+        # step B: one all-to-all; chunk j of this rank's page goes to rank j and lands there as chunk `rank`
+        self.loc.Finish()
+        torch = self.shard.torch
+        src, dst = self.shard.buf, self.shard.scratch
+        if self.world > 1:
+            if self.dist.get_backend() == "nccl":
+                self.dist.all_to_all_single(dst, src)
+            else:
+                chunk = src.numel() // self.world
+                reqs = []
+                for peer in range(self.world):
+                    if peer == self.rank:
+                        dst[peer * chunk:(peer + 1) * chunk].copy_(src[peer * chunk:(peer + 1) * chunk])
+                    else:
+                        reqs.append(self.dist.isend(src[peer * chunk:(peer + 1) * chunk], peer))
+                        reqs.append(self.dist.irecv(dst[peer * chunk:(peer + 1) * chunk], peer))
+                for r in reqs:
+                    r.wait()
+            self.shard.swap()
+            self.exchange_bytes += src.numel() * src.element_size() * (self.world - 1) // self.world
+        self.exchanges += 1
+        for b in range(k):
+            pl, pg = nl - k + b, nl + b
+            ql, qg = inv[pl], inv[pg]
+            self.perm[ql], self.perm[qg] = pg, pl
+            inv[pl], inv[pg] = qg, ql
+
+
+class QEngineSharded(QEngineHost):
+    """QPager-like engine over `world` ranks; constructed collectively by every rank with the same arguments."""
+
+    def __init__(self, qBitCount: int, initState: int = 0, rgp=None, phaseFac=None, doNorm: bool = False,
+                 randomGlobalPhase: bool = False, precision: int = 32, dist=None, world: int = 1, rank: int = 0,
+                 device=None, make_engine: Optional[Callable] = None, **kw):
+        if doNorm:
+            raise ValueError("QEngineSharded: doNormalize is not supported (QPager forces it off as well)")
+        self._dist, self._world, self._rank = dist, world, rank
+        self._device, self._make_engine = device, make_engine
+        super().__init__(qBitCount, initState, rgp, 1.0 + 0j if phaseFac is None else phaseFac, False, randomGlobalPhase,
+                         precision=precision)
+
+    def _make_backend(self, n_qubits: int):
+        k = int(round(math.log2(self._world))) if self._world > 1 else 0
+        shard = ShardBuffers(n_qubits - k, self.precision, self._device, self._make_engine)
+        return _ShardedBackend(n_qubits, self.precision, shard, self._dist, self._world, self._rank)
+
+    def flush(self):
+        self.be.flush()

@@ -61,10 +61,13 @@ int b200sv_device_ptr(b200sv_t s, void** ptr);
 /* adopt an externally owned device buffer of 2^n amplitudes (e.g. a torch tensor); never freed by the library */
 int b200sv_create_external(int device, int n_qubits, int precision, void* device_ptr, b200sv_t* out);
 
+/* point an external-buffer state at another caller-owned buffer of the same size (double-buffered exchanges) */
+int b200sv_rebind_external(b200sv_t s, void* device_ptr);
+
 /* run this state's work on a caller-owned CUDA stream (e.g. torch's current stream, so that NCCL collectives issued by
  * torch.distributed and the engine's kernels are ordered on one stream and can be timed with one pair of events).
- * `stream` is a cudaStream_t passed as void*; NULL restores a private stream. */
-int b200sv_set_stream(b200sv_t s, void* stream);
+ * `stream` is a cudaStream_t passed as void* (0 = the legacy default stream); adopt == 0 restores a private stream. */
+int b200sv_set_stream(b200sv_t s, void* stream, int adopt);
 
 /* ---- state I/O (QEngine page ops, qengine.hpp:127-145; CPU semantics src/qengine/state.cpp:66-351) ---- */
 int b200sv_set_permutation(b200sv_t s, uint64_t perm, double phase_re, double phase_im); /* SetPermutation :228-254 */

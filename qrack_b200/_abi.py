@@ -37,7 +37,8 @@ SIGNATURES = {
     "b200sv_set_device": [H, c_int],
     "b200sv_device_ptr": [H, POINTER(c_void_p)],
     "b200sv_create_external": [c_int, c_int, c_int, c_void_p, POINTER(H)],
-    "b200sv_set_stream": [H, c_void_p],
+    "b200sv_rebind_external": [H, c_void_p],
+    "b200sv_set_stream": [H, c_void_p, c_int],
     "b200sv_set_permutation": [H, c_uint64, c_double, c_double],
     "b200sv_zero": [H],
     "b200sv_is_zero": [H, POINTER(c_int)],

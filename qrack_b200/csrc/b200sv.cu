@@ -973,7 +973,18 @@ int b200sv_device(b200sv_t s, int* d)
     return B200SV_OK;
 }
 
-int b200sv_set_stream(b200sv_t s, void* stream)
+int b200sv_rebind_external(b200sv_t s, void* device_ptr)
+{
+    SV_ENTER(s);
+    if (!s->external || !device_ptr) {
+        return einval("rebind_external: not an external-buffer state or null pointer");
+    }
+    SV_TRY(flush_queue(s));
+    s->amps = device_ptr; // stream order is preserved: later work on this state is queued behind the flush
+    return B200SV_OK;
+}
+
+int b200sv_set_stream(b200sv_t s, void* stream, int adopt)
 {
     SV_ENTER(s);
     SV_TRY(flush_queue(s));
@@ -981,7 +992,7 @@ int b200sv_set_stream(b200sv_t s, void* stream)
     if (s->ownStream) {
         cudaStreamDestroy(s->stream);
     }
-    if (stream) {
+    if (adopt) {
         s->stream = (cudaStream_t)stream;
         s->ownStream = false;
     } else {

@@ -886,10 +886,15 @@ class _CudaBackend:
         self.device = max(device, 0)
         self.h = _abi.create(self.lib, self.device, n_qubits, precision, external_ptr)
 
-    def set_stream(self, cuda_stream: int):
-        """run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0 restores a private one"""
+    def rebind_external(self, device_ptr: int):
         import ctypes
-        self._ck(self.lib.b200sv_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+        self._ck(self.lib.b200sv_rebind_external(self.h, ctypes.c_void_p(device_ptr)))
+
+    def set_stream(self, cuda_stream, adopt: bool = True):
+        """run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream, 0 = legacy default stream);
+        adopt=False restores a private stream"""
+        import ctypes
+        self._ck(self.lib.b200sv_set_stream(self.h, ctypes.c_void_p(cuda_stream or 0), 1 if adopt else 0))
 
     def __del__(self):
         try:

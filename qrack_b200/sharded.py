@@ -69,10 +69,15 @@ class ShardBuffers:
 
     def swap(self):
         """the exchange wrote into `scratch`: make it the live page"""
-        self.engine.Finish()
-        self._retire()
         self.buf, self.scratch = self.scratch, self.buf
-        self.engine = self.make_engine(self.buf, self.nl)
+        rebind = getattr(self.engine.be, "rebind_external", None)
+        if rebind is not None:
+            rebind(self.buf.data_ptr())  # same handle, same stream: ordered behind the exchange
+            self.engine.runningNorm = REAL1_DEFAULT_ARG
+        else:
+            self.engine.Finish()
+            self._retire()
+            self.engine = self.make_engine(self.buf, self.nl)
 
 
 def cuda_engine_factory(device_index: int, precision: int = 32):
@@ -359,7 +364,10 @@ class _ShardedBackend:
             self.perm[v], self.perm[other] = p, pv
             inv[p], inv[pv] = v, other
         # step B: one all-to-all; chunk j of this rank's page goes to rank j and lands there as chunk `rank`
-        self.loc.Finish()
+        if self.dist is not None and self.world > 1 and self.dist.get_backend() == "nccl":
+            self.loc.be.flush()  # NCCL runs on the same (torch current) stream as the engine: stream order suffices
+        else:
+            self.loc.Finish()
         torch = self.shard.torch
         src, dst = self.shard.buf, self.shard.scratch
         if self.world > 1:

@@ -47,7 +47,13 @@ def _worker(rank, world, port, text, prec, out_path):
 
 def run_sharded(text, world, prec, tmp_path):
     out = str(tmp_path / ("out_%d.npz" % world))
-    mp.spawn(_worker, args=(world, _free_port(), text, prec, out), nprocs=world, join=True)
+    for attempt in range(3):  # the rendezvous port can be taken between probing and binding
+        try:
+            mp.spawn(_worker, args=(world, _free_port(), text, prec, out), nprocs=world, join=True)
+            break
+        except Exception as e:
+            if "EADDRINUSE" not in str(e) or attempt == 2:
+                raise
     z = np.load(out)
     return z["state"], z["results"], int(z["exchanges"])
 

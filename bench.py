@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--fusion", type=int, default=1)
     ap.add_argument("--cpu-sample-gates", type=int, default=45)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: qubit exchange by the fused NVLink peer-store kernel (default) or NCCL all_to_all + local swaps")
     ap.add_argument("--workload", default="htcnot", choices=["htcnot", "qft", "qv"],
                     help="htcnot = BASELINE configs[1] (default, the headline); qft = configs[2]; qv = configs[3]-style layers")
     args = ap.parse_args()
@@ -227,7 +229,8 @@ def main():
         workload = "%d-qubit %s circuit (%d gates), fp%d amplitudes, 2^%d amplitudes per GPU" % (n, args.workload, gates, prec, args.qubits)
         os.environ["B200SV_FUSED"] = os.environ.get("B200SV_FUSED", "")
         q = QEngineSharded(n, 0, random.Random(1), 1.0 + 0j, precision=prec, dist=dist, world=world, rank=rank,
-                           device=torch.device("cuda", local), make_engine=cuda_engine_factory(local, prec))
+                           device=torch.device("cuda", local), make_engine=cuda_engine_factory(local, prec),
+                           p2p=(args.exchange == "p2p"))
     else:
         q = QEngineCUDA(n, 0, random.Random(1), 1.0 + 0j, False, False, deviceId=local, precision=prec)
         q.be.set_fusion(args.fusion)
@@ -321,7 +324,7 @@ def main():
             "config": {"workload": workload, "l2_policy": "state vector (%.1f GiB) is far larger than the 126 MB L2" %
                        ((1 << n) * amp_bytes / 2 ** 30), "fusion": args.fusion,
                        "parallelism": "1 GPU" if world == 1 else
-                       "1 state vector sharded over %d GPUs (top %d qubits = rank), all-to-all qubit exchange" % (world, world.bit_length() - 1),
+                       "1 state vector sharded over %d GPUs (top %d qubits = rank), qubit exchange: %s" % (world, world.bit_length() - 1, "fused NVLink peer-store kernel" if args.exchange == "p2p" else "NCCL all_to_all_single + local swap sweeps"),
                        "exchanges_per_step": (exchanges / max(1, args.steps)) if sharded else 0},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -135,6 +135,20 @@ int b200sv_decompose(b200sv_t s, int start, int length, b200sv_t dest);
 /* Dispose(start,length,perm) (:1708-1748): pure gather of the slice where the disposed bits == perm */
 int b200sv_dispose_perm(b200sv_t s, int start, int length, uint64_t perm);
 
+/* ---- multi-process exchange over NVLink peer memory (one process per GPU) ----
+ * Pages are plain cudaMalloc allocations so that they can be exported with CUDA IPC and mapped by the peer processes.
+ * b200sv_exchange_scatter is the fused "re-page" step: ONE kernel reads this rank's page once and stores every 16-byte
+ * chunk straight into the destination rank's page through the peer mapping (the element with local index i goes to
+ * rank r' = the bits of i at victim_bits[0..k-1], to index i with those bits replaced by this rank's bits) — i.e. the
+ * k rank-index qubits are exchanged with k arbitrary local qubits without any local pre-permutation sweep and without
+ * staging (reference: QPager re-pages with SetAmplitudePage / 2x ShuffleBuffers, src/qpager.cpp:316-367,425-432). */
+int b200sv_alloc_page(int device, uint64_t bytes, void** ptr);
+int b200sv_free_page(int device, void* ptr);
+int b200sv_ipc_export(int device, void* ptr, unsigned char handle_out[64]);
+int b200sv_ipc_import(int device, const unsigned char handle[64], void** ptr);
+int b200sv_ipc_release(int device, void* ptr);
+int b200sv_exchange_scatter(b200sv_t s, int k, const int* victim_bits, int rank, void* const* dst_pages);
+
 /* ---- queue / fusion control ---- */
 int b200sv_flush(b200sv_t s);  /* launch everything queued; does not wait */
 int b200sv_finish(b200sv_t s); /* flush + wait for the device (QInterface::Finish) */

@@ -74,6 +74,12 @@ SIGNATURES = {
     "b200sv_compose": [H, H, c_int],
     "b200sv_decompose": [H, c_int, c_int, H],
     "b200sv_dispose_perm": [H, c_int, c_int, c_uint64],
+    "b200sv_alloc_page": [c_int, c_uint64, POINTER(c_void_p)],
+    "b200sv_free_page": [c_int, c_void_p],
+    "b200sv_ipc_export": [c_int, c_void_p, c_void_p],
+    "b200sv_ipc_import": [c_int, c_void_p, POINTER(c_void_p)],
+    "b200sv_ipc_release": [c_int, c_void_p],
+    "b200sv_exchange_scatter": [H, c_int, POINTER(c_int), c_int, POINTER(c_void_p)],
     "b200sv_flush": [H],
     "b200sv_finish": [H],
     "b200sv_set_fusion": [H, c_int],

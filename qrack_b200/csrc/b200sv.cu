@@ -683,6 +683,45 @@ template <typename C> __global__ void __launch_bounds__(256) k_swap_ranges(C* a,
     }
 }
 
+// K7: fused re-page over NVLink.  dst[r'][c'] = src[c] with r' = victim bits of c, c' = c with the victim bits := rank bits.
+struct ScatterArgs {
+    uint4* dst[8 * 32]; // up to 2^8 destination pages
+    int k;
+    int cb[8];          // victim chunk-bit positions
+    uint64_t vmask;     // OR of the victim chunk bits
+    uint64_t rankDep;   // this rank's bits deposited at the victim positions
+};
+__global__ void __launch_bounds__(256) k_exchange_scatter(const uint4* __restrict__ src, uint64_t nChunks, const ScatterArgs* __restrict__ ap)
+{
+    __shared__ ScatterArgs a;
+    for (unsigned i = threadIdx.x; i < sizeof(ScatterArgs) / 4; i += blockDim.x) {
+        reinterpret_cast<unsigned*>(&a)[i] = reinterpret_cast<const unsigned*>(ap)[i];
+    }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t c0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c0 < nChunks; c0 += stride * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t c = c0 + u * stride;
+            if (c < nChunks) {
+                v[u] = src[c];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t c = c0 + u * stride;
+            if (c < nChunks) {
+                unsigned r = 0;
+                for (int b = 0; b < a.k; ++b) {
+                    r |= (unsigned)((c >> a.cb[b]) & 1ULL) << b;
+                }
+                a.dst[r][(c & ~a.vmask) | a.rankDep] = v[u];
+            }
+        }
+    }
+}
+
 __global__ void k_fill_bytes(uint4* p, uint64_t n, unsigned v)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -981,6 +1020,101 @@ int b200sv_rebind_external(b200sv_t s, void* device_ptr)
     }
     SV_TRY(flush_queue(s));
     s->amps = device_ptr; // stream order is preserved: later work on this state is queued behind the flush
+    return B200SV_OK;
+}
+
+int b200sv_alloc_page(int device, uint64_t bytes, void** ptr)
+{
+    if (!ptr) {
+        return einval("null out pointer");
+    }
+    DevGuard g(device);
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) {
+        *ptr = nullptr;
+        return cuda_fail(e, "cudaMalloc(page)");
+    }
+    return B200SV_OK;
+}
+int b200sv_free_page(int device, void* ptr)
+{
+    DevGuard g(device);
+    SV_CUDA(cudaDeviceSynchronize());
+    SV_CUDA(cudaFree(ptr));
+    return B200SV_OK;
+}
+int b200sv_ipc_export(int device, void* ptr, unsigned char handle_out[64])
+{
+    DevGuard g(device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    SV_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle_out, &h, 64);
+    return B200SV_OK;
+}
+int b200sv_ipc_import(int device, const unsigned char handle[64], void** ptr)
+{
+    DevGuard g(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    SV_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200SV_OK;
+}
+int b200sv_ipc_release(int device, void* ptr)
+{
+    DevGuard g(device);
+    SV_CUDA(cudaIpcCloseMemHandle(ptr));
+    return B200SV_OK;
+}
+
+int b200sv_exchange_scatter(b200sv_t s, int k, const int* victim_bits, int rank, void* const* dst_pages)
+{
+    SV_ENTER(s);
+    if (k < 1 || k > 8 || !victim_bits || !dst_pages) {
+        return einval("exchange_scatter: bad arguments");
+    }
+    if (!s->amps) {
+        return einval("exchange_scatter: zero state");
+    }
+    const int apcLog = (s->prec == 32) ? 1 : 0;
+    ScatterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.k = k;
+    for (int b = 0; b < k; ++b) {
+        const int cb = victim_bits[b] - apcLog;
+        if (cb < 0 || victim_bits[b] >= s->nq) {
+            return einval("exchange_scatter: victim qubit out of range (must be a local qubit above the 16-byte chunk)");
+        }
+        for (int b2 = 0; b2 < b; ++b2) {
+            if (a.cb[b2] == cb) {
+                return einval("exchange_scatter: duplicate victim qubit");
+            }
+        }
+        a.cb[b] = cb;
+        a.vmask |= 1ULL << cb;
+        if ((rank >> b) & 1) {
+            a.rankDep |= 1ULL << cb;
+        }
+    }
+    for (int r = 0; r < (1 << k); ++r) {
+        if (!dst_pages[r]) {
+            return einval("exchange_scatter: null destination page");
+        }
+        a.dst[r] = (uint4*)dst_pages[r];
+    }
+    SV_TRY(flush_queue(s));
+    // argument block: reuse the per-state scratch (device) via pinned staging
+    SV_TRY(ensure_scratch(s, (sizeof(ScatterArgs) + 7) / 8 + 8));
+    memcpy(s->h_scratch, &a, sizeof(a));
+    SV_CUDA(cudaMemcpyAsync(s->d_scratch, s->h_scratch, sizeof(a), cudaMemcpyHostToDevice, s->stream));
+    const uint64_t nChunks = (s->dim() * s->amp_bytes()) / 16U;
+    const unsigned grid = stream_grid(s->dev, (nChunks + 3) / 4, 256);
+    k_exchange_scatter<<<grid, 256, 0, s->stream>>>((const uint4*)s->amps, nChunks, (const ScatterArgs*)s->d_scratch);
+    SV_CUDA(cudaGetLastError());
+    // the pinned staging block must not be overwritten before the copy has run
+    SV_CUDA(cudaEventRecord(s->evx, s->stream));
+    SV_CUDA(cudaEventSynchronize(s->evx));
+    s->stats.kernel_launches++;
     return B200SV_OK;
 }
 

@@ -67,6 +67,36 @@ class ShardBuffers:
                 out[k] = out.get(k, 0) + v
         return out
 
+    needs_top = True  # the all-to-all exchanges the TOP k local bits: victims must be moved there first
+    min_victim_bit = 0
+
+    def zero_live(self):
+        self.buf.zero_()
+
+    def local_host(self, cplx) -> np.ndarray:
+        return self.buf.cpu().numpy().view(cplx)
+
+    def exchange(self, dist, world, rank, k, victim_bits):
+        """all k rank bits <-> top k local bits: chunk j of this page goes to rank j and lands there as chunk `rank`"""
+        src, dst = self.buf, self.scratch
+        if dist.get_backend() == "nccl":
+            self.engine.be.flush()  # NCCL runs on the same (torch current) stream as the engine: stream order suffices
+            dist.all_to_all_single(dst, src)
+        else:
+            self.engine.Finish()
+            chunk = src.numel() // world
+            reqs = []
+            for peer in range(world):
+                if peer == rank:
+                    dst[peer * chunk:(peer + 1) * chunk].copy_(src[peer * chunk:(peer + 1) * chunk])
+                else:
+                    reqs.append(dist.isend(src[peer * chunk:(peer + 1) * chunk], peer))
+                    reqs.append(dist.irecv(dst[peer * chunk:(peer + 1) * chunk], peer))
+            for r in reqs:
+                r.wait()
+        self.swap()
+        return src.numel() * src.element_size() * (world - 1) // world
+
     def swap(self):
         """the exchange wrote into `scratch`: make it the live page"""
         self.buf, self.scratch = self.scratch, self.buf
@@ -78,6 +108,81 @@ class ShardBuffers:
             self.engine.Finish()
             self._retire()
             self.engine = self.make_engine(self.buf, self.nl)
+
+
+class P2PShardBuffers:
+    """CUDA pages owned by libb200sv (cudaMalloc, exported with CUDA IPC) + the fused NVLink re-page kernel
+    (b200sv_exchange_scatter): the k rank bits are exchanged with ANY k local qubits in one pass that reads the page once
+    and stores straight into the peers' pages — no local pre-permutation, no NCCL staging."""
+
+    needs_top = False
+    min_victim_bit = 8  # keep >= 2 KB contiguous runs per destination
+
+    def __init__(self, n_local: int, precision: int, device_index: int, dist, world: int, rank: int):
+        import ctypes
+        import torch
+        from . import _abi
+        from .qengine import QEngineCUDA
+        self.torch, self.dist, self.world, self.rank = torch, dist, world, rank
+        self.lib = _abi.load()
+        self.abi = _abi
+        self.nl, self.precision, self.dev = n_local, precision, device_index
+        self.device = torch.device("cuda", device_index)
+        self.nbytes = (1 << n_local) * (8 if precision == 32 else 16)
+        self.pages = []
+        for _ in range(2):
+            p = ctypes.c_void_p()
+            _abi.check(self.lib, self.lib.b200sv_alloc_page(device_index, self.nbytes, ctypes.byref(p)))
+            self.pages.append(p.value)
+        # exchange the IPC handles of both pages
+        mine = torch.zeros(2, 64, dtype=torch.uint8)
+        for i, p in enumerate(self.pages):
+            hb = (ctypes.c_ubyte * 64)()
+            _abi.check(self.lib, self.lib.b200sv_ipc_export(device_index, ctypes.c_void_p(p), hb))
+            mine[i] = torch.tensor(list(hb), dtype=torch.uint8)
+        allh = [torch.empty(2, 64, dtype=torch.uint8, device=self.device) for _ in range(world)]
+        dist.all_gather(allh, mine.to(self.device))
+        self.peer_pages = []  # [rank][page] -> device pointer valid in THIS process
+        for r in range(world):
+            if r == rank:
+                self.peer_pages.append(list(self.pages))
+                continue
+            ptrs = []
+            hr = allh[r].cpu()
+            for i in range(2):
+                hb = (ctypes.c_ubyte * 64)(*hr[i].tolist())
+                p = ctypes.c_void_p()
+                _abi.check(self.lib, self.lib.b200sv_ipc_import(device_index, hb, ctypes.byref(p)))
+                ptrs.append(p.value)
+            self.peer_pages.append(ptrs)
+        self.live = 0
+        self.engine = QEngineCUDA.over_buffer(self.pages[0], n_local, device_index, precision, random.Random(1))
+        self.engine.be.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.zero_live()
+        dist.barrier()
+
+    def zero_live(self):
+        self.engine.be.zero()
+
+    def local_host(self, cplx) -> np.ndarray:
+        return self.engine.be.get_state()
+
+    def stats(self) -> dict:
+        return self.engine.be.stats()
+
+    def exchange(self, dist, world, rank, k, victim_bits):
+        import ctypes
+        other = 1 - self.live
+        dst = (ctypes.c_void_p * world)(*[self.peer_pages[r][other] for r in range(world)])
+        vb = (ctypes.c_int * k)(*victim_bits)
+        be = self.engine.be
+        be._ck(self.lib.b200sv_exchange_scatter(be.h, k, vb, rank, dst))
+        # every rank's stores into my `other` page are complete once the stream-ordered barrier has completed everywhere
+        dist.barrier()
+        self.live = other
+        be.rebind_external(self.pages[other])
+        self.engine.runningNorm = REAL1_DEFAULT_ARG
+        return self.nbytes * (world - 1) // world
 
 
 def cuda_engine_factory(device_index: int, precision: int = 32):
@@ -162,13 +267,14 @@ class _ShardedBackend:
 
     def zero(self):
         self.pending.clear()
-        self.shard.buf.zero_()
+        self.loc.Finish()
+        self.shard.zero_live()
 
     def set_permutation(self, perm: int, phase: complex):
         self.pending.clear()
         self.perm = list(range(self.n))
         self.loc.Finish()
-        self.shard.buf.zero_()
+        self.shard.zero_live()
         if (perm >> self.nl) == self.rank:
             self.loc.SetAmplitude(perm & ((1 << self.nl) - 1), phase)
         self.loc.runningNorm = REAL1_DEFAULT_ARG
@@ -228,7 +334,7 @@ class _ShardedBackend:
         lr, gr = self._split(self._pindex(result))
         if (self.rank & gm) != gr:
             self.loc.Finish()
-            self.shard.buf.zero_()
+            self.shard.zero_live()
         elif lm:
             self.loc.be.apply_m(lm, lr, nrm)
         else:
@@ -280,14 +386,14 @@ class _ShardedBackend:
         self.flush()
         self.loc.Finish()
         torch = self.shard.torch
-        local = self.shard.buf
+        mine = np.ascontiguousarray(self.shard.local_host(self.cplx))
         if self.world > 1:
+            local = torch.from_numpy(mine.view(self.real)).to(self.shard.device)
             parts = [torch.empty_like(local) for _ in range(self.world)]
             self.dist.all_gather(parts, local)
-            full = torch.cat(parts)
+            phys = torch.cat(parts).cpu().numpy().view(self.cplx)
         else:
-            full = local
-        phys = full.cpu().numpy().view(self.cplx)
+            phys = mine
         # phys index bit perm[q] holds logical qubit q: transpose the 2^n tensor accordingly
         t = phys.reshape([2] * self.n)  # axis 0 = most significant physical bit (n-1)
         axes = [self.n - 1 - self.perm[q] for q in range(self.n - 1, -1, -1)]
@@ -351,44 +457,29 @@ class _ShardedBackend:
             if not g.diag and g.t in far and far[g.t] > horizon:
                 far[g.t] = j
         # k local logical qubits with the farthest next non-diagonal use (ties: higher physical position = cheaper)
-        victims = sorted(far.keys(), key=lambda q: (-far[q], -self.perm[q]))[:k]
-        top = list(range(nl - k, nl))
-        # step A: bring the victims to the top k local positions with local swaps
-        need = [v for v in victims if self.perm[v] < nl - k]
-        free_top = [p for p in top if inv[p] not in victims]
-        for v, p in zip(need, free_top):
-            pv = self.perm[v]
-            other = inv[p]
-            self.loc.Swap(pv, p)
-            self.local_swaps += 1
-            self.perm[v], self.perm[other] = p, pv
-            inv[p], inv[pv] = v, other
-        # step B: one all-to-all; chunk j of this rank's page goes to rank j and lands there as chunk `rank`
-        if self.dist is not None and self.world > 1 and self.dist.get_backend() == "nccl":
-            self.loc.be.flush()  # NCCL runs on the same (torch current) stream as the engine: stream order suffices
+        lo = self.shard.min_victim_bit
+        cands = [q for q in far if self.perm[q] >= lo] if (nl - lo) >= k else list(far.keys())
+        victims = sorted(cands, key=lambda q: (-far[q], -self.perm[q]))[:k]
+        if self.shard.needs_top:
+            # bring the victims to the top k local positions with local swaps, then exchange bit nl-k+b <-> rank bit b
+            top = list(range(nl - k, nl))
+            need = [v for v in victims if self.perm[v] < nl - k]
+            free_top = [p for p in top if inv[p] not in victims]
+            for v, p in zip(need, free_top):
+                pv = self.perm[v]
+                other = inv[p]
+                self.loc.Swap(pv, p)
+                self.local_swaps += 1
+                self.perm[v], self.perm[other] = p, pv
+                inv[p], inv[pv] = v, other
+            vbits = top
         else:
-            self.loc.Finish()
-        torch = self.shard.torch
-        src, dst = self.shard.buf, self.shard.scratch
+            vbits = sorted(self.perm[v] for v in victims)
         if self.world > 1:
-            if self.dist.get_backend() == "nccl":
-                self.dist.all_to_all_single(dst, src)
-            else:
-                chunk = src.numel() // self.world
-                reqs = []
-                for peer in range(self.world):
-                    if peer == self.rank:
-                        dst[peer * chunk:(peer + 1) * chunk].copy_(src[peer * chunk:(peer + 1) * chunk])
-                    else:
-                        reqs.append(self.dist.isend(src[peer * chunk:(peer + 1) * chunk], peer))
-                        reqs.append(self.dist.irecv(dst[peer * chunk:(peer + 1) * chunk], peer))
-                for r in reqs:
-                    r.wait()
-            self.shard.swap()
-            self.exchange_bytes += src.numel() * src.element_size() * (self.world - 1) // self.world
+            self.exchange_bytes += self.shard.exchange(self.dist, self.world, self.rank, k, vbits)
         self.exchanges += 1
         for b in range(k):
-            pl, pg = nl - k + b, nl + b
+            pl, pg = vbits[b], nl + b
             ql, qg = inv[pl], inv[pg]
             self.perm[ql], self.perm[qg] = pg, pl
             inv[pl], inv[pg] = qg, ql
@@ -399,17 +490,20 @@ class QEngineSharded(QEngineHost):
 
     def __init__(self, qBitCount: int, initState: int = 0, rgp=None, phaseFac=None, doNorm: bool = False,
                  randomGlobalPhase: bool = False, precision: int = 32, dist=None, world: int = 1, rank: int = 0,
-                 device=None, make_engine: Optional[Callable] = None, **kw):
+                 device=None, make_engine: Optional[Callable] = None, p2p: bool = False, **kw):
         if doNorm:
             raise ValueError("QEngineSharded: doNormalize is not supported (QPager forces it off as well)")
         self._dist, self._world, self._rank = dist, world, rank
-        self._device, self._make_engine = device, make_engine
+        self._device, self._make_engine, self._p2p = device, make_engine, p2p
         super().__init__(qBitCount, initState, rgp, 1.0 + 0j if phaseFac is None else phaseFac, False, randomGlobalPhase,
                          precision=precision)
 
     def _make_backend(self, n_qubits: int):
         k = int(round(math.log2(self._world))) if self._world > 1 else 0
-        shard = ShardBuffers(n_qubits - k, self.precision, self._device, self._make_engine)
+        if self._p2p:
+            shard = P2PShardBuffers(n_qubits - k, self.precision, self._device.index, self._dist, self._world, self._rank)
+        else:
+            shard = ShardBuffers(n_qubits - k, self.precision, self._device, self._make_engine)
         return _ShardedBackend(n_qubits, self.precision, shard, self._dist, self._world, self._rank)
 
     def flush(self):

@@ -23,7 +23,7 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, port, text, prec, out_path):
+def _worker(rank, world, port, text, prec, out_path, p2p):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -35,7 +35,7 @@ def _worker(rank, world, port, text, prec, out_path):
 
         def make(n, perm):
             return QEngineSharded(n, perm, random.Random(1), 1.0 + 0j, precision=prec, dist=dist, world=world, rank=rank,
-                                  device=torch.device("cuda", rank), make_engine=cuda_engine_factory(rank, prec))
+                                  device=torch.device("cuda", rank), make_engine=cuda_engine_factory(rank, prec), p2p=p2p)
         regs, results = qscript.run(text, make)
         st = regs[0].GetQuantumState()
         if rank == 0:
@@ -44,8 +44,9 @@ def _worker(rank, world, port, text, prec, out_path):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [False, True], ids=["nccl_all_to_all", "p2p_scatter_kernel"])
 @pytest.mark.parametrize("prec", [32, 64])
-def test_sharded_nccl_matches_oracle(prec, tmp_path):
+def test_sharded_nccl_matches_oracle(prec, p2p, tmp_path):
     world = 2 if _ngpu() < 4 else 4
     if _ngpu() < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -55,7 +56,7 @@ def test_sharded_nccl_matches_oracle(prec, tmp_path):
     out = str(tmp_path / "o.npz")
     for attempt in range(3):  # the rendezvous port can be taken between probing and binding
         try:
-            mp.spawn(_worker, args=(world, _free_port(), text, prec, out), nprocs=world, join=True)
+            mp.spawn(_worker, args=(world, _free_port(), text, prec, out, p2p), nprocs=world, join=True)
             break
         except Exception as e:
             if "EADDRINUSE" not in str(e) or attempt == 2:

@@ -30,9 +30,9 @@ constexpr int MAX_OPS = 96;
 constexpr int MAX_NCH = 16; // register chunks per sub-block (RB <= 4)
 constexpr int MAX_NA = 32;  // register amplitudes per sub-block
 
-// device op codes.  Single-gate ops: kind * 5 + jr (jr = register-bit index of the target).  Bundles: K_LAYER (several
-// uncontrolled non-diagonal 1-qubit gates on distinct register bits) and K_PHGROUP (any number of diagonal gates whose
-// predicate touches at most one register bit).  bit 8 = has a sub-block predicate; bits 16..31 = payload offset (16-B units).
+// device op codes.  Single-gate ops: kind * 5 + jr (jr = register-bit index of the target; dense so that the dispatch is a
+// shallow branch tree).  OPC_LAYER = Hadamard butterflies on several register bits; OPC_SCALE = per-tile scalar.
+// bit 8 = the op has a sub-block predicate.
 enum { K_HAD = 0, K_XSWAP = 1, K_GEN_U = 2, K_GEN_P = 3, K_PHREG1 = 4, K_PHUNI = 5, K_PHGEN = 6 };
 constexpr uint32_t OPC_LAYER = 40U;
 constexpr uint32_t OPC_SCALE = 41U; // multiply every amplitude by the per-tile scalar (outer phases x Hadamard scale)
@@ -50,18 +50,6 @@ template <typename R> struct alignas(16) DevOp {
     uint32_t lvalSb;
     R m[8];           // inline, so that its loads do not wait for the header
 };
-// member of a K_PHGROUP: predicate on the sub-block base only (tile-local bits outside the register set)
-template <typename R> struct DevPhaseMember;
-template <> struct DevPhaseMember<float> { // 16 bytes
-    uint32_t lmaskSb, lvalSb;
-    float ph[2];
-};
-template <> struct DevPhaseMember<double> { // 32 bytes
-    uint32_t lmaskSb, lvalSb;
-    double ph[2];
-    double pad;
-};
-
 struct DevPass {
     int opBegin, opEnd;
     int nsb;                       // number of sub-block index bits
@@ -79,7 +67,6 @@ struct alignas(16) DevSweep {
     int nOps;
     int hasScale;
     double scale;
-    int poolOff;  // byte offset of the payload pool from the start of the program
     int nOuter;   // outer-only phases (DevOuterPhase records at outerOff)
     int outerOff;
     int pad2;   // deferred scalar of the un-normalised Hadamard butterflies, applied once in the last pass
@@ -620,7 +607,7 @@ struct TileCfg {
     int H;    // capacity of high qubits
     int NT;   // threads per CTA
     int maxOps; // ops per sweep (bounded by the shared-memory program area: 3 CTAs/SM must fit)
-    int bundle; // bit 0: LAYER bundles, bit 1: PHGROUP bundles
+    int bundle; // bit 0: merge Hadamards on distinct register bits into one LAYER op
 };
 
 static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref, int NT = 256)
@@ -639,7 +626,7 @@ static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref, int NT = 256
     }
     c.H = c.kA - c.L;
     c.maxOps = MAX_OPS;
-    c.bundle = 3;
+    c.bundle = 1;
     return c;
 }
 
@@ -779,13 +766,7 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
     DevSweep ds;
     memset(&ds, 0, sizeof(ds));
     std::vector<DevOp<R>> dops;
-    std::vector<unsigned char> pool;
     std::vector<DevOuterPhase<R>> outerList;
-    auto pool_alloc = [&](size_t bytes) {
-        const size_t off = pool.size();
-        pool.resize(off + ((bytes + 15U) & ~(size_t)15U), 0);
-        return off;
-    };
     ds.nHigh = (int)sp.highQ.size();
     ds.lowAmpBits = cfg.L;
     ds.kc = kc;
@@ -901,13 +882,7 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
         LayerMember layer[5];
         bool layerUsed[5] = { false, false, false, false, false };
         int layerCount = 0;
-        struct GroupMember {
-            int cls; // 0 scalar, 1+b register bit b
-            DevPhaseMember<R> d;
-        };
-        std::vector<GroupMember> group;
-        uint64_t ndq = 0; // qubits with a non-diagonal layer member in the open bundle
-        uint64_t dq = 0;  // qubits used diagonally by a group member in the open bundle
+        uint64_t ndq = 0; // qubits with a (non-diagonal) layer member in the open bundle
         auto close_bundle = [&]() {
             if (layerCount) {
                 DevOp<R> d;
@@ -926,9 +901,7 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
             for (bool& u : layerUsed) {
                 u = false;
             }
-            group.clear();
             ndq = 0;
-            dq = 0;
         };
         dp.opBegin = (int)dops.size();
         for (const HostOp& hop : pp.ops) {
@@ -947,30 +920,10 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
                     outerList.push_back(op);
                     continue;
                 }
-                const int nreg = __builtin_popcount(lmr);
-                if (false && !(hop.cmask & ~tileMask) && (nreg == 0 || (nreg == 1 && lvr == lmr))) {
-                    // purely tile-local predicate touching at most one register bit: group member
-                    if (hop.cmask & ndq) {
-                        close_bundle();
-                    }
-                    if (group.size() >= 200) {
-                        close_bundle();
-                    }
-                    GroupMember g;
-                    memset(&g, 0, sizeof(g));
-                    g.cls = nreg ? 1 + reg_index(__builtin_ctz(lmr)) : 0;
-                    g.d.lmaskSb = lmask & ~regAmpMask;
-                    g.d.lvalSb = lval & ~regAmpMask;
-                    g.d.ph[0] = (R)hop.m[0];
-                    g.d.ph[1] = (R)hop.m[1];
-                    group.push_back(g);
-                    dq |= hop.cmask;
-                    continue;
-                }
             } else if ((cfg.bundle & 1) && !hop.cmask && hop.kind == OP_HAD) {
                 // uncontrolled non-diagonal 1-qubit gate: layer member
                 const int jr = reg_index(tile_bit(cfg, sp.highQ, hop.tq));
-                if ((bitq(hop.tq) & (ndq | dq)) || layerUsed[jr]) {
+                if ((bitq(hop.tq) & ndq) || layerUsed[jr]) {
                     close_bundle();
                 }
                 layer[jr].kind = (hop.kind == OP_HAD) ? 1 : 2;
@@ -1042,17 +995,13 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
     ds.nOuter = (int)outerList.size();
     const size_t opsBytes = ((dops.size() * sizeof(DevOp<R>)) + 15U) & ~(size_t)15U;
     const size_t outerBytes = ((outerList.size() * sizeof(DevOuterPhase<R>)) + 15U) & ~(size_t)15U;
-    ds.poolOff = (int)(sizeof(DevSweep) + opsBytes);
-    ds.outerOff = (int)(sizeof(DevSweep) + opsBytes + pool.size());
+    ds.outerOff = (int)(sizeof(DevSweep) + opsBytes);
     const size_t start = buf.size();
-    const size_t bytes = ((sizeof(DevSweep) + opsBytes + pool.size() + outerBytes) + 15U) & ~(size_t)15U;
+    const size_t bytes = ((sizeof(DevSweep) + opsBytes + outerBytes) + 15U) & ~(size_t)15U;
     buf.resize(start + bytes, 0);
     memcpy(buf.data() + start, &ds, sizeof(ds));
     if (!dops.empty()) {
         memcpy(buf.data() + start + sizeof(DevSweep), dops.data(), dops.size() * sizeof(DevOp<R>));
-    }
-    if (!pool.empty()) {
-        memcpy(buf.data() + start + ds.poolOff, pool.data(), pool.size());
     }
     if (!outerList.empty()) {
         memcpy(buf.data() + start + ds.outerOff, outerList.data(), outerList.size() * sizeof(DevOuterPhase<R>));
@@ -1174,7 +1123,7 @@ struct FusedKnobs {
     int L32 = 6;
     int L64 = 6;
     int RB64 = 3; // fp64: 8 double2 amplitudes per sub-block keep 3 CTAs/SM resident
-    int bundle = 3; // bit 0: LAYER bundles, bit 1: PHGROUP bundles
+    int bundle = 1; // bit 0: merge Hadamards on distinct register bits into one LAYER op
 };
 static const FusedKnobs& knobs()
 {
@@ -1182,7 +1131,7 @@ static const FusedKnobs& knobs()
         FusedKnobs v;
         const char* e = getenv("B200SV_FUSED");
         if (e) {
-            int rb = 0, l32 = 0, l64 = 0, bn = 3, rb64 = 0;
+            int rb = 0, l32 = 0, l64 = 0, bn = 1, rb64 = 0;
             const int got = sscanf(e, "%d,%d,%d,%d,%d", &rb, &l32, &l64, &bn, &rb64);
             if (got >= 4) {
                 v.bundle = bn;

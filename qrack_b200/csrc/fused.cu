@@ -69,7 +69,8 @@ struct alignas(16) DevSweep {
     double scale;
     int nOuter;   // outer-only phases (DevOuterPhase records at outerOff)
     int outerOff;
-    int pad2;   // deferred scalar of the un-normalised Hadamard butterflies, applied once in the last pass
+    int prefetch; // 1: pull the CTA's next tile into L2 while this one is being computed
+    // scale: deferred scalar of the un-normalised Hadamard butterflies, applied once in the last pass
     uint64_t highLow[MAX_HIGH]; // (2^q - 1) for push_apart of the tile base, ascending
     uint64_t highPow[MAX_HIGH]; // 2^q
     DevPass pass[MAX_PASS];
@@ -341,6 +342,15 @@ template <typename R> struct DevOuterPhase {
     R pad[(sizeof(R) == 4) ? 2 : 2];
 };
 
+constexpr int MAX_OUTER = 64;
+// The whole sweep program as ONE kernel parameter (constant bank): op headers, matrices and pass descriptors are read with
+// LDC/ULDC and decoded on the uniform datapath instead of through shared memory and vector registers.
+template <typename R> struct alignas(16) ProgParam {
+    DevSweep sw;
+    DevOp<R> ops[MAX_OPS];
+    DevOuterPhase<R> outer[MAX_OUTER];
+};
+
 template <typename R, int KC, int RB, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
     k_fused_sweep(typename Cx<R>::type* __restrict__ psi, const unsigned char* __restrict__ prog, uint32_t progBytes, uint64_t nTiles)
@@ -464,6 +474,18 @@ __global__ void __launch_bounds__(NT, MINB)
             }
         }
         __syncthreads();
+        if (sw.prefetch && (t + gridDim.x < nTiles) && mover && ((tid & 7) == 0)) {
+            // one 128-byte line per 8 movers: the next tile of this CTA streams into L2 under the passes below
+            uint64_t nb = (t + gridDim.x) << sw.lowAmpBits;
+            for (int h = 0; h < sw.nHigh; ++h) {
+                const uint64_t lo = nb & sw.highLow[h];
+                nb = ((nb ^ lo) << 1) | lo;
+            }
+            const C* np = psi + nb + tOff;
+            for (uint32_t u = 0; u < nU; ++u) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(np + uOff[u]));
+            }
+        }
         // ---- passes ----------------------------------------------------------------------------------------------
         for (int p = 0; p < sw.nPass; ++p) {
             const DevPass& ps = sw.pass[p];
@@ -485,6 +507,216 @@ __global__ void __launch_bounds__(NT, MINB)
             for (int w = 0; w < 3; ++w) {
                 const int lo = ps.opBegin - 32 * w, hi = ps.opEnd - 32 * w;
                 uint32_t m = ballots[w];
+                m = (lo > 0) ? ((lo >= 32) ? 0U : (m & (0xffffffffU << lo))) : m;
+                m = (hi < 32) ? ((hi <= 0) ? 0U : (m & (0xffffffffU >> (32 - hi)))) : m;
+                pm[w] = m;
+            }
+            const int wBegin = ps.opBegin >> 5, wEnd = (ps.opEnd > ps.opBegin) ? ((ps.opEnd - 1) >> 5) : (wBegin - 1);
+            for (int it = 0; it < ps.nIt; ++it) {
+                if ((uint32_t)(it * NT + tid) >= nSub) {
+                    break;
+                }
+                const uint32_t sbc = dep | ps.itoffC[it];
+                const uint32_t swb = swz(sbc) << 4;
+                A a[NA];
+#pragma unroll
+                for (int e = 0; e < NCH; ++e) {
+                    const Chunk c = *reinterpret_cast<const Chunk*>(tileB + (swb ^ po[e]));
+                    O::get(c, &a[e * APC]);
+                }
+                const uint32_t xsb = sbc * APC;
+#pragma unroll 1
+                for (int w = wBegin; w <= wEnd; ++w) {
+                    uint32_t m = (w == 0) ? pm[0] : ((w == 1) ? pm[1] : pm[2]);
+                    while (m) {
+                        const int o = 32 * w + __ffs(m) - 1;
+                        m &= m - 1U;
+                        exec_op<R, NA>(a, ops[o], xsb, tileScale);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NCH; ++e) {
+                    *reinterpret_cast<Chunk*>(tileB + (swb ^ po[e])) = O::put(&a[e * APC]);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- store: swizzled smem -> global ------------------------------------------------------------------------
+        if (mover) {
+            uint4* gp = reinterpret_cast<uint4*>(psi + base + tOff);
+            if (nU == NU) {
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    st_stream(reinterpret_cast<uint4*>(reinterpret_cast<C*>(gp) + uOff[u]),
+                        *reinterpret_cast<const uint4*>(tSlot + (size_t)u * NT * 16));
+                }
+            } else {
+                for (uint32_t u = 0; u < nU; ++u) {
+                    st_stream(reinterpret_cast<uint4*>(reinterpret_cast<C*>(gp) + uOff[u]),
+                        *reinterpret_cast<const uint4*>(tSlot + (size_t)u * NT * 16));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename R, int KC, int RB, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+    k_fused_sweep_cp(typename Cx<R>::type* __restrict__ psi, const __grid_constant__ ProgParam<R> prog, uint64_t nTiles)
+{
+    typedef typename Cx<R>::type C;
+    typedef AmpOps<R> O;
+    typedef typename O::A A;
+    typedef typename O::Chunk Chunk;
+    constexpr int APC = O::APC;
+    constexpr int NCH = 1 << RB;
+    constexpr int NA = NCH * APC;
+    static_assert(NA <= MAX_NA && NCH <= MAX_NCH, "register sub-block too large");
+    static_assert(NT >= 128, "the per-tile preamble uses warps 0..3");
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* tileB = smem;
+    __shared__ uint64_t uOff[(1 << KC) / NT];
+    __shared__ R tileScale[2];
+
+    const int tid = threadIdx.x;
+    const DevSweep& sw = prog.sw;
+    const DevOp<R>* ops = prog.ops;
+    const int kc = sw.kc;
+    const uint32_t nChunk = 1U << kc;
+    const int lcb = sw.lowAmpBits - (APC == 2 ? 1 : 0); // low (contiguous) chunk bits
+    const uint32_t colMask = (1U << lcb) - 1U;
+    // global amplitude offset of each chunk row (depends only on the sweep's high qubits); the tile area is free
+    // scratch until the first load
+    uint64_t* rowOff = reinterpret_cast<uint64_t*>(smem);
+    for (uint32_t r = tid; r < (nChunk >> lcb); r += NT) {
+        uint64_t off = 0;
+        for (int h = 0; h < sw.nHigh; ++h) {
+            if ((r >> h) & 1U) {
+                off |= sw.highPow[h];
+            }
+        }
+        rowOff[r] = off;
+    }
+    __syncthreads();
+    // Thread `tid` moves chunks c = tid + NT*u.  Because NT is a power of two, the global offset of chunk c separates
+    // into a per-thread part and a per-iteration (uniform) part, and the swizzled smem slot is swz(tid) + NT*u.
+    constexpr int NU = (1 << KC) / NT; // chunks per thread for a full tile
+    if (tid < NU) {
+        const uint32_t cu = (uint32_t)tid * NT;
+        uOff[tid] = (cu < nChunk) ? rowOff[cu >> lcb] + (uint64_t)(cu & colMask) * APC : 0;
+    }
+    const uint32_t nU = (nChunk >= (uint32_t)NT) ? (nChunk / NT) : 1U; // iterations actually needed
+    const bool mover = (uint32_t)tid < nChunk;
+    const uint64_t tOff = mover ? rowOff[(uint32_t)tid >> lcb] + (uint64_t)((uint32_t)tid & colMask) * APC : 0;
+    unsigned char* const tSlot = tileB + ((size_t)swz((uint32_t)tid) << 4);
+    __syncthreads();
+    const uint32_t nSub = nChunk >> RB;
+    const int nOps = sw.nOps;
+    const int nOuter = sw.nOuter;
+    const DevOuterPhase<R>* outer = prog.outer;
+
+    for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
+        uint64_t base = t << sw.lowAmpBits;
+        for (int h = 0; h < sw.nHigh; ++h) {
+            const uint64_t lo = base & sw.highLow[h];
+            base = ((base ^ lo) << 1) | lo;
+        }
+        // ---- per-tile preamble ---------------------------------------------------------------------------------------
+        // every warp: which ops act on this tile (predicates on qubits outside the tile are uniform per tile) -> three
+        // warp-uniform ballot words; warp 3 additionally folds the outer-only phases into the per-tile scalar
+        uint32_t act[3];
+        {
+            const int lane = tid & 31;
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const int o = 32 * w + lane;
+                bool a = false;
+                if (o < nOps) {
+                    a = (base & ops[o].omask) == ops[o].oval;
+                }
+                act[w] = __ballot_sync(0xffffffffU, a);
+            }
+        }
+        if (tid >= 96 && tid < 128) {
+            R fx = (R)1, fy = (R)0;
+            for (int i = tid - 96; i < nOuter; i += 32) {
+                if ((base & outer[i].omask) == outer[i].oval) {
+                    const R px = outer[i].ph[0], py = outer[i].ph[1];
+                    const R nx = fx * px - fy * py;
+                    fy = fx * py + fy * px;
+                    fx = nx;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const R ox = __shfl_xor_sync(0xffffffffU, fx, d), oy = __shfl_xor_sync(0xffffffffU, fy, d);
+                const R nx = fx * ox - fy * oy;
+                fy = fx * oy + fy * ox;
+                fx = nx;
+            }
+            if (tid == 96) {
+                tileScale[0] = fx * (R)sw.scale;
+                tileScale[1] = fy * (R)sw.scale;
+            }
+        }
+        // ---- load: global -> swizzled smem ----------------------------------------------------------------------
+        if (mover) {
+            const uint4* gp = reinterpret_cast<const uint4*>(psi + base + tOff);
+            if (nU == NU) {
+#pragma unroll
+                for (int u0 = 0; u0 < NU; u0 += 8) {
+                    uint4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        v[u] = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const C*>(gp) + uOff[u0 + u]));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        *reinterpret_cast<uint4*>(tSlot + (size_t)(u0 + u) * NT * 16) = v[u];
+                    }
+                }
+            } else {
+                for (uint32_t u = 0; u < nU; ++u) {
+                    *reinterpret_cast<uint4*>(tSlot + (size_t)u * NT * 16) =
+                        ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const C*>(gp) + uOff[u]));
+                }
+            }
+        }
+        __syncthreads();
+        if (sw.prefetch && (t + gridDim.x < nTiles) && mover && ((tid & 7) == 0)) {
+            // one 128-byte line per 8 movers: the next tile of this CTA streams into L2 under the passes below
+            uint64_t nb = (t + gridDim.x) << sw.lowAmpBits;
+            for (int h = 0; h < sw.nHigh; ++h) {
+                const uint64_t lo = nb & sw.highLow[h];
+                nb = ((nb ^ lo) << 1) | lo;
+            }
+            const C* np = psi + nb + tOff;
+            for (uint32_t u = 0; u < nU; ++u) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(np + uOff[u]));
+            }
+        }
+        // ---- passes ----------------------------------------------------------------------------------------------
+        for (int p = 0; p < sw.nPass; ++p) {
+            const DevPass& ps = sw.pass[p];
+            uint32_t po[NCH];
+#pragma unroll
+            for (int e = 0; e < NCH; ++e) {
+                po[e] = ps.pswzB[e];
+            }
+            uint32_t dep = 0;
+            {
+                const int nb = ps.nsb < 8 ? ps.nsb : 8;
+                for (int i = 0; i < nb; ++i) {
+                    dep |= ((tid >> i) & 1U) << ps.sbit[i];
+                }
+            }
+            // active ops of this pass as (up to 3) 32-bit words
+            uint32_t pm[3];
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const int lo = ps.opBegin - 32 * w, hi = ps.opEnd - 32 * w;
+                uint32_t m = act[w];
                 m = (lo > 0) ? ((lo >= 32) ? 0U : (m & (0xffffffffU << lo))) : m;
                 m = (hi < 32) ? ((hi <= 0) ? 0U : (m & (0xffffffffU >> (32 - hi)))) : m;
                 pm[w] = m;
@@ -752,6 +984,7 @@ static int tile_bit(const TileCfg& cfg, const std::vector<int>& highQ, int q)
 // Encoded size limits of one sweep program (must fit beside the tile in shared memory with 3 CTAs/SM)
 constexpr size_t MAX_PROG_BYTES = 7168;
 
+static int knob_prefetch();
 template <typename R> static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<unsigned char>& buf)
 {
     const int kc = cfg.kA - cfg.apcLog;
@@ -909,7 +1142,7 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
             local_pred(hop, lmask, lval);
             const uint32_t lmr = lmask & regAmpMask, lvr = lval & regAmpMask;
             if (hop.kind == OP_PHASE) {
-                if (!(hop.cmask & tileMask)) {
+                if (!(hop.cmask & tileMask) && outerList.size() < (size_t)MAX_OUTER) {
                     // every qubit of the predicate is outside the tile: uniform per tile, commutes with the whole sweep
                     DevOuterPhase<R> op;
                     memset(&op, 0, sizeof(op));
@@ -990,6 +1223,25 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
         dp.opEnd = (int)dops.size();
     }
     ds.scale = scale;
+    if (getenv("B200SV_FUSED_DEBUG")) {
+        static const char* names[] = { "HAD", "XSWAP", "GEN_U", "GEN_P", "PHREG1", "PHUNI", "PHGEN" };
+        for (int p = 0; p < ds.nPass; ++p) {
+            fprintf(stderr, "  pass %d:", p);
+            for (int o = ds.pass[p].opBegin; o < ds.pass[p].opEnd; ++o) {
+                const uint32_t c = dops[o].code & 0xffU;
+                if (c == OPC_LAYER) {
+                    fprintf(stderr, " LAYER(%x)", dops[o].emask);
+                } else if (c == OPC_SCALE) {
+                    fprintf(stderr, " SCALE");
+                } else {
+                    fprintf(stderr, " %s.%u%s%s", names[c / 5U], c % 5U, (dops[o].code & CODE_HAS_SB) ? "s" : "", dops[o].omask ? "o" : "");
+                }
+            }
+            fprintf(stderr, "\n");
+        }
+        fprintf(stderr, "  sweep: %d ops, %d outer phases\n", (int)dops.size(), (int)outerList.size());
+    }
+    ds.prefetch = knob_prefetch();
     ds.hasScale = (scale != 1.0 || !outerList.empty()) ? 1 : 0;
     ds.nOps = (int)dops.size();
     ds.nOuter = (int)outerList.size();
@@ -1117,13 +1369,37 @@ static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes
     return B200SV_OK;
 }
 
+template <typename R, int KC, int RB, int NT, int MINB>
+static int launch_sweep_cp(State* s, const unsigned char* hprog, uint64_t nTiles)
+{
+    auto kern = k_fused_sweep_cp<R, KC, RB, NT, MINB>;
+    static unsigned long long attr_set_mask = 0; // per device: the attribute is per-context
+    if (!(attr_set_mask & (1ULL << s->dev))) {
+        SV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)16 << KC)));
+        attr_set_mask |= 1ULL << s->dev;
+    }
+    // unpack the encoded program [DevSweep][ops][outer phases] into the parameter block
+    static thread_local ProgParam<R> pp;
+    const DevSweep* ds = reinterpret_cast<const DevSweep*>(hprog);
+    pp.sw = *ds;
+    memcpy(pp.ops, hprog + sizeof(DevSweep), (size_t)ds->nOps * sizeof(DevOp<R>));
+    memcpy(pp.outer, hprog + ds->outerOff, (size_t)ds->nOuter * sizeof(DevOuterPhase<R>));
+    const uint64_t maxGrid = (uint64_t)sm_count(s->dev) * MINB;
+    const unsigned grid = (unsigned)std::min<uint64_t>(nTiles, maxGrid);
+    kern<<<grid, NT, (size_t)16 << KC, s->stream>>>(reinterpret_cast<typename Cx<R>::type*>(s->amps), pp, nTiles);
+    SV_CUDA(cudaGetLastError());
+    return B200SV_OK;
+}
+
 // tuning knobs (env B200SV_FUSED="RB,L32,L64"): register chunk bits per pass and the contiguous-run length (low tile bits)
 struct FusedKnobs {
     int RB = 4;   // measured on B200 (profiles/r1_tuning.md): RB=4/L=6 beats RB=3/L=7 by ~12% on the 30-qubit H/T/CNOT circuit
     int L32 = 6;
     int L64 = 6;
     int RB64 = 3; // fp64: 8 double2 amplitudes per sub-block keep 3 CTAs/SM resident
+    int cp = 0;   // 1: sweep program travels as a kernel parameter (constant bank); 0: device arena + shared-memory copy (measured 1.5 % faster)
     int bundle = 1; // bit 0: merge Hadamards on distinct register bits into one LAYER op
+    int pf = 0;     // 1: L2 prefetch of the CTA's next tile during the passes
 };
 static const FusedKnobs& knobs()
 {
@@ -1131,8 +1407,14 @@ static const FusedKnobs& knobs()
         FusedKnobs v;
         const char* e = getenv("B200SV_FUSED");
         if (e) {
-            int rb = 0, l32 = 0, l64 = 0, bn = 1, rb64 = 0;
-            const int got = sscanf(e, "%d,%d,%d,%d,%d", &rb, &l32, &l64, &bn, &rb64);
+            int rb = 0, l32 = 0, l64 = 0, bn = 1, rb64 = 0, cp = 0, pf = 0;
+            const int got = sscanf(e, "%d,%d,%d,%d,%d,%d,%d", &rb, &l32, &l64, &bn, &rb64, &cp, &pf);
+            if (got >= 7) {
+                v.pf = pf;
+            }
+            if (got >= 6) {
+                v.cp = cp;
+            }
             if (got >= 4) {
                 v.bundle = bn;
             }
@@ -1153,6 +1435,7 @@ static const FusedKnobs& knobs()
     }();
     return k;
 }
+static int knob_prefetch() { return knobs().pf; }
 constexpr int FUSED_KC = 12;
 constexpr int FUSED_NT = 256;
 
@@ -1195,6 +1478,30 @@ int fused_flush(State* s)
         SV_TRY(plan_and_encode(pending, cfg, s->prec, buf, &bytes, &nops, &npass));
         segs.push_back({ off, bytes });
     }
+    const uint64_t nTiles = s->dim() >> cfg.kA;
+    if (knobs().cp) {
+        for (size_t i = 0; i < segs.size(); ++i) {
+            const unsigned char* hp = buf.data() + segs[i].first;
+            if (s->prec == 32) {
+                if (cfg.RB == 4) {
+                    SV_TRY((launch_sweep_cp<float, FUSED_KC, 4, FUSED_NT, 2>(s, hp, nTiles)));
+                } else {
+                    SV_TRY((launch_sweep_cp<float, FUSED_KC, 3, FUSED_NT, 3>(s, hp, nTiles)));
+                }
+            } else {
+                if (cfg.RB == 4) {
+                    SV_TRY((launch_sweep_cp<double, FUSED_KC, 4, FUSED_NT, 2>(s, hp, nTiles)));
+                } else {
+                    SV_TRY((launch_sweep_cp<double, FUSED_KC, 3, FUSED_NT, 3>(s, hp, nTiles)));
+                }
+            }
+            s->stats.kernel_launches++;
+            s->stats.fused_sweeps++;
+            s->stats.bytes_swept += 2ULL * s->dim() * s->amp_bytes();
+        }
+        s->stats.fused_gates += nGates;
+        return B200SV_OK;
+    }
     if (ar->pending) {
         SV_CUDA(cudaEventSynchronize(ar->done));
         ar->pending = false;
@@ -1210,7 +1517,6 @@ int fused_flush(State* s)
     }
     memcpy(ar->host, buf.data(), buf.size());
     SV_CUDA(cudaMemcpyAsync(ar->dev, ar->host, buf.size(), cudaMemcpyHostToDevice, s->stream));
-    const uint64_t nTiles = s->dim() >> cfg.kA;
     for (size_t i = 0; i < segs.size(); ++i) {
         const unsigned char* dp = ar->dev + segs[i].first;
         const uint32_t pb = (uint32_t)segs[i].second;
@@ -1261,6 +1567,10 @@ int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targ
             g.m[4] = 0.8;
             g.m[6] = -0.6;
             g.m[1] = (kinds[i] == 3) ? 0.1 : 0.0; // kind 3: complex general
+            if (kinds[i] == 4) { // exact Hadamard
+                g.m[0] = g.m[2] = g.m[4] = 0.70710678118654752440;
+                g.m[6] = -g.m[0];
+            }
         }
     }
     std::vector<HostOp> pending;

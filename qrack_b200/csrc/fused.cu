@@ -27,6 +27,8 @@ namespace b200sv {
 constexpr int MAX_HIGH = 8;
 constexpr int MAX_PASS = 12;
 constexpr int MAX_OPS = 96;
+constexpr int MAX_HOST_OPS = 384; // gates per sweep before merging (LAYER / DIAG groups shrink them to <= MAX_OPS device ops)
+constexpr int MAX_SLOTS = 128; // per-tile phase table (1 + register-bit phases of the DIAG ops); filled by warps 4..7
 constexpr int MAX_NCH = 16; // register chunks per sub-block (RB <= 4)
 constexpr int MAX_NA = 32;  // register amplitudes per sub-block
 
@@ -35,7 +37,7 @@ constexpr int MAX_NA = 32;  // register amplitudes per sub-block
 // bit 8 = the op has a sub-block predicate.
 enum { K_HAD = 0, K_XSWAP = 1, K_GEN_U = 2, K_GEN_P = 3, K_PHREG1 = 4, K_PHUNI = 5, K_PHGEN = 6 };
 constexpr uint32_t OPC_LAYER = 40U;
-constexpr uint32_t OPC_SCALE = 41U; // multiply every amplitude by the per-tile scalar (outer phases x Hadamard scale)
+constexpr uint32_t OPC_SCALE = 41, OPC_DIAG = 42U; // multiply every amplitude by the per-tile scalar (outer phases x Hadamard scale)
 constexpr uint32_t CODE_HAS_SB = 0x100U;
 // host (scheduler) op kinds
 enum { OP_GENERAL = 0, OP_HAD = 1, OP_XSWAP = 2, OP_PHASE = 3 };
@@ -71,6 +73,9 @@ struct alignas(16) DevSweep {
     int outerOff;
     int prefetch; // 1: pull the CTA's next tile into L2 while this one is being computed
     // scale: deferred scalar of the un-normalised Hadamard butterflies, applied once in the last pass
+    int nSlots;   // per-tile phase table entries: slot 0 = tile scalar, slots 1.. = register-bit phases of the DIAG ops
+    int pad3[3];
+    unsigned short slotBeg[MAX_SLOTS + 1]; // slot s multiplies the outer records [slotBeg[s], slotBeg[s+1])
     uint64_t highLow[MAX_HIGH]; // (2^q - 1) for push_apart of the tile base, ascending
     uint64_t highPow[MAX_HIGH]; // 2^q
     DevPass pass[MAX_PASS];
@@ -298,6 +303,24 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         SV_LAYER_BIT(4)
 #undef SV_LAYER_BIT
     } break;
+    case OPC_DIAG: {
+        // per-tile phases on several register bits (hd.y = mask of register bits, hd.z = first table slot); each phase
+        // is the product of the group's members whose outer predicate holds for this tile, 1 if none does
+#define SV_DIAG_BIT(J)                                                                                                 \
+    if (((1 << (J)) < NA) && ((hd.y >> (J)) & 1U)) {                                                                   \
+        const R* tp2 = tileScale + 2U * (hd.z + __popc(hd.y & ((1U << (J)) - 1U)));                                    \
+        const R px = tp2[0], py = tp2[1];                                                                              \
+        if (px != (R)1 || py != (R)0) {                                                                                \
+            app_phase_reg<R, SV_J(J), NA>(a, O::mkph(px, py));                                                         \
+        }                                                                                                              \
+    }
+        SV_DIAG_BIT(0)
+        SV_DIAG_BIT(1)
+        SV_DIAG_BIT(2)
+        SV_DIAG_BIT(3)
+        SV_DIAG_BIT(4)
+#undef SV_DIAG_BIT
+    } break;
     case OPC_SCALE: {
         const typename O::Ph sc = O::mkph(tileScale[0], tileScale[1]);
 #pragma unroll
@@ -343,13 +366,6 @@ template <typename R> struct DevOuterPhase {
 };
 
 constexpr int MAX_OUTER = 64;
-// The whole sweep program as ONE kernel parameter (constant bank): op headers, matrices and pass descriptors are read with
-// LDC/ULDC and decoded on the uniform datapath instead of through shared memory and vector registers.
-template <typename R> struct alignas(16) ProgParam {
-    DevSweep sw;
-    DevOp<R> ops[MAX_OPS];
-    DevOuterPhase<R> outer[MAX_OUTER];
-};
 
 template <typename R, int KC, int RB, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
@@ -363,13 +379,13 @@ __global__ void __launch_bounds__(NT, MINB)
     constexpr int NCH = 1 << RB;
     constexpr int NA = NCH * APC;
     static_assert(NA <= MAX_NA && NCH <= MAX_NCH, "register sub-block too large");
-    static_assert(NT >= 128, "the per-tile preamble uses warps 0..3");
+    static_assert(NT >= 128 + MAX_SLOTS, "the per-tile preamble uses warps 0..3 and one thread per table slot");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* tileB = smem;
     unsigned char* sprog = smem + ((size_t)16 << KC);
     __shared__ uint64_t uOff[(1 << KC) / NT];
     __shared__ uint32_t ballots[4];
-    __shared__ R tileScale[2];
+    __shared__ R tileScale[2 * MAX_SLOTS]; // [0..1] tile scalar, then the DIAG register-bit phases
 
     const int tid = threadIdx.x;
     for (uint32_t i = tid; i < progBytes / 16; i += NT) {
@@ -449,6 +465,20 @@ __global__ void __launch_bounds__(NT, MINB)
                 tileScale[0] = fx * (R)sw.scale;
                 tileScale[1] = fy * (R)sw.scale;
             }
+        } else if (tid - 127 < sw.nSlots) {
+            // one thread per DIAG table slot: product (in double) of the member phases that fire for this tile
+            const int sl = tid - 127;
+            double fx = 1.0, fy = 0.0;
+            for (int i = sw.slotBeg[sl], e = sw.slotBeg[sl + 1]; i < e; ++i) {
+                const DevOuterPhase<R>& op = outer[i];
+                if ((base & op.omask) == op.oval) {
+                    const double nx = fx * (double)op.ph[0] - fy * (double)op.ph[1];
+                    fy = fx * (double)op.ph[1] + fy * (double)op.ph[0];
+                    fx = nx;
+                }
+            }
+            tileScale[2 * sl] = (R)fx;
+            tileScale[2 * sl + 1] = (R)fy;
         }
         // ---- load: global -> swizzled smem ----------------------------------------------------------------------
         if (mover) {
@@ -507,216 +537,6 @@ __global__ void __launch_bounds__(NT, MINB)
             for (int w = 0; w < 3; ++w) {
                 const int lo = ps.opBegin - 32 * w, hi = ps.opEnd - 32 * w;
                 uint32_t m = ballots[w];
-                m = (lo > 0) ? ((lo >= 32) ? 0U : (m & (0xffffffffU << lo))) : m;
-                m = (hi < 32) ? ((hi <= 0) ? 0U : (m & (0xffffffffU >> (32 - hi)))) : m;
-                pm[w] = m;
-            }
-            const int wBegin = ps.opBegin >> 5, wEnd = (ps.opEnd > ps.opBegin) ? ((ps.opEnd - 1) >> 5) : (wBegin - 1);
-            for (int it = 0; it < ps.nIt; ++it) {
-                if ((uint32_t)(it * NT + tid) >= nSub) {
-                    break;
-                }
-                const uint32_t sbc = dep | ps.itoffC[it];
-                const uint32_t swb = swz(sbc) << 4;
-                A a[NA];
-#pragma unroll
-                for (int e = 0; e < NCH; ++e) {
-                    const Chunk c = *reinterpret_cast<const Chunk*>(tileB + (swb ^ po[e]));
-                    O::get(c, &a[e * APC]);
-                }
-                const uint32_t xsb = sbc * APC;
-#pragma unroll 1
-                for (int w = wBegin; w <= wEnd; ++w) {
-                    uint32_t m = (w == 0) ? pm[0] : ((w == 1) ? pm[1] : pm[2]);
-                    while (m) {
-                        const int o = 32 * w + __ffs(m) - 1;
-                        m &= m - 1U;
-                        exec_op<R, NA>(a, ops[o], xsb, tileScale);
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < NCH; ++e) {
-                    *reinterpret_cast<Chunk*>(tileB + (swb ^ po[e])) = O::put(&a[e * APC]);
-                }
-            }
-            __syncthreads();
-        }
-        // ---- store: swizzled smem -> global ------------------------------------------------------------------------
-        if (mover) {
-            uint4* gp = reinterpret_cast<uint4*>(psi + base + tOff);
-            if (nU == NU) {
-#pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    st_stream(reinterpret_cast<uint4*>(reinterpret_cast<C*>(gp) + uOff[u]),
-                        *reinterpret_cast<const uint4*>(tSlot + (size_t)u * NT * 16));
-                }
-            } else {
-                for (uint32_t u = 0; u < nU; ++u) {
-                    st_stream(reinterpret_cast<uint4*>(reinterpret_cast<C*>(gp) + uOff[u]),
-                        *reinterpret_cast<const uint4*>(tSlot + (size_t)u * NT * 16));
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-template <typename R, int KC, int RB, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-    k_fused_sweep_cp(typename Cx<R>::type* __restrict__ psi, const __grid_constant__ ProgParam<R> prog, uint64_t nTiles)
-{
-    typedef typename Cx<R>::type C;
-    typedef AmpOps<R> O;
-    typedef typename O::A A;
-    typedef typename O::Chunk Chunk;
-    constexpr int APC = O::APC;
-    constexpr int NCH = 1 << RB;
-    constexpr int NA = NCH * APC;
-    static_assert(NA <= MAX_NA && NCH <= MAX_NCH, "register sub-block too large");
-    static_assert(NT >= 128, "the per-tile preamble uses warps 0..3");
-    extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* tileB = smem;
-    __shared__ uint64_t uOff[(1 << KC) / NT];
-    __shared__ R tileScale[2];
-
-    const int tid = threadIdx.x;
-    const DevSweep& sw = prog.sw;
-    const DevOp<R>* ops = prog.ops;
-    const int kc = sw.kc;
-    const uint32_t nChunk = 1U << kc;
-    const int lcb = sw.lowAmpBits - (APC == 2 ? 1 : 0); // low (contiguous) chunk bits
-    const uint32_t colMask = (1U << lcb) - 1U;
-    // global amplitude offset of each chunk row (depends only on the sweep's high qubits); the tile area is free
-    // scratch until the first load
-    uint64_t* rowOff = reinterpret_cast<uint64_t*>(smem);
-    for (uint32_t r = tid; r < (nChunk >> lcb); r += NT) {
-        uint64_t off = 0;
-        for (int h = 0; h < sw.nHigh; ++h) {
-            if ((r >> h) & 1U) {
-                off |= sw.highPow[h];
-            }
-        }
-        rowOff[r] = off;
-    }
-    __syncthreads();
-    // Thread `tid` moves chunks c = tid + NT*u.  Because NT is a power of two, the global offset of chunk c separates
-    // into a per-thread part and a per-iteration (uniform) part, and the swizzled smem slot is swz(tid) + NT*u.
-    constexpr int NU = (1 << KC) / NT; // chunks per thread for a full tile
-    if (tid < NU) {
-        const uint32_t cu = (uint32_t)tid * NT;
-        uOff[tid] = (cu < nChunk) ? rowOff[cu >> lcb] + (uint64_t)(cu & colMask) * APC : 0;
-    }
-    const uint32_t nU = (nChunk >= (uint32_t)NT) ? (nChunk / NT) : 1U; // iterations actually needed
-    const bool mover = (uint32_t)tid < nChunk;
-    const uint64_t tOff = mover ? rowOff[(uint32_t)tid >> lcb] + (uint64_t)((uint32_t)tid & colMask) * APC : 0;
-    unsigned char* const tSlot = tileB + ((size_t)swz((uint32_t)tid) << 4);
-    __syncthreads();
-    const uint32_t nSub = nChunk >> RB;
-    const int nOps = sw.nOps;
-    const int nOuter = sw.nOuter;
-    const DevOuterPhase<R>* outer = prog.outer;
-
-    for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
-        uint64_t base = t << sw.lowAmpBits;
-        for (int h = 0; h < sw.nHigh; ++h) {
-            const uint64_t lo = base & sw.highLow[h];
-            base = ((base ^ lo) << 1) | lo;
-        }
-        // ---- per-tile preamble ---------------------------------------------------------------------------------------
-        // every warp: which ops act on this tile (predicates on qubits outside the tile are uniform per tile) -> three
-        // warp-uniform ballot words; warp 3 additionally folds the outer-only phases into the per-tile scalar
-        uint32_t act[3];
-        {
-            const int lane = tid & 31;
-#pragma unroll
-            for (int w = 0; w < 3; ++w) {
-                const int o = 32 * w + lane;
-                bool a = false;
-                if (o < nOps) {
-                    a = (base & ops[o].omask) == ops[o].oval;
-                }
-                act[w] = __ballot_sync(0xffffffffU, a);
-            }
-        }
-        if (tid >= 96 && tid < 128) {
-            R fx = (R)1, fy = (R)0;
-            for (int i = tid - 96; i < nOuter; i += 32) {
-                if ((base & outer[i].omask) == outer[i].oval) {
-                    const R px = outer[i].ph[0], py = outer[i].ph[1];
-                    const R nx = fx * px - fy * py;
-                    fy = fx * py + fy * px;
-                    fx = nx;
-                }
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                const R ox = __shfl_xor_sync(0xffffffffU, fx, d), oy = __shfl_xor_sync(0xffffffffU, fy, d);
-                const R nx = fx * ox - fy * oy;
-                fy = fx * oy + fy * ox;
-                fx = nx;
-            }
-            if (tid == 96) {
-                tileScale[0] = fx * (R)sw.scale;
-                tileScale[1] = fy * (R)sw.scale;
-            }
-        }
-        // ---- load: global -> swizzled smem ----------------------------------------------------------------------
-        if (mover) {
-            const uint4* gp = reinterpret_cast<const uint4*>(psi + base + tOff);
-            if (nU == NU) {
-#pragma unroll
-                for (int u0 = 0; u0 < NU; u0 += 8) {
-                    uint4 v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        v[u] = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const C*>(gp) + uOff[u0 + u]));
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        *reinterpret_cast<uint4*>(tSlot + (size_t)(u0 + u) * NT * 16) = v[u];
-                    }
-                }
-            } else {
-                for (uint32_t u = 0; u < nU; ++u) {
-                    *reinterpret_cast<uint4*>(tSlot + (size_t)u * NT * 16) =
-                        ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const C*>(gp) + uOff[u]));
-                }
-            }
-        }
-        __syncthreads();
-        if (sw.prefetch && (t + gridDim.x < nTiles) && mover && ((tid & 7) == 0)) {
-            // one 128-byte line per 8 movers: the next tile of this CTA streams into L2 under the passes below
-            uint64_t nb = (t + gridDim.x) << sw.lowAmpBits;
-            for (int h = 0; h < sw.nHigh; ++h) {
-                const uint64_t lo = nb & sw.highLow[h];
-                nb = ((nb ^ lo) << 1) | lo;
-            }
-            const C* np = psi + nb + tOff;
-            for (uint32_t u = 0; u < nU; ++u) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(np + uOff[u]));
-            }
-        }
-        // ---- passes ----------------------------------------------------------------------------------------------
-        for (int p = 0; p < sw.nPass; ++p) {
-            const DevPass& ps = sw.pass[p];
-            uint32_t po[NCH];
-#pragma unroll
-            for (int e = 0; e < NCH; ++e) {
-                po[e] = ps.pswzB[e];
-            }
-            uint32_t dep = 0;
-            {
-                const int nb = ps.nsb < 8 ? ps.nsb : 8;
-                for (int i = 0; i < nb; ++i) {
-                    dep |= ((tid >> i) & 1U) << ps.sbit[i];
-                }
-            }
-            // active ops of this pass as (up to 3) 32-bit words
-            uint32_t pm[3];
-#pragma unroll
-            for (int w = 0; w < 3; ++w) {
-                const int lo = ps.opBegin - 32 * w, hi = ps.opEnd - 32 * w;
-                uint32_t m = act[w];
                 m = (lo > 0) ? ((lo >= 32) ? 0U : (m & (0xffffffffU << lo))) : m;
                 m = (hi < 32) ? ((hi <= 0) ? 0U : (m & (0xffffffffU >> (32 - hi)))) : m;
                 pm[w] = m;
@@ -857,8 +677,8 @@ static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref, int NT = 256
         c.L = c.kA; // whole state is one tile
     }
     c.H = c.kA - c.L;
-    c.maxOps = MAX_OPS;
-    c.bundle = 1;
+    c.maxOps = MAX_HOST_OPS;
+    c.bundle = 3;
     return c;
 }
 
@@ -945,7 +765,7 @@ static void plan_sweep(std::vector<HostOp>& pending, const TileCfg& cfg, SweepPl
         PassPlan pp;
         uint64_t regSet = cfg.apcLog ? 1ULL : 0ULL; // fp32: qubit 0 is always register-resident
         int freeReg = cfg.RB;
-        greedy_select(sel, pp.ops, MAX_OPS, 4096, [&](const HostOp& op) {
+        greedy_select(sel, pp.ops, (size_t)cfg.maxOps, 4096, [&](const HostOp& op) {
             if (op.tq < 0 || (regSet & bitq(op.tq))) {
                 return true;
             }
@@ -982,7 +802,8 @@ static int tile_bit(const TileCfg& cfg, const std::vector<int>& highQ, int q)
 }
 
 // Encoded size limits of one sweep program (must fit beside the tile in shared memory with 3 CTAs/SM)
-constexpr size_t MAX_PROG_BYTES = 7168;
+constexpr size_t MAX_PROG_BYTES_3CTA = 7168;
+constexpr size_t MAX_PROG_BYTES_2CTA = 24576;
 
 static int knob_prefetch();
 template <typename R> static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<unsigned char>& buf)
@@ -1000,6 +821,7 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
     memset(&ds, 0, sizeof(ds));
     std::vector<DevOp<R>> dops;
     std::vector<DevOuterPhase<R>> outerList;
+    std::vector<std::vector<DevOuterPhase<R>>> slotMembers; // table slots 1.. (register-bit phases of the DIAG ops)
     ds.nHigh = (int)sp.highQ.size();
     ds.lowAmpBits = cfg.L;
     ds.kc = kc;
@@ -1136,11 +958,57 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
             }
             ndq = 0;
         };
+        // ---- open DIAG group: phases whose predicate is (outer qubits) AND (one register bit), per register bit.
+        // Members are diagonal, so they commute with everything except a non-diagonal op on their register bit;
+        // the group is emitted just before the first such op (or at the end of the pass).
+        std::vector<DevOuterPhase<R>> diag[5];
+        uint32_t diagBits = 0;
+        auto close_diag = [&]() {
+            if (!diagBits) {
+                return;
+            }
+            DevOp<R> d;
+            memset(&d, 0, sizeof(d));
+            d.code = OPC_DIAG;
+            d.emask = diagBits;
+            d.lmaskSb = (uint32_t)slotMembers.size() + 1U; // first table slot of this group
+            for (int b = 0; b < JRN; ++b) {
+                if (diagBits & (1U << b)) {
+                    slotMembers.push_back(diag[b]);
+                    diag[b].clear();
+                }
+            }
+            dops.push_back(d);
+            diagBits = 0;
+        };
         dp.opBegin = (int)dops.size();
         for (const HostOp& hop : pp.ops) {
             uint32_t lmask, lval;
             local_pred(hop, lmask, lval);
             const uint32_t lmr = lmask & regAmpMask, lvr = lval & regAmpMask;
+            if ((cfg.bundle & 2) && hop.kind == OP_PHASE && !(lmask & ~regAmpMask) && __builtin_popcount(lmr) == 1 && lvr == lmr &&
+                slotMembers.size() + (size_t)__builtin_popcount(diagBits) + 2U < (size_t)MAX_SLOTS) {
+                const int jr = reg_index(__builtin_ctz(lmr));
+                if (layerUsed[jr]) {
+                    close_bundle(); // the open layer has a butterfly on this bit: it must run first
+                }
+                DevOuterPhase<R> mem;
+                memset(&mem, 0, sizeof(mem));
+                mem.omask = hop.cmask & ~tileMask;
+                mem.oval = hop.cval & ~tileMask;
+                mem.ph[0] = (R)hop.m[0];
+                mem.ph[1] = (R)hop.m[1];
+                diag[jr].push_back(mem);
+                diagBits |= 1U << jr;
+                continue;
+            }
+            if (hop.kind != OP_PHASE && diagBits) {
+                // non-diagonal op: pending phases on its target register bit have to be applied before it
+                const int jt = reg_index(tile_bit(cfg, sp.highQ, hop.tq));
+                if (diagBits & (1U << jt)) {
+                    close_diag();
+                }
+            }
             if (hop.kind == OP_PHASE) {
                 if (!(hop.cmask & tileMask) && outerList.size() < (size_t)MAX_OUTER) {
                     // every qubit of the predicate is outside the tile: uniform per tile, commutes with the whole sweep
@@ -1214,6 +1082,7 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
             dops.push_back(d);
         }
         close_bundle();
+        close_diag();
         if (p == ds.nPass - 1 && (scale != 1.0 || !outerList.empty())) {
             DevOp<R> d;
             memset(&d, 0, sizeof(d));
@@ -1233,6 +1102,14 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
                     fprintf(stderr, " LAYER(%x)", dops[o].emask);
                 } else if (c == OPC_SCALE) {
                     fprintf(stderr, " SCALE");
+                } else if (c == OPC_DIAG) {
+                    int nm = 0;
+                    for (int b = 0, sl = (int)dops[o].lmaskSb - 1; b < 5; ++b) {
+                        if (dops[o].emask & (1U << b)) {
+                            nm += (int)slotMembers[sl++].size();
+                        }
+                    }
+                    fprintf(stderr, " DIAG(%x:%d)", dops[o].emask, nm);
                 } else {
                     fprintf(stderr, " %s.%u%s%s", names[c / 5U], c % 5U, (dops[o].code & CODE_HAS_SB) ? "s" : "", dops[o].omask ? "o" : "");
                 }
@@ -1245,11 +1122,23 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
     ds.hasScale = (scale != 1.0 || !outerList.empty()) ? 1 : 0;
     ds.nOps = (int)dops.size();
     ds.nOuter = (int)outerList.size();
+    // table slots: slot 0 = the outer-only phases (tile scalar), then one slot per (DIAG op, register bit)
+    ds.nSlots = 1 + (int)slotMembers.size();
+    ds.slotBeg[0] = 0;
+    ds.slotBeg[1] = (unsigned short)outerList.size();
+    for (size_t k = 0; k < slotMembers.size(); ++k) {
+        outerList.insert(outerList.end(), slotMembers[k].begin(), slotMembers[k].end());
+        ds.slotBeg[k + 2] = (unsigned short)outerList.size();
+    }
     const size_t opsBytes = ((dops.size() * sizeof(DevOp<R>)) + 15U) & ~(size_t)15U;
     const size_t outerBytes = ((outerList.size() * sizeof(DevOuterPhase<R>)) + 15U) & ~(size_t)15U;
     ds.outerOff = (int)(sizeof(DevSweep) + opsBytes);
     const size_t start = buf.size();
-    const size_t bytes = ((sizeof(DevSweep) + opsBytes + outerBytes) + 15U) & ~(size_t)15U;
+    size_t bytes = ((sizeof(DevSweep) + opsBytes + outerBytes) + 15U) & ~(size_t)15U;
+    if (dops.size() > (size_t)MAX_OPS || outerList.size() > 60000U) {
+        bytes = (size_t)1 << 30; // does not fit the descriptor: the caller retries with a smaller window
+        return bytes;
+    }
     buf.resize(start + bytes, 0);
     memcpy(buf.data() + start, &ds, sizeof(ds));
     if (!dops.empty()) {
@@ -1279,9 +1168,14 @@ static int plan_and_encode(std::vector<HostOp>& pending, const TileCfg& cfg0, in
         }
         const size_t mark = buf.size();
         const size_t bytes = (prec == 32) ? encode_sweep<float>(sp, cfg, buf) : encode_sweep<double>(sp, cfg, buf);
-        if (bytes > MAX_PROG_BYTES && cfg.maxOps > 4) {
+        const size_t limit = (cfg.RB >= 4) ? MAX_PROG_BYTES_2CTA : MAX_PROG_BYTES_3CTA;
+        if (bytes > limit) {
+            if (cfg.maxOps <= 4) {
+                set_error("fused sweep program does not fit");
+                return B200SV_ESTATE;
+            }
             buf.resize(mark);
-            cfg.maxOps /= 2;
+            cfg.maxOps = cfg.maxOps * 3 / 4;
             continue;
         }
         // commit: the window's leftovers go back in front of the untouched tail
@@ -1359,34 +1253,12 @@ static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes
     static unsigned long long attr_set_mask = 0; // per device: the attribute is per-context
     if (!(attr_set_mask & (1ULL << s->dev))) {
         SV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (int)(((size_t)16 << KC) + MAX_PROG_BYTES)));
+            (int)(((size_t)16 << KC) + (MINB >= 3 ? MAX_PROG_BYTES_3CTA : MAX_PROG_BYTES_2CTA))));
         attr_set_mask |= 1ULL << s->dev;
     }
     const uint64_t maxGrid = (uint64_t)sm_count(s->dev) * MINB;
     const unsigned grid = (unsigned)std::min<uint64_t>(nTiles, maxGrid);
     kern<<<grid, NT, shm, s->stream>>>(reinterpret_cast<typename Cx<R>::type*>(s->amps), dprog, progBytes, nTiles);
-    SV_CUDA(cudaGetLastError());
-    return B200SV_OK;
-}
-
-template <typename R, int KC, int RB, int NT, int MINB>
-static int launch_sweep_cp(State* s, const unsigned char* hprog, uint64_t nTiles)
-{
-    auto kern = k_fused_sweep_cp<R, KC, RB, NT, MINB>;
-    static unsigned long long attr_set_mask = 0; // per device: the attribute is per-context
-    if (!(attr_set_mask & (1ULL << s->dev))) {
-        SV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)16 << KC)));
-        attr_set_mask |= 1ULL << s->dev;
-    }
-    // unpack the encoded program [DevSweep][ops][outer phases] into the parameter block
-    static thread_local ProgParam<R> pp;
-    const DevSweep* ds = reinterpret_cast<const DevSweep*>(hprog);
-    pp.sw = *ds;
-    memcpy(pp.ops, hprog + sizeof(DevSweep), (size_t)ds->nOps * sizeof(DevOp<R>));
-    memcpy(pp.outer, hprog + ds->outerOff, (size_t)ds->nOuter * sizeof(DevOuterPhase<R>));
-    const uint64_t maxGrid = (uint64_t)sm_count(s->dev) * MINB;
-    const unsigned grid = (unsigned)std::min<uint64_t>(nTiles, maxGrid);
-    kern<<<grid, NT, (size_t)16 << KC, s->stream>>>(reinterpret_cast<typename Cx<R>::type*>(s->amps), pp, nTiles);
     SV_CUDA(cudaGetLastError());
     return B200SV_OK;
 }
@@ -1397,8 +1269,7 @@ struct FusedKnobs {
     int L32 = 6;
     int L64 = 6;
     int RB64 = 3; // fp64: 8 double2 amplitudes per sub-block keep 3 CTAs/SM resident
-    int cp = 0;   // 1: sweep program travels as a kernel parameter (constant bank); 0: device arena + shared-memory copy (measured 1.5 % faster)
-    int bundle = 1; // bit 0: merge Hadamards on distinct register bits into one LAYER op
+    int bundle = 3; // bit 0: merge Hadamards on distinct register bits into one LAYER op; bit 1: DIAG phase groups
     int pf = 0;     // 1: L2 prefetch of the CTA's next tile during the passes
 };
 static const FusedKnobs& knobs()
@@ -1411,9 +1282,6 @@ static const FusedKnobs& knobs()
             const int got = sscanf(e, "%d,%d,%d,%d,%d,%d,%d", &rb, &l32, &l64, &bn, &rb64, &cp, &pf);
             if (got >= 7) {
                 v.pf = pf;
-            }
-            if (got >= 6) {
-                v.cp = cp;
             }
             if (got >= 4) {
                 v.bundle = bn;
@@ -1479,29 +1347,6 @@ int fused_flush(State* s)
         segs.push_back({ off, bytes });
     }
     const uint64_t nTiles = s->dim() >> cfg.kA;
-    if (knobs().cp) {
-        for (size_t i = 0; i < segs.size(); ++i) {
-            const unsigned char* hp = buf.data() + segs[i].first;
-            if (s->prec == 32) {
-                if (cfg.RB == 4) {
-                    SV_TRY((launch_sweep_cp<float, FUSED_KC, 4, FUSED_NT, 2>(s, hp, nTiles)));
-                } else {
-                    SV_TRY((launch_sweep_cp<float, FUSED_KC, 3, FUSED_NT, 3>(s, hp, nTiles)));
-                }
-            } else {
-                if (cfg.RB == 4) {
-                    SV_TRY((launch_sweep_cp<double, FUSED_KC, 4, FUSED_NT, 2>(s, hp, nTiles)));
-                } else {
-                    SV_TRY((launch_sweep_cp<double, FUSED_KC, 3, FUSED_NT, 3>(s, hp, nTiles)));
-                }
-            }
-            s->stats.kernel_launches++;
-            s->stats.fused_sweeps++;
-            s->stats.bytes_swept += 2ULL * s->dim() * s->amp_bytes();
-        }
-        s->stats.fused_gates += nGates;
-        return B200SV_OK;
-    }
     if (ar->pending) {
         SV_CUDA(cudaEventSynchronize(ar->done));
         ar->pending = false;

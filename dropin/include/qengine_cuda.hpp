@@ -36,9 +36,8 @@ protected:
     void Copy(QInterfacePtr orig) { Copy(std::dynamic_pointer_cast<QEngineCUDA>(orig)); }
     void Copy(QEngineCUDAPtr orig);
 
-    typedef std::function<void(QInterfacePtr)> CpuFn;
-    /// ALU members are outside the hot path: round-trip through a temporary QEngineCPU.
-    void ViaCpu(CpuFn fn);
+    /// OR of 2^control; throws std::invalid_argument like ThrowIfQbIdArrayIsBad (common/qrack_functions.hpp)
+    uint64_t CtrlMask(const std::vector<bitLenInt>& controls, const char* what) const;
 
 public:
     /// 1 / OclMemDenom of device memory is the most a single state vector should take (test/benchmarks_main.cpp:288)
@@ -128,8 +127,21 @@ public:
         real1_f nrm = REAL1_DEFAULT_ARG, real1_f norm_thresh = REAL1_DEFAULT_ARG, real1_f phaseArg = ZERO_R1_F);
     void UpdateRunningNorm(real1_f norm_thresh = REAL1_DEFAULT_ARG);
 
+    void ROL(bitLenInt shift, bitLenInt start, bitLenInt length);
+    void ROR(bitLenInt shift, bitLenInt start, bitLenInt length);
+
 #if ENABLE_ALU
-    // ---- QAlu (include/qalu.hpp): CPU round trip, not part of the hot path ----
+    // ---- QAlu (include/qalu.hpp): one device sweep each (include/b200sv.h "QAlu family") ----
+    void INC(const bitCapInt& toAdd, bitLenInt start, bitLenInt length);
+    void CINC(const bitCapInt& toAdd, bitLenInt start, bitLenInt length, const std::vector<bitLenInt>& controls);
+    void INCDECC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt carryIndex);
+    void INCS(const bitCapInt& toAdd, bitLenInt start, bitLenInt length, bitLenInt overflowIndex);
+    void MULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length);
+    void IMULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length);
+    void CMULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length,
+        const std::vector<bitLenInt>& controls);
+    void CIMULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length,
+        const std::vector<bitLenInt>& controls);
     void PhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length);
     void CPhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length, bitLenInt flagIndex);
     void INCDECSC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt carryIndex);

@@ -804,105 +804,238 @@ void QEngineCUDA::UpdateRunningNorm(real1_f norm_thresh)
     }
 }
 
-// ---- QAlu: host round trip through the reference's own QEngineCPU (out of the hot path) -------------------------------
+// ---- QAlu / ROL: each member is ONE out-of-place basis-map sweep on the device (include/b200sv.h "QAlu family").
+// What stays here is what the reference's QEngineCPU does above its loops (src/qengine/arithmetic.cpp): argument
+// checks that throw std::invalid_argument, the trivial-argument shortcuts, and the SetReg / M / X pre-steps.
 
-// QEngineCPU keeps INCDECSC protected; expose it for the round trip
-struct CpuAlu : public QEngineCPU {
-    using QEngineCPU::QEngineCPU;
-#if ENABLE_ALU
-    using QEngineCPU::INCDECSC;
-#endif
-};
-
-void QEngineCUDA::ViaCpu(CpuFn fn)
+uint64_t QEngineCUDA::CtrlMask(const std::vector<bitLenInt>& controls, const char* what) const
 {
-    if (IsZeroAmplitude()) {
+    uint64_t m = 0U;
+    for (const bitLenInt c : controls) {
+        if (c >= qubitCount) {
+            throw std::invalid_argument(std::string("QEngineCUDA::") + what + " control is out-of-bounds!");
+        }
+        m |= pow2Ocl(c);
+    }
+    return m;
+}
+
+void QEngineCUDA::ROL(bitLenInt shift, bitLenInt start, bitLenInt length)
+{
+    Check(b200sv_rol(sv, (int)shift, (int)start, (int)length));
+}
+
+void QEngineCUDA::ROR(bitLenInt shift, bitLenInt start, bitLenInt length)
+{
+    if (!length) {
         return;
     }
-    QInterfacePtr cpu = std::make_shared<CpuAlu>(qubitCount, ZERO_BCI, rand_generator, ONE_CMPLX, doNormalize,
-        randGlobalPhase, false, -1, !hardware_rand_generator ? false : true, false, (real1_f)amplitudeFloor);
-    std::unique_ptr<complex[]> tmp(new complex[maxQPowerOcl]);
-    GetQuantumState(tmp.get());
-    cpu->SetQuantumState(tmp.get());
-    fn(cpu);
-    cpu->GetQuantumState(tmp.get());
-    SetQuantumState(tmp.get());
+    shift %= length;
+    if (shift) {
+        ROL(length - shift, start, length);
+    }
 }
 
 #if ENABLE_ALU
-#define VIA_ALU(call) ViaCpu([&](QInterfacePtr q) { std::dynamic_pointer_cast<CpuAlu>(q)->call; })
-void QEngineCUDA::PhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length)
+#define U64(x) ((uint64_t)(bitCapIntOcl)(x))
+void QEngineCUDA::INC(const bitCapInt& toAdd, bitLenInt start, bitLenInt length)
 {
-    VIA_ALU(PhaseFlipIfLess(greaterPerm, start, length));
+    Check(b200sv_inc(sv, U64(toAdd), (int)start, (int)length, 0U));
 }
-void QEngineCUDA::CPhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length, bitLenInt flagIndex)
+void QEngineCUDA::CINC(const bitCapInt& toAdd, bitLenInt start, bitLenInt length, const std::vector<bitLenInt>& controls)
 {
-    VIA_ALU(CPhaseFlipIfLess(greaterPerm, start, length, flagIndex));
+    Check(b200sv_inc(sv, U64(toAdd), (int)start, (int)length, CtrlMask(controls, "CINC")));
+}
+void QEngineCUDA::INCDECC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt carryIndex)
+{
+    Check(b200sv_incdecc(sv, U64(toMod), (int)start, (int)length, (int)carryIndex));
+}
+void QEngineCUDA::INCS(const bitCapInt& toAdd, bitLenInt start, bitLenInt length, bitLenInt overflowIndex)
+{
+    Check(b200sv_incs(sv, U64(toAdd), (int)start, (int)length, (int)overflowIndex));
 }
 void QEngineCUDA::INCDECSC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt carryIndex)
 {
-    VIA_ALU(INCDECSC(toMod, start, length, carryIndex));
+    Check(b200sv_incdecsc(sv, U64(toMod), (int)start, (int)length, -1, (int)carryIndex));
 }
 void QEngineCUDA::INCDECSC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt overflowIndex, bitLenInt carryIndex)
 {
-    VIA_ALU(INCDECSC(toMod, start, length, overflowIndex, carryIndex));
+    Check(b200sv_incdecsc(sv, U64(toMod), (int)start, (int)length, (int)overflowIndex, (int)carryIndex));
 }
+void QEngineCUDA::PhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length)
+{
+    Check(b200sv_phase_flip_if_less(sv, U64(greaterPerm), (int)start, (int)length, -1));
+}
+void QEngineCUDA::CPhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length, bitLenInt flagIndex)
+{
+    Check(b200sv_phase_flip_if_less(sv, U64(greaterPerm), (int)start, (int)length, (int)flagIndex));
+}
+
+// MUL / DIV and controlled forms: arithmetic.cpp:458-485, 553-593
 void QEngineCUDA::MUL(const bitCapInt& toMul, bitLenInt start, bitLenInt carryStart, bitLenInt length)
 {
-    VIA_ALU(MUL(toMul, start, carryStart, length));
+    SetReg(carryStart, length, ZERO_BCI);
+    if (bi_compare_0(toMul) == 0) {
+        return SetReg(start, length, ZERO_BCI);
+    }
+    if (bi_compare_1(toMul) == 0) {
+        return;
+    }
+    Check(b200sv_muldiv(sv, 0, U64(toMul), (int)start, (int)carryStart, (int)length, 0U));
 }
 void QEngineCUDA::DIV(const bitCapInt& toDiv, bitLenInt start, bitLenInt carryStart, bitLenInt length)
 {
-    VIA_ALU(DIV(toDiv, start, carryStart, length));
-}
-void QEngineCUDA::POWModNOut(const bitCapInt& base, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length)
-{
-    VIA_ALU(POWModNOut(base, modN, inStart, outStart, length));
+    if (bi_compare_0(toDiv) == 0) {
+        throw std::runtime_error("DIV by zero");
+    }
+    if (bi_compare_1(toDiv) == 0) {
+        return;
+    }
+    Check(b200sv_muldiv(sv, 1, U64(toDiv), (int)start, (int)carryStart, (int)length, 0U));
 }
 void QEngineCUDA::CMUL(const bitCapInt& toMul, bitLenInt start, bitLenInt carryStart, bitLenInt length,
     const std::vector<bitLenInt>& controls)
 {
-    VIA_ALU(CMUL(toMul, start, carryStart, length, controls));
+    if (controls.empty()) {
+        return MUL(toMul, start, carryStart, length);
+    }
+    SetReg(carryStart, length, ZERO_BCI);
+    if (bi_compare_0(toMul) == 0) {
+        return SetReg(start, length, ZERO_BCI);
+    }
+    if (bi_compare_1(toMul) == 0) {
+        return;
+    }
+    Check(b200sv_muldiv(sv, 0, U64(toMul), (int)start, (int)carryStart, (int)length, CtrlMask(controls, "CMULDIV")));
 }
 void QEngineCUDA::CDIV(const bitCapInt& toDiv, bitLenInt start, bitLenInt carryStart, bitLenInt length,
     const std::vector<bitLenInt>& controls)
 {
-    VIA_ALU(CDIV(toDiv, start, carryStart, length, controls));
+    if (controls.empty()) {
+        return DIV(toDiv, start, carryStart, length);
+    }
+    if (bi_compare_0(toDiv) == 0) {
+        throw std::runtime_error("DIV by zero");
+    }
+    if (bi_compare_1(toDiv) == 0) {
+        return;
+    }
+    Check(b200sv_muldiv(sv, 1, U64(toDiv), (int)start, (int)carryStart, (int)length, CtrlMask(controls, "CMULDIV")));
+}
+
+// ModNOut family: arithmetic.cpp:634-667, 737-775
+void QEngineCUDA::MULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length)
+{
+    SetReg(outStart, length, ZERO_BCI);
+    if (bi_compare_0(toMod) == 0) {
+        return;
+    }
+    Check(b200sv_modnout(sv, 0, U64(toMod), U64(modN), (int)inStart, (int)outStart, (int)length, 0U));
+}
+void QEngineCUDA::IMULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length)
+{
+    if (bi_compare_0(toMod) == 0) {
+        return;
+    }
+    Check(b200sv_modnout(sv, 1, U64(toMod), U64(modN), (int)inStart, (int)outStart, (int)length, 0U));
+}
+void QEngineCUDA::POWModNOut(const bitCapInt& base, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length)
+{
+    if (bi_compare_1(base) == 0) {
+        return SetReg(outStart, length, ONE_BCI);
+    }
+    Check(b200sv_modnout(sv, 2, U64(base), U64(modN), (int)inStart, (int)outStart, (int)length, 0U));
+}
+void QEngineCUDA::CMULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart,
+    bitLenInt length, const std::vector<bitLenInt>& controls)
+{
+    if (controls.empty()) {
+        return MULModNOut(toMod, modN, inStart, outStart, length);
+    }
+    SetReg(outStart, length, ZERO_BCI);
+    Check(b200sv_modnout(sv, 0, U64(toMod), U64(modN), (int)inStart, (int)outStart, (int)length, CtrlMask(controls, "ModNOut")));
+}
+void QEngineCUDA::CIMULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart,
+    bitLenInt length, const std::vector<bitLenInt>& controls)
+{
+    if (controls.empty()) {
+        return IMULModNOut(toMod, modN, inStart, outStart, length);
+    }
+    Check(b200sv_modnout(sv, 1, U64(toMod), U64(modN), (int)inStart, (int)outStart, (int)length, CtrlMask(controls, "ModNOut")));
 }
 void QEngineCUDA::CPOWModNOut(const bitCapInt& base, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart,
     bitLenInt length, const std::vector<bitLenInt>& controls)
 {
-    VIA_ALU(CPOWModNOut(base, modN, inStart, outStart, length, controls));
+    if (controls.empty()) {
+        return POWModNOut(base, modN, inStart, outStart, length);
+    }
+    Check(b200sv_modnout(sv, 2, U64(base), U64(modN), (int)inStart, (int)outStart, (int)length, CtrlMask(controls, "ModNOut")));
 }
+
+// Indexed loads / adds from a classical table: arithmetic.cpp:983-1444.  The carry is measured (and cleared) first.
 bitCapInt QEngineCUDA::IndexedLDA(bitLenInt indexStart, bitLenInt indexLength, bitLenInt valueStart, bitLenInt valueLength,
     const unsigned char* values, bool resetValue)
 {
-    bitCapInt r = ZERO_BCI;
-    ViaCpu([&](QInterfacePtr q) {
-        r = std::dynamic_pointer_cast<CpuAlu>(q)->IndexedLDA(indexStart, indexLength, valueStart, valueLength, values, resetValue);
-    });
-    return r;
+    if (isBadBitRange(indexStart, indexLength, qubitCount)) {
+        throw std::invalid_argument("QEngineCUDA::IndexedLDA range is out-of-bounds!");
+    }
+    if (isBadBitRange(valueStart, valueLength, qubitCount)) {
+        throw std::invalid_argument("QEngineCUDA::IndexedLDA range is out-of-bounds!");
+    }
+    if (IsZeroAmplitude()) {
+        return ZERO_BCI;
+    }
+    if (resetValue) {
+        SetReg(valueStart, valueLength, ZERO_BCI);
+    }
+    Check(b200sv_indexed(sv, 0, (int)indexStart, (int)indexLength, (int)valueStart, (int)valueLength, -1, 0, values));
+    return ZERO_BCI;
 }
 bitCapInt QEngineCUDA::IndexedADC(bitLenInt indexStart, bitLenInt indexLength, bitLenInt valueStart, bitLenInt valueLength,
     bitLenInt carryIndex, const unsigned char* values)
 {
-    bitCapInt r = ZERO_BCI;
-    ViaCpu([&](QInterfacePtr q) {
-        r = std::dynamic_pointer_cast<CpuAlu>(q)->IndexedADC(indexStart, indexLength, valueStart, valueLength, carryIndex, values);
-    });
-    return r;
+    if (isBadBitRange(indexStart, indexLength, qubitCount) || isBadBitRange(valueStart, valueLength, qubitCount)) {
+        throw std::invalid_argument("QEngineCUDA::IndexedADC range is out-of-bounds!");
+    }
+    if (carryIndex >= qubitCount) {
+        throw std::invalid_argument("QEngineCUDA::IndexedADC carryIndex is out-of-bounds!");
+    }
+    if (IsZeroAmplitude()) {
+        return ZERO_BCI;
+    }
+    int carryIn = 0;
+    if (M(carryIndex)) {
+        carryIn = 1;
+        X(carryIndex);
+    }
+    Check(b200sv_indexed(sv, 1, (int)indexStart, (int)indexLength, (int)valueStart, (int)valueLength, (int)carryIndex, carryIn, values));
+    return ZERO_BCI;
 }
 bitCapInt QEngineCUDA::IndexedSBC(bitLenInt indexStart, bitLenInt indexLength, bitLenInt valueStart, bitLenInt valueLength,
     bitLenInt carryIndex, const unsigned char* values)
 {
-    bitCapInt r = ZERO_BCI;
-    ViaCpu([&](QInterfacePtr q) {
-        r = std::dynamic_pointer_cast<CpuAlu>(q)->IndexedSBC(indexStart, indexLength, valueStart, valueLength, carryIndex, values);
-    });
-    return r;
+    if (isBadBitRange(indexStart, indexLength, qubitCount) || isBadBitRange(valueStart, valueLength, qubitCount)) {
+        throw std::invalid_argument("QEngineCUDA::IndexedSBC range is out-of-bounds!");
+    }
+    if (carryIndex >= qubitCount) {
+        throw std::invalid_argument("QEngineCUDA::IndexedSBC carryIndex is out-of-bounds!");
+    }
+    if (IsZeroAmplitude()) {
+        return ZERO_BCI;
+    }
+    int carryIn = 1;
+    if (M(carryIndex)) {
+        carryIn = 0;
+        X(carryIndex);
+    }
+    Check(b200sv_indexed(sv, 2, (int)indexStart, (int)indexLength, (int)valueStart, (int)valueLength, (int)carryIndex, carryIn, values));
+    return ZERO_BCI;
 }
-void QEngineCUDA::Hash(bitLenInt start, bitLenInt length, const unsigned char* values) { VIA_ALU(Hash(start, length, values)); }
-#undef VIA_ALU
+void QEngineCUDA::Hash(bitLenInt start, bitLenInt length, const unsigned char* values)
+{
+    Check(b200sv_hash(sv, (int)start, (int)length, values));
+}
+#undef U64
 #endif
 
 } // namespace Qrack

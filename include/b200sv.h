@@ -155,6 +155,30 @@ int b200sv_finish(b200sv_t s); /* flush + wait for the device (QInterface::Finis
 /* mode 0: every gate is its own launch (reference-like); 1: fused multi-gate sweeps (default) */
 int b200sv_set_fusion(b200sv_t s, int mode);
 
+/* ---- QAlu family: basis-state maps, one out-of-place sweep each -------------------------------
+ * Replaces the QEngineCPU members of src/qengine/arithmetic.cpp that a QEngine must provide (include/qalu.hpp:34-236,
+ * include/qengine.hpp ROL).  bitCapIntOcl arguments travel as uint64_t; `ctrl_mask` = OR of 2^control (0: uncontrolled).
+ * Pre-steps the reference performs at QInterface level (SetReg of the carry register, M/X of the carry qubit) are the
+ * adapter's job, as in the reference.  A zero (unallocated) state is left untouched (CHECK_ZERO_SKIP). */
+int b200sv_rol(b200sv_t s, int shift, int start, int length);                              /* arithmetic.cpp:23-70 */
+int b200sv_inc(b200sv_t s, uint64_t to_add, int start, int length, uint64_t ctrl_mask);    /* INC :73-118, CINC :121-172 */
+int b200sv_incdecc(b200sv_t s, uint64_t to_mod, int start, int length, int carry_index);   /* :175-224 */
+int b200sv_incs(b200sv_t s, uint64_t to_add, int start, int length, int overflow_index);   /* :227-309 */
+/* overflow_index < 0: the carry-only form (:312-361); else overflow flag + carry (:364-419) */
+int b200sv_incdecsc(b200sv_t s, uint64_t to_mod, int start, int length, int overflow_index, int carry_index);
+/* inverse = 0: MUL / CMUL (:422-471, :488-573); 1: DIV / CDIV */
+int b200sv_muldiv(b200sv_t s, int inverse, uint64_t to_mul, int start, int carry_start, int length, uint64_t ctrl_mask);
+/* kind 0: MULModNOut, 1: IMULModNOut, 2: POWModNOut and their controlled forms (:595-775) */
+int b200sv_modnout(b200sv_t s, int kind, uint64_t to_mod, uint64_t mod_n, int in_start, int out_start, int length,
+    uint64_t ctrl_mask);
+/* kind 0: IndexedLDA (:983-1083), 1: IndexedADC (:1086-1260), 2: IndexedSBC (:1263-1444); `values` is a HOST table of
+ * 2^index_length entries of (value_length+7)/8 bytes; carry_in = the classical carry the adapter measured */
+int b200sv_indexed(b200sv_t s, int kind, int index_start, int index_length, int value_start, int value_length,
+    int carry_index, int carry_in, const unsigned char* values);
+int b200sv_hash(b200sv_t s, int start, int length, const unsigned char* values);           /* :1447-1506 */
+/* flag_index < 0: PhaseFlipIfLess (:1703-1720); else CPhaseFlipIfLess (:1678-1701) */
+int b200sv_phase_flip_if_less(b200sv_t s, uint64_t greater_perm, int start, int length, int flag_index);
+
 /* Scheduler diagnostic (no device needed): how many fused sweeps / in-tile passes a gate list would take.
  * kinds[i]: 0 real 2x2 (H-like), 1 diagonal (T/CZ-like), 2 X-like (CNOT), 3 complex general; cmasks = control qubits. */
 int b200sv_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks,

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -13,6 +14,7 @@
 #define SUF _f32
 #define FP_NORM_EPS (1.1920928955078125e-07f / 4)
 #include "qengine_restate_impl.h"
+#include "qalu_restate_impl.h"
 #undef REAL
 #undef SUF
 #undef FP_NORM_EPS
@@ -21,6 +23,7 @@
 #define SUF _f64
 #define FP_NORM_EPS (2.220446049250313e-16 / 4)
 #include "qengine_restate_impl.h"
+#include "qalu_restate_impl.h"
 #undef REAL
 #undef SUF
 #undef FP_NORM_EPS

@@ -85,6 +85,15 @@ struct Tok {
         }
         return v;
     }
+    std::vector<unsigned char> hex() // classical table as one hex token
+    {
+        const std::string h = s();
+        std::vector<unsigned char> v;
+        for (size_t k = 0; k + 1 < h.size(); k += 2) {
+            v.push_back((unsigned char)std::stoul(h.substr(k, 2), nullptr, 16));
+        }
+        return v;
+    }
     void mtrx(complex* m)
     {
         for (int k = 0; k < 4; ++k) {
@@ -332,6 +341,117 @@ int main(int argc, char** argv)
             const uint64_t v = tk.u();
             const bitLenInt s = tk.i(), l = tk.i();
             q->DEC(bitCapInt(v), s, l);
+        } else if (op == "ROL" || op == "ROR") {
+            const bitLenInt sh = tk.i(), s = tk.i(), l = tk.i();
+            if (op == "ROL") {
+                q->ROL(sh, s, l);
+            } else {
+                q->ROR(sh, s, l);
+            }
+#if ENABLE_ALU
+        } else if (op == "CINC" || op == "CDEC") {
+            std::vector<bitLenInt> c = tk.qubits();
+            const uint64_t v = tk.u();
+            const bitLenInt s = tk.i(), l = tk.i();
+            if (op == "CINC") {
+                q->CINC(bitCapInt(v), s, l, c);
+            } else {
+                q->CDEC(bitCapInt(v), s, l, c);
+            }
+        } else if (op == "INCC" || op == "DECC" || op == "INCS" || op == "DECS" || op == "INCSCc" || op == "DECSCc") {
+            const uint64_t v = tk.u();
+            const bitLenInt s = tk.i(), l = tk.i(), x = tk.i();
+            QAlu* a = dynamic_cast<QAlu*>(q.get());
+            if (op == "INCC") {
+                a->INCC(bitCapInt(v), s, l, x);
+            } else if (op == "DECC") {
+                a->DECC(bitCapInt(v), s, l, x);
+            } else if (op == "INCS") {
+                a->INCS(bitCapInt(v), s, l, x);
+            } else if (op == "DECS") {
+                a->DECS(bitCapInt(v), s, l, x);
+            } else if (op == "INCSCc") {
+                a->INCSC(bitCapInt(v), s, l, x);
+            } else {
+                a->DECSC(bitCapInt(v), s, l, x);
+            }
+        } else if (op == "INCSC" || op == "DECSC") {
+            const uint64_t v = tk.u();
+            const bitLenInt s = tk.i(), l = tk.i(), o = tk.i(), cy = tk.i();
+            QAlu* a = dynamic_cast<QAlu*>(q.get());
+            if (op == "INCSC") {
+                a->INCSC(bitCapInt(v), s, l, o, cy);
+            } else {
+                a->DECSC(bitCapInt(v), s, l, o, cy);
+            }
+        } else if (op == "MUL" || op == "DIV") {
+            const uint64_t v = tk.u();
+            const bitLenInt s = tk.i(), cs = tk.i(), l = tk.i();
+            QAlu* a = dynamic_cast<QAlu*>(q.get());
+            if (op == "MUL") {
+                a->MUL(bitCapInt(v), s, cs, l);
+            } else {
+                a->DIV(bitCapInt(v), s, cs, l);
+            }
+        } else if (op == "CMUL" || op == "CDIV") {
+            std::vector<bitLenInt> c = tk.qubits();
+            const uint64_t v = tk.u();
+            const bitLenInt s = tk.i(), cs = tk.i(), l = tk.i();
+            QAlu* a = dynamic_cast<QAlu*>(q.get());
+            if (op == "CMUL") {
+                a->CMUL(bitCapInt(v), s, cs, l, c);
+            } else {
+                a->CDIV(bitCapInt(v), s, cs, l, c);
+            }
+        } else if (op == "MULModNOut" || op == "IMULModNOut" || op == "POWModNOut") {
+            const uint64_t v = tk.u(), n = tk.u();
+            const bitLenInt is = tk.i(), os = tk.i(), l = tk.i();
+            QAlu* a = dynamic_cast<QAlu*>(q.get());
+            if (op == "MULModNOut") {
+                a->MULModNOut(bitCapInt(v), bitCapInt(n), is, os, l);
+            } else if (op == "IMULModNOut") {
+                a->IMULModNOut(bitCapInt(v), bitCapInt(n), is, os, l);
+            } else {
+                a->POWModNOut(bitCapInt(v), bitCapInt(n), is, os, l);
+            }
+        } else if (op == "CMULModNOut" || op == "CIMULModNOut" || op == "CPOWModNOut") {
+            std::vector<bitLenInt> c = tk.qubits();
+            const uint64_t v = tk.u(), n = tk.u();
+            const bitLenInt is = tk.i(), os = tk.i(), l = tk.i();
+            QAlu* a = dynamic_cast<QAlu*>(q.get());
+            if (op == "CMULModNOut") {
+                a->CMULModNOut(bitCapInt(v), bitCapInt(n), is, os, l, c);
+            } else if (op == "CIMULModNOut") {
+                a->CIMULModNOut(bitCapInt(v), bitCapInt(n), is, os, l, c);
+            } else {
+                a->CPOWModNOut(bitCapInt(v), bitCapInt(n), is, os, l, c);
+            }
+        } else if (op == "IndexedLDA") {
+            const bitLenInt is = tk.i(), il = tk.i(), vs = tk.i(), vl = tk.i();
+            std::vector<unsigned char> tab = tk.hex();
+            dynamic_cast<QAlu*>(q.get())->IndexedLDA(is, il, vs, vl, tab.data(), true);
+        } else if (op == "IndexedADC" || op == "IndexedSBC") {
+            const bitLenInt is = tk.i(), il = tk.i(), vs = tk.i(), vl = tk.i(), cy = tk.i();
+            std::vector<unsigned char> tab = tk.hex();
+            QAlu* a = dynamic_cast<QAlu*>(q.get());
+            if (op == "IndexedADC") {
+                a->IndexedADC(is, il, vs, vl, cy, tab.data());
+            } else {
+                a->IndexedSBC(is, il, vs, vl, cy, tab.data());
+            }
+        } else if (op == "Hash") {
+            const bitLenInt s = tk.i(), l = tk.i();
+            std::vector<unsigned char> tab = tk.hex();
+            dynamic_cast<QAlu*>(q.get())->Hash(s, l, tab.data());
+        } else if (op == "PhaseFlipIfLess") {
+            const uint64_t v = tk.u();
+            const bitLenInt s = tk.i(), l = tk.i();
+            dynamic_cast<QAlu*>(q.get())->PhaseFlipIfLess(bitCapInt(v), s, l);
+        } else if (op == "CPhaseFlipIfLess") {
+            const uint64_t v = tk.u();
+            const bitLenInt s = tk.i(), l = tk.i(), f = tk.i();
+            dynamic_cast<QAlu*>(q.get())->CPhaseFlipIfLess(bitCapInt(v), s, l, f);
+#endif
         } else if (op == "SetPermutation") {
             q->SetPermutation(bitCapInt(tk.u()), ONE_CMPLX);
         } else if (op == "ForceM") {

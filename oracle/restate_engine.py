@@ -21,7 +21,7 @@ _lib = None
 
 
 def build_restatement(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("qengine_restate.c", "qengine_restate_impl.h")]
+    src = [os.path.join(_HERE, f) for f in ("qengine_restate.c", "qengine_restate_impl.h", "qalu_restate_impl.h")]
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in src):
         subprocess.run(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-fno-fast-math", "-ffp-contract=off", src[0], "-lm",
                         "-o", _LIB], check=True)
@@ -185,6 +185,44 @@ class _RestateBackend:
 
     def expectation(self, start, length):
         return self.fn("orc_expectation")(self._p(), c_int(self.nq), c_int(start), c_int(length))
+
+    # ---- QAlu family (oracle/qalu_restate_impl.h); the zero state is left untouched (CHECK_ZERO_SKIP) ----
+    def _alu(self, name, *args):
+        if self.amps is not None:
+            self.fn(name)(self._p(), c_int(self.nq), *args)
+
+    def alu_rol(self, shift, start, length):
+        self._alu("orc_rol", c_int(shift), c_int(start), c_int(length))
+
+    def alu_inc(self, to_add, start, length, ctrl_mask):
+        self._alu("orc_inc", c_uint64(to_add), c_int(start), c_int(length), c_uint64(ctrl_mask))
+
+    def alu_incdecc(self, to_mod, start, length, carry_index):
+        self._alu("orc_incdecc", c_uint64(to_mod), c_int(start), c_int(length), c_int(carry_index))
+
+    def alu_incs(self, to_add, start, length, overflow_index):
+        self._alu("orc_incs", c_uint64(to_add), c_int(start), c_int(length), c_int(overflow_index))
+
+    def alu_incdecsc(self, to_mod, start, length, overflow_index, carry_index):
+        self._alu("orc_incdecsc", c_uint64(to_mod), c_int(start), c_int(length), c_int(overflow_index), c_int(carry_index))
+
+    def alu_muldiv(self, inverse, to_mul, start, carry_start, length, ctrl_mask):
+        self._alu("orc_muldiv", c_int(inverse), c_uint64(to_mul), c_int(start), c_int(carry_start), c_int(length),
+                  c_uint64(ctrl_mask))
+
+    def alu_modnout(self, kind, to_mod, mod_n, in_start, out_start, length, ctrl_mask):
+        self._alu("orc_modnout", c_int(kind), c_uint64(to_mod), c_uint64(mod_n), c_int(in_start), c_int(out_start),
+                  c_int(length), c_uint64(ctrl_mask))
+
+    def alu_indexed(self, kind, index_start, index_length, value_start, value_length, carry_index, carry_in, values: bytes):
+        self._alu("orc_indexed", c_int(kind), c_int(index_start), c_int(index_length), c_int(value_start),
+                  c_int(value_length), c_int(carry_index), c_int(carry_in), ctypes.c_char_p(values))
+
+    def alu_hash(self, start, length, values: bytes):
+        self._alu("orc_hash", c_int(start), c_int(length), ctypes.c_char_p(values))
+
+    def alu_phase_flip_if_less(self, greater_perm, start, length, flag_index):
+        self._alu("orc_phase_flip_if_less", c_uint64(greater_perm), c_int(start), c_int(length), c_int(flag_index))
 
     def highest_prob(self):
         return 0 if self.amps is None else int(np.argmax(np.abs(self.amps) ** 2))

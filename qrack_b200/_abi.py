@@ -80,6 +80,16 @@ SIGNATURES = {
     "b200sv_ipc_import": [c_int, c_void_p, POINTER(c_void_p)],
     "b200sv_ipc_release": [c_int, c_void_p],
     "b200sv_exchange_scatter": [H, c_int, POINTER(c_int), c_int, POINTER(c_void_p)],
+    "b200sv_rol": [H, c_int, c_int, c_int],
+    "b200sv_inc": [H, c_uint64, c_int, c_int, c_uint64],
+    "b200sv_incdecc": [H, c_uint64, c_int, c_int, c_int],
+    "b200sv_incs": [H, c_uint64, c_int, c_int, c_int],
+    "b200sv_incdecsc": [H, c_uint64, c_int, c_int, c_int, c_int],
+    "b200sv_muldiv": [H, c_int, c_uint64, c_int, c_int, c_int, c_uint64],
+    "b200sv_modnout": [H, c_int, c_uint64, c_uint64, c_int, c_int, c_int, c_uint64],
+    "b200sv_indexed": [H, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_char_p],
+    "b200sv_hash": [H, c_int, c_int, c_char_p],
+    "b200sv_phase_flip_if_less": [H, c_uint64, c_int, c_int, c_int],
     "b200sv_flush": [H],
     "b200sv_finish": [H],
     "b200sv_set_fusion": [H, c_int],
@@ -98,7 +108,7 @@ _lib = None
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libb200sv.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inl"))]
     deps.append(os.path.join(_HERE, "..", "include", "b200sv.h"))
     if not force and os.path.exists(LIB_PATH):
         newest = max(os.path.getmtime(d) for d in deps if os.path.exists(d))

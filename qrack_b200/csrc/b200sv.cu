@@ -829,6 +829,8 @@ static int flush_queue(State* s)
 
 } // namespace b200sv
 
+#include "alu_kernels.cuh"
+
 using namespace b200sv;
 
 #define SV_ENTER(s)                                                                                                    \
@@ -2482,5 +2484,7 @@ int b200sv_flush_l2(b200sv_t s, uint64_t bytes)
     SV_CUDA(cudaGetLastError());
     return B200SV_OK;
 }
+
+#include "alu_abi.inl"
 
 } // extern "C"

@@ -367,7 +367,12 @@ class QEngineHost:
         controls = [start + i for i in range(length - 1)]
         self.MACPhase(controls, -1.0, 1.0, start + len(controls))
 
-    def INC(self, toAdd: int, start: int, length: int):  # src/qinterface/arithmetic.cpp:20-51 (gate-level)
+    def INC(self, toAdd: int, start: int, length: int):
+        """QEngineCPU::INC (src/qengine/arithmetic.cpp:73-118) as one basis-map sweep when the backend has ALU kernels;
+        otherwise the gate-level QInterface::INC (src/qinterface/arithmetic.cpp:20-51)."""
+        if self._has_alu():
+            self._check_range(start, length, "INC")
+            return self.be.alu_inc(toAdd & self._U64, start, length, 0)
         if not length:
             return
         if length == 1:
@@ -386,6 +391,268 @@ class QEngineHost:
     def DEC(self, toSub: int, start: int, length: int):  # qinterface.hpp:2050-2054: INC(2^length - toSub)
         invToSub = (1 << length) - toSub
         self.INC(invToSub & ((1 << length) - 1), start, length)
+
+    # ------------------------------------------------------------------------------------------------
+    # QAlu (include/qalu.hpp, src/qalu.cpp, src/qengine/arithmetic.cpp).  Engines whose backend provides the basis-map
+    # primitives (``alu_*``) run each member as ONE sweep; otherwise INC/DEC fall back to the gate-level QInterface form.
+    # ------------------------------------------------------------------------------------------------
+    _U64 = (1 << 64) - 1
+
+    def _has_alu(self) -> bool:
+        return hasattr(self.be, "alu_inc")
+
+    def _need_alu(self, what: str):
+        if not self._has_alu():
+            raise NotImplementedError("%s needs an engine with native ALU kernels" % what)
+
+    def _check_range(self, start: int, length: int, what: str):  # isBadBitRange
+        if start < 0 or length < 0 or start + length > self.qubitCount:
+            raise ValueError("%s range is out-of-bounds!" % what)
+
+    def _ctrl_mask(self, controls, what: str) -> int:  # ThrowIfQbIdArrayIsBad
+        m = 0
+        for c in controls:
+            self._check_qubit(c, what + " control")
+            m |= 1 << c
+        return m
+
+    def SetBit(self, qubit: int, value: bool):  # qinterface.hpp: if (value != M(qubit)) X(qubit)
+        if bool(value) != self.M(qubit):
+            self.X(qubit)
+
+    def MReg(self, start: int, length: int) -> int:
+        return self.ForceMReg(start, length, 0, False, True)
+
+    def SetReg(self, start: int, length: int, value: int):  # src/qinterface/qinterface.cpp:195-212
+        if length == 1:
+            return self.SetBit(start, bool(value & 1))
+        if start == 0 and length == self.qubitCount:
+            return self.SetPermutation(value)
+        reg = self.MReg(start, length)
+        for i in range(length):
+            if ((reg >> i) & 1) != ((value >> i) & 1):
+                self.X(start + i)
+
+    def ROL(self, shift: int, start: int, length: int):  # arithmetic.cpp:23-70
+        self._need_alu("ROL")
+        self._check_range(start, length, "ROL")
+        self.be.alu_rol(shift, start, length)
+
+    def ROR(self, shift: int, start: int, length: int):  # qengine.hpp: ROL(length - shift)
+        if not length:
+            return
+        self.ROL(length - (shift % length), start, length)
+
+    def CINC(self, toAdd: int, start: int, length: int, controls):  # arithmetic.cpp:121-172
+        self._need_alu("CINC")
+        self._check_range(start, length, "CINC")
+        self.be.alu_inc(toAdd & self._U64, start, length, self._ctrl_mask(controls, "CINC"))
+
+    def CDEC(self, toSub: int, start: int, length: int, controls):  # qalu.cpp:30-34
+        self.CINC(((1 << length) - toSub) & self._U64, start, length, controls)
+
+    def INCDECC(self, toMod: int, start: int, length: int, carryIndex: int):  # arithmetic.cpp:175-224
+        self._need_alu("INCDECC")
+        self._check_range(start, length, "INCDECC")
+        self._check_qubit(carryIndex, "INCDECC carryIndex")
+        self.be.alu_incdecc(toMod & self._U64, start, length, carryIndex)
+
+    def INCC(self, toAdd: int, start: int, length: int, carryIndex: int):  # qalu.cpp:48-61
+        if not length:
+            return
+        if self.M(carryIndex):
+            self.X(carryIndex)
+            self.INCDECC((toAdd + 1) & self._U64, start, length, carryIndex)
+        else:
+            self.INCDECC(toAdd, start, length, carryIndex)
+
+    def _inv_carry(self, toSub: int, length: int, carryIndex: int) -> int:  # qalu.cpp:64-77 (shared by DECC / DECSC)
+        inv = (1 << length) - toSub
+        if self.M(carryIndex):
+            self.X(carryIndex)
+        elif inv == 0:
+            inv = self._U64
+        else:
+            inv -= 1
+        return inv & self._U64
+
+    def DECC(self, toSub: int, start: int, length: int, carryIndex: int):
+        self.INCDECC(self._inv_carry(toSub, length, carryIndex), start, length, carryIndex)
+
+    def INCS(self, toAdd: int, start: int, length: int, overflowIndex: int):  # arithmetic.cpp:227-309
+        self._need_alu("INCS")
+        self._check_range(start, length, "INCS")
+        self._check_qubit(overflowIndex, "INCS overflowIndex")
+        self.be.alu_incs(toAdd & self._U64, start, length, overflowIndex)
+
+    def DECS(self, toSub: int, start: int, length: int, overflowIndex: int):  # qalu.cpp:41-45
+        self.INCS(((1 << length) - toSub) & self._U64, start, length, overflowIndex)
+
+    def INCDECSC(self, toMod: int, start: int, length: int, *idx):  # arithmetic.cpp:312-419; idx = (carry) | (overflow, carry)
+        self._need_alu("INCDECSC")
+        self._check_range(start, length, "INCDECSC")
+        overflowIndex, carryIndex = (-1, idx[0]) if len(idx) == 1 else (idx[0], idx[1])
+        self._check_qubit(carryIndex, "INCDECSC carryIndex")
+        if overflowIndex >= 0:
+            self._check_qubit(overflowIndex, "INCDECSC overflowIndex")
+        self.be.alu_incdecsc(toMod & self._U64, start, length, overflowIndex, carryIndex)
+
+    def INCSC(self, toAdd: int, start: int, length: int, *idx):  # qalu.cpp:85-96, 131-140
+        carryIndex = idx[-1]
+        if self.M(carryIndex):
+            self.X(carryIndex)
+            self.INCDECSC((toAdd + 1) & self._U64, start, length, *idx)
+        else:
+            self.INCDECSC(toAdd, start, length, *idx)
+
+    def DECSC(self, toSub: int, start: int, length: int, *idx):  # qalu.cpp:103-117, 148-160
+        self.INCDECSC(self._inv_carry(toSub, length, idx[-1]), start, length, *idx)
+
+    def MUL(self, toMul: int, inOutStart: int, carryStart: int, length: int):  # arithmetic.cpp:458-471
+        self._need_alu("MUL")
+        self.SetReg(carryStart, length, 0)
+        if toMul == 0:
+            return self.SetReg(inOutStart, length, 0)
+        if toMul == 1:
+            return
+        self._check_range(inOutStart, length, "MUL")
+        self._check_range(carryStart, length, "MUL carry")
+        self.be.alu_muldiv(0, toMul & self._U64, inOutStart, carryStart, length, 0)
+
+    def DIV(self, toDiv: int, inOutStart: int, carryStart: int, length: int):  # :474-485
+        self._need_alu("DIV")
+        if toDiv == 0:
+            raise ValueError("DIV by zero")
+        if toDiv == 1:
+            return
+        self._check_range(inOutStart, length, "DIV")
+        self._check_range(carryStart, length, "DIV carry")
+        self.be.alu_muldiv(1, toDiv & self._U64, inOutStart, carryStart, length, 0)
+
+    def CMUL(self, toMul: int, inOutStart: int, carryStart: int, length: int, controls):  # :553-573
+        if not controls:
+            return self.MUL(toMul, inOutStart, carryStart, length)
+        self._need_alu("CMUL")
+        self.SetReg(carryStart, length, 0)
+        if toMul == 0:
+            return self.SetReg(inOutStart, length, 0)
+        if toMul == 1:
+            return
+        self._check_range(inOutStart, length, "CMUL")
+        self._check_range(carryStart, length, "CMUL carry")
+        self.be.alu_muldiv(0, toMul & self._U64, inOutStart, carryStart, length, self._ctrl_mask(controls, "CMUL"))
+
+    def CDIV(self, toDiv: int, inOutStart: int, carryStart: int, length: int, controls):  # :575-593
+        if not controls:
+            return self.DIV(toDiv, inOutStart, carryStart, length)
+        self._need_alu("CDIV")
+        if toDiv == 0:
+            raise ValueError("CDIV by zero")
+        if toDiv == 1:
+            return
+        self._check_range(inOutStart, length, "CDIV")
+        self._check_range(carryStart, length, "CDIV carry")
+        self.be.alu_muldiv(1, toDiv & self._U64, inOutStart, carryStart, length, self._ctrl_mask(controls, "CDIV"))
+
+    def _modnout(self, kind: int, toMod: int, modN: int, inStart: int, outStart: int, length: int, controls, what: str):
+        self._need_alu(what)
+        self._check_range(inStart, length, what + " inStart")
+        self._check_range(outStart, length, what + " outStart")
+        self.be.alu_modnout(kind, toMod & self._U64, modN & self._U64, inStart, outStart, length,
+                             self._ctrl_mask(controls, what))
+
+    def MULModNOut(self, toMod: int, modN: int, inStart: int, outStart: int, length: int):  # :634-644
+        self.SetReg(outStart, length, 0)
+        if toMod == 0:
+            return
+        self._modnout(0, toMod, modN, inStart, outStart, length, (), "MULModNOut")
+
+    def IMULModNOut(self, toMod: int, modN: int, inStart: int, outStart: int, length: int):  # :647-655
+        if toMod == 0:
+            return
+        self._modnout(1, toMod, modN, inStart, outStart, length, (), "IMULModNOut")
+
+    def POWModNOut(self, toMod: int, modN: int, inStart: int, outStart: int, length: int):  # :658-667
+        if toMod == 1:
+            return self.SetReg(outStart, length, 1)
+        self._modnout(2, toMod, modN, inStart, outStart, length, (), "POWModNOut")
+
+    def CMULModNOut(self, toMod: int, modN: int, inStart: int, outStart: int, length: int, controls):  # :737-748
+        if not controls:
+            return self.MULModNOut(toMod, modN, inStart, outStart, length)
+        self.SetReg(outStart, length, 0)
+        self._modnout(0, toMod, modN, inStart, outStart, length, controls, "CMULModNOut")
+
+    def CIMULModNOut(self, toMod: int, modN: int, inStart: int, outStart: int, length: int, controls):  # :751-760
+        if not controls:
+            return self.IMULModNOut(toMod, modN, inStart, outStart, length)
+        self._modnout(1, toMod, modN, inStart, outStart, length, controls, "CIMULModNOut")
+
+    def CPOWModNOut(self, toMod: int, modN: int, inStart: int, outStart: int, length: int, controls):  # :763-774
+        if not controls:
+            return self.POWModNOut(toMod, modN, inStart, outStart, length)
+        self._modnout(2, toMod, modN, inStart, outStart, length, controls, "CPOWModNOut")
+
+    def _table(self, values, entries: int, entryBytes: int) -> bytes:
+        b = bytes(values)
+        if len(b) < entries * entryBytes:
+            raise ValueError("classical table is too short")
+        return b
+
+    def IndexedLDA(self, indexStart: int, indexLength: int, valueStart: int, valueLength: int, values,
+                   resetValue: bool = True) -> int:  # :983-1083
+        self._need_alu("IndexedLDA")
+        self._check_range(indexStart, indexLength, "IndexedLDA index")
+        self._check_range(valueStart, valueLength, "IndexedLDA value")
+        if resetValue:
+            self.SetReg(valueStart, valueLength, 0)
+        tab = self._table(values, 1 << indexLength, (valueLength + 7) >> 3)
+        self.be.alu_indexed(0, indexStart, indexLength, valueStart, valueLength, 0, 0, tab)
+        return 0
+
+    def IndexedADC(self, indexStart: int, indexLength: int, valueStart: int, valueLength: int, carryIndex: int,
+                   values) -> int:  # :1086-1260
+        self._need_alu("IndexedADC")
+        self._check_range(indexStart, indexLength, "IndexedADC index")
+        self._check_range(valueStart, valueLength, "IndexedADC value")
+        self._check_qubit(carryIndex, "IndexedADC carryIndex")
+        carryIn = 0
+        if self.M(carryIndex):
+            carryIn = 1
+            self.X(carryIndex)
+        tab = self._table(values, 1 << indexLength, (valueLength + 7) >> 3)
+        self.be.alu_indexed(1, indexStart, indexLength, valueStart, valueLength, carryIndex, carryIn, tab)
+        return 0
+
+    def IndexedSBC(self, indexStart: int, indexLength: int, valueStart: int, valueLength: int, carryIndex: int,
+                   values) -> int:  # :1263-1444
+        self._need_alu("IndexedSBC")
+        self._check_range(indexStart, indexLength, "IndexedSBC index")
+        self._check_range(valueStart, valueLength, "IndexedSBC value")
+        self._check_qubit(carryIndex, "IndexedSBC carryIndex")
+        carryIn = 1
+        if self.M(carryIndex):
+            carryIn = 0
+            self.X(carryIndex)
+        tab = self._table(values, 1 << indexLength, (valueLength + 7) >> 3)
+        self.be.alu_indexed(2, indexStart, indexLength, valueStart, valueLength, carryIndex, carryIn, tab)
+        return 0
+
+    def Hash(self, start: int, length: int, values):  # :1447-1506
+        self._need_alu("Hash")
+        self._check_range(start, length, "Hash")
+        self.be.alu_hash(start, length, self._table(values, 1 << length, (length + 7) >> 3))
+
+    def PhaseFlipIfLess(self, greaterPerm: int, start: int, length: int):  # :1703-1720
+        self._need_alu("PhaseFlipIfLess")
+        self._check_range(start, length, "PhaseFlipIfLess")
+        self.be.alu_phase_flip_if_less(greaterPerm & self._U64, start, length, -1)
+
+    def CPhaseFlipIfLess(self, greaterPerm: int, start: int, length: int, flagIndex: int):  # :1678-1701
+        self._need_alu("CPhaseFlipIfLess")
+        self._check_range(start, length, "CPhaseFlipIfLess")
+        self._check_qubit(flagIndex, "CPhaseFlipIfLess flagIndex")
+        self.be.alu_phase_flip_if_less(greaterPerm & self._U64, start, length, flagIndex)
 
     # swap family (qengine.cpp:407-460)
     def _swap2(self, q1: int, q2: int, m):
@@ -1065,6 +1332,38 @@ class _CudaBackend:
 
     def dispose_perm(self, start, length, perm):
         self._ck(self.lib.b200sv_dispose_perm(self.h, start, length, perm))
+
+    # ---- QAlu family (include/b200sv.h "QAlu family") ----
+    def alu_rol(self, shift, start, length):
+        self._ck(self.lib.b200sv_rol(self.h, shift, start, length))
+
+    def alu_inc(self, to_add, start, length, ctrl_mask):
+        self._ck(self.lib.b200sv_inc(self.h, to_add, start, length, ctrl_mask))
+
+    def alu_incdecc(self, to_mod, start, length, carry_index):
+        self._ck(self.lib.b200sv_incdecc(self.h, to_mod, start, length, carry_index))
+
+    def alu_incs(self, to_add, start, length, overflow_index):
+        self._ck(self.lib.b200sv_incs(self.h, to_add, start, length, overflow_index))
+
+    def alu_incdecsc(self, to_mod, start, length, overflow_index, carry_index):
+        self._ck(self.lib.b200sv_incdecsc(self.h, to_mod, start, length, overflow_index, carry_index))
+
+    def alu_muldiv(self, inverse, to_mul, start, carry_start, length, ctrl_mask):
+        self._ck(self.lib.b200sv_muldiv(self.h, inverse, to_mul, start, carry_start, length, ctrl_mask))
+
+    def alu_modnout(self, kind, to_mod, mod_n, in_start, out_start, length, ctrl_mask):
+        self._ck(self.lib.b200sv_modnout(self.h, kind, to_mod, mod_n, in_start, out_start, length, ctrl_mask))
+
+    def alu_indexed(self, kind, index_start, index_length, value_start, value_length, carry_index, carry_in, values: bytes):
+        self._ck(self.lib.b200sv_indexed(self.h, kind, index_start, index_length, value_start, value_length, carry_index,
+                                        carry_in, values))
+
+    def alu_hash(self, start, length, values: bytes):
+        self._ck(self.lib.b200sv_hash(self.h, start, length, values))
+
+    def alu_phase_flip_if_less(self, greater_perm, start, length, flag_index):
+        self._ck(self.lib.b200sv_phase_flip_if_less(self.h, greater_perm, start, length, flag_index))
 
     def set_fusion(self, mode: int):
         self._ck(self.lib.b200sv_set_fusion(self.h, mode))

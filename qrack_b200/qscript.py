@@ -133,6 +133,37 @@ def run(text: str, make_reg: Callable[[int, int], object]) -> Tuple[Dict[int, ob
             q.PhaseRootNMask(int(t[1]), int(t[2]))
         elif op in ("INC", "DEC"):
             getattr(q, op)(int(t[1]), int(t[2]), int(t[3]))
+        elif op in ("ROL", "ROR"):
+            getattr(q, op)(int(t[1]), int(t[2]), int(t[3]))
+        elif op in ("CINC", "CDEC"):
+            c, p = _qubits(t, 1)
+            getattr(q, op)(int(t[p]), int(t[p + 1]), int(t[p + 2]), c)
+        elif op in ("INCC", "DECC", "INCS", "DECS"):
+            getattr(q, op)(int(t[1]), int(t[2]), int(t[3]), int(t[4]))
+        elif op in ("INCSCc", "DECSCc"):  # carry-only forms
+            getattr(q, op[:-1])(int(t[1]), int(t[2]), int(t[3]), int(t[4]))
+        elif op in ("INCSC", "DECSC"):  # overflow flag + carry
+            getattr(q, op)(int(t[1]), int(t[2]), int(t[3]), int(t[4]), int(t[5]))
+        elif op in ("MUL", "DIV"):
+            getattr(q, op)(int(t[1]), int(t[2]), int(t[3]), int(t[4]))
+        elif op in ("CMUL", "CDIV"):
+            c, p = _qubits(t, 1)
+            getattr(q, op)(int(t[p]), int(t[p + 1]), int(t[p + 2]), int(t[p + 3]), c)
+        elif op in ("MULModNOut", "IMULModNOut", "POWModNOut"):
+            getattr(q, op)(int(t[1]), int(t[2]), int(t[3]), int(t[4]), int(t[5]))
+        elif op in ("CMULModNOut", "CIMULModNOut", "CPOWModNOut"):
+            c, p = _qubits(t, 1)
+            getattr(q, op)(int(t[p]), int(t[p + 1]), int(t[p + 2]), int(t[p + 3]), int(t[p + 4]), c)
+        elif op == "IndexedLDA":
+            q.IndexedLDA(int(t[1]), int(t[2]), int(t[3]), int(t[4]), bytes.fromhex(t[5]), True)
+        elif op in ("IndexedADC", "IndexedSBC"):
+            getattr(q, op)(int(t[1]), int(t[2]), int(t[3]), int(t[4]), int(t[5]), bytes.fromhex(t[6]))
+        elif op == "Hash":
+            q.Hash(int(t[1]), int(t[2]), bytes.fromhex(t[3]))
+        elif op == "PhaseFlipIfLess":
+            q.PhaseFlipIfLess(int(t[1]), int(t[2]), int(t[3]))
+        elif op == "CPhaseFlipIfLess":
+            q.CPhaseFlipIfLess(int(t[1]), int(t[2]), int(t[3]), int(t[4]))
         elif op == "SetPermutation":
             q.SetPermutation(int(t[1]), 1.0 + 0j)
         elif op == "ForceM":

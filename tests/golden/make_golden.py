@@ -151,6 +151,60 @@ def qft_roundtrip(n=10, seed=4):
     return "\n".join(L) + "\n"
 
 
+def _u_layer(L, rng, qubits):
+    for q in qubits:
+        L.append("U %d %.17g %.17g %.17g" % (q, rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-3, 3)))
+
+
+def alu_add(seed=21):
+    """QAlu adders.  Register 0..4, carries 5..8 (each used once, so every M(carry) is deterministic),
+    overflow flag 9 (in superposition), controls 10, 11."""
+    rng = random.Random(seed)
+    L = ["qubits 12"]
+    _u_layer(L, rng, [0, 1, 2, 3, 4, 9, 10, 11])
+    L += ["CNOT 0 3", "CNOT 10 2", "CNOT 4 11"]
+    L += ["INC 7 0 5", "DEC 3 1 4", "CINC 2 10 11 5 0 5", "CDEC 1 11 9 1 4", "ROL 2 0 5", "ROR 1 0 5"]
+    L += ["PhaseFlipIfLess 13 0 5", "CPhaseFlipIfLess 21 0 5 10"]
+    L += ["INCS 11 0 5 9", "DECS 6 0 5 9"]
+    L += ["INCC 9 0 5 5", "X 6", "DECC 5 0 5 6", "INCSC 13 0 5 9 7", "X 8", "DECSCc 4 0 5 8"]
+    for q in range(12):
+        L.append("Prob %d" % q)
+    L += ["GetAmplitude 77", "Norm"]
+    return "\n".join(L) + "\n"
+
+
+def alu_mul(seed=22):
+    """MUL/DIV and the ModNOut family.  in 0..3, out/carry A 4..7, out B 8..11, controls 12, 13."""
+    rng = random.Random(seed)
+    L = ["qubits 14"]
+    _u_layer(L, rng, [0, 1, 2, 3, 12, 13])
+    L += ["CNOT 1 12", "CNOT 13 2"]
+    L += ["MUL 5 0 4 4", "Prob 5", "DIV 5 0 4 4", "CMUL 2 12 13 3 0 4 4", "Prob 4", "CDIV 2 12 13 3 0 4 4"]
+    L += ["MULModNOut 3 13 0 4 4", "Prob 6", "IMULModNOut 3 13 0 4 4", "POWModNOut 2 11 0 4 4"]
+    L += ["CMULModNOut 2 12 13 5 7 0 8 4", "Prob 9", "CIMULModNOut 2 12 13 5 7 0 8 4", "CPOWModNOut 1 12 3 13 0 8 4"]
+    for q in range(14):
+        L.append("Prob %d" % q)
+    L += ["GetAmplitude 1234", "Norm"]
+    return "\n".join(L) + "\n"
+
+
+def alu_idx(seed=23):
+    """IndexedLDA / ADC / SBC and Hash.  index 0..2, value 3..6, ADC carry 7, hash register 8..10, SBC carry 11."""
+    rng = random.Random(seed)
+    L = ["qubits 12"]
+    _u_layer(L, rng, [0, 1, 2, 8, 9, 10])
+    L += ["CNOT 0 9"]
+    tab = lambda: bytes(rng.randrange(16) for _ in range(8)).hex()
+    perm = list(range(8))
+    rng.shuffle(perm)
+    L += ["IndexedLDA 0 3 3 4 %s" % tab(), "Prob 4", "IndexedADC 0 3 3 4 7 %s" % tab(), "X 11",
+          "IndexedSBC 0 3 3 4 11 %s" % tab(), "Hash 8 3 %s" % bytes(perm).hex()]
+    for q in range(12):
+        L.append("Prob %d" % q)
+    L += ["GetAmplitude 99", "Norm"]
+    return "\n".join(L) + "\n"
+
+
 SCRIPTS = {
     "htcnot_10q": qscript.random_htcnot(10, 12, seed=20250921, timed=False),
     "htcnot_12q": qscript.random_htcnot(12, 20, seed=12, timed=False),
@@ -160,6 +214,9 @@ SCRIPTS = {
     "misc_8q": misc_gates(8),
     "structure": structure(),
     "grover_8q": qscript.grover(8, 4, target=3, timed=False),
+    "alu_add_12q": alu_add(),
+    "alu_mul_14q": alu_mul(),
+    "alu_idx_12q": alu_idx(),
 }
 
 

@@ -106,6 +106,9 @@ public:
     real1_f ProbParity(const bitCapInt& mask);
     bool ForceMParity(const bitCapInt& mask, bool result, bool doForce = true);
     bitCapInt MAll();
+    using QInterface::HighestProbAll;
+    bitCapInt HighestProbAll(); // device arg-max; the QInterface default asks ProbAll() for every permutation
+    real1_f FirstNonzeroPhase() { return IsZeroAmplitude() ? ZERO_R1_F : QInterface::FirstNonzeroPhase(); }
     real1_f GetExpectation(bitLenInt valueStart, bitLenInt valueLength);
 
     // ---- structure ----

@@ -607,6 +607,16 @@ bool QEngineCUDA::ForceMParity(const bitCapInt& mask, bool result, bool doForce)
     return result;
 }
 
+bitCapInt QEngineCUDA::HighestProbAll()
+{
+    if (IsZeroAmplitude()) {
+        return ZERO_BCI; // reference src/qengine/cuda.cu:2906-2912
+    }
+    uint64_t perm = 0U;
+    Check(b200sv_highest_prob(sv, &perm));
+    return bitCapInt((bitCapIntOcl)perm);
+}
+
 bitCapInt QEngineCUDA::MAll()
 {
     // QEngineCPU::MAll (state.cpp:2026-2050) with the cumulative search done on the device

@@ -16,11 +16,25 @@ static int alu_run(State* s, AluDesc d, bool needZero, const unsigned char* host
     }
     const uint64_t n = s->dim();
     const size_t bytes = (size_t)n * s->amp_bytes();
+    // destination: the state's spare buffer (kept from the previous QAlu call) or a fresh allocation
     void* out = nullptr;
-    cudaError_t e = cudaMalloc(&out, bytes);
-    if (e != cudaSuccess) {
-        return cuda_fail(e, "cudaMalloc(alu)");
+    cudaError_t e = cudaSuccess;
+    if (s->spare && s->spare_bytes == bytes) {
+        out = s->spare;
+    } else {
+        if (s->spare) {
+            cudaStreamSynchronize(s->stream);
+            cudaFree(s->spare);
+        }
+        s->spare = nullptr;
+        s->spare_bytes = 0;
+        e = cudaMalloc(&out, bytes);
+        if (e != cudaSuccess) {
+            return cuda_fail(e, "cudaMalloc(alu)");
+        }
     }
+    s->spare = out; // owned by the state from here on, whatever happens below
+    s->spare_bytes = bytes;
     unsigned char* dtab = nullptr;
     if (hostTable && tableBytes) {
         e = cudaMalloc(&dtab, tableBytes);
@@ -28,7 +42,6 @@ static int alu_run(State* s, AluDesc d, bool needZero, const unsigned char* host
             e = cudaMemcpyAsync(dtab, hostTable, tableBytes, cudaMemcpyHostToDevice, s->stream);
         }
         if (e != cudaSuccess) {
-            cudaFree(out);
             cudaFree(dtab);
             return cuda_fail(e, "alu table upload");
         }
@@ -49,20 +62,21 @@ static int alu_run(State* s, AluDesc d, bool needZero, const unsigned char* host
         s->stats.bytes_swept += 2ULL * bytes;
     }
     if (e == cudaSuccess && s->external) {
+        // the caller owns the buffer (P2P page / torch tensor): results go back into it
         e = cudaMemcpyAsync(s->amps, out, bytes, cudaMemcpyDeviceToDevice, s->stream);
     }
-    if (e == cudaSuccess && (s->external || dtab)) {
-        e = cudaStreamSynchronize(s->stream);
+    if (dtab) {
+        if (e == cudaSuccess) {
+            e = cudaStreamSynchronize(s->stream); // the host table may go away as soon as we return
+        }
+        cudaFree(dtab);
     }
-    cudaFree(dtab);
     if (e != cudaSuccess) {
-        cudaFree(out);
         return cuda_fail(e, "alu map");
     }
-    if (s->external) {
-        cudaFree(out);
-    } else {
-        free_amps(s); // synchronises the stream first
+    if (!s->external) {
+        // ping-pong: the old buffer becomes the spare; everything is ordered on the state's stream, no sync needed
+        s->spare = s->amps;
         s->amps = out;
     }
     return B200SV_OK;
@@ -91,8 +105,11 @@ int b200sv_rol(b200sv_t s, int shift, int start, int length)
     if (!shift) {
         return B200SV_OK;
     }
+    // gather form: out[i] = in[rotr(i, shift)] — the strided side of the bit rotation is then the READ side (sector
+    // over-fetch) instead of the WRITE side (partial-sector read-modify-write), ~2x faster on HBM
     AluDesc d = alu_desc(ALU_ROL, start, length);
-    d.arg = (uint64_t)shift;
+    d.arg = (uint64_t)(length - shift);
+    d.gather = 1;
     return alu_run(s, d, false, nullptr, 0);
 }
 

@@ -793,9 +793,16 @@ static int alloc_amps(State* s, bool clear)
 
 static void free_amps(State* s)
 {
-    if (s->amps && !s->external) {
+    if ((s->amps && !s->external) || s->spare) {
         cudaStreamSynchronize(s->stream);
+    }
+    if (s->amps && !s->external) {
         cudaFree(s->amps);
+    }
+    if (s->spare) {
+        cudaFree(s->spare); // the ping-pong buffer goes with the state it was sized for
+        s->spare = nullptr;
+        s->spare_bytes = 0;
     }
     s->amps = nullptr;
 }

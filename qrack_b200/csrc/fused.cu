@@ -25,7 +25,7 @@
 namespace b200sv {
 
 constexpr int MAX_HIGH = 8;
-constexpr int MAX_PASS = 12;
+constexpr int MAX_PASS = 8;
 constexpr int MAX_OPS = 96;
 constexpr int MAX_HOST_OPS = 384; // gates per sweep before merging (LAYER / DIAG groups shrink them to <= MAX_OPS device ops)
 constexpr int MAX_SLOTS = 128; // per-tile phase table (1 + register-bit phases of the DIAG ops); filled by warps 4..7
@@ -59,6 +59,8 @@ struct DevPass {
     unsigned char sbit[16];        // sub-block index bit i -> tile chunk bit
     unsigned short pswzB[MAX_NCH]; // register chunk e -> swizzled byte offset inside the tile
     unsigned short itoffC[16];     // iteration -> chunk-index contribution of the sub-block bits above the thread id
+    unsigned int pad;
+    uint64_t goff[MAX_NCH];        // register chunk e -> global amplitude offset (first / last pass move straight HBM <-> registers)
 };
 
 struct alignas(16) DevSweep {
@@ -74,7 +76,9 @@ struct alignas(16) DevSweep {
     int prefetch; // 1: pull the CTA's next tile into L2 while this one is being computed
     // scale: deferred scalar of the un-normalised Hadamard butterflies, applied once in the last pass
     int nSlots;   // per-tile phase table entries: slot 0 = tile scalar, slots 1.. = register-bit phases of the DIAG ops
-    int pad3[3];
+    int scratchBytes; // shared memory behind the program: chunk-row offsets + the double-buffered phase table
+    int directIn;  // 1: the first pass reads its sub-blocks straight from HBM; 0: coalesced copy into the smem tile first
+    int directOut; // 1: the last pass writes straight to HBM; 0: through the smem tile
     unsigned short slotBeg[MAX_SLOTS + 1]; // slot s multiplies the outer records [slotBeg[s], slotBeg[s+1])
     uint64_t highLow[MAX_HIGH]; // (2^q - 1) for push_apart of the tile base, ascending
     uint64_t highPow[MAX_HIGH]; // 2^q
@@ -367,6 +371,46 @@ template <typename R> struct DevOuterPhase {
 
 constexpr int MAX_OUTER = 64;
 
+// Staged tile copies (used when the first / last pass has register bits on low chunk bits): coalesced HBM <-> swizzled
+// smem.  Kept out of line so that their registers do not weigh on the pass loop.
+template <typename R, int NT>
+__device__ __noinline__ void stage_in(const typename Cx<R>::type* __restrict__ tilePsi, unsigned char* tileB, const uint64_t* rowOff,
+    uint32_t nChunk, int lcb, uint32_t colMask, int tid)
+{
+    constexpr int APC = AmpOps<R>::APC;
+    if (nChunk >= 8U * NT) {
+        for (uint32_t c0 = (uint32_t)tid; c0 < nChunk; c0 += 8U * NT) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t c = c0 + (uint32_t)u * NT;
+                v[u] = ld_stream(reinterpret_cast<const uint4*>(tilePsi + rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t c = c0 + (uint32_t)u * NT;
+                *reinterpret_cast<uint4*>(tileB + ((size_t)swz(c) << 4)) = v[u];
+            }
+        }
+    } else {
+        for (uint32_t c = (uint32_t)tid; c < nChunk; c += NT) {
+            *reinterpret_cast<uint4*>(tileB + ((size_t)swz(c) << 4)) =
+                ld_stream(reinterpret_cast<const uint4*>(tilePsi + rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC));
+        }
+    }
+}
+template <typename R, int NT>
+__device__ __noinline__ void stage_out(typename Cx<R>::type* __restrict__ tilePsi, const unsigned char* tileB, const uint64_t* rowOff,
+    uint32_t nChunk, int lcb, uint32_t colMask, int tid)
+{
+    constexpr int APC = AmpOps<R>::APC;
+#pragma unroll 4
+    for (uint32_t c = (uint32_t)tid; c < nChunk; c += NT) {
+        st_stream(reinterpret_cast<uint4*>(tilePsi + rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC),
+            *reinterpret_cast<const uint4*>(tileB + ((size_t)swz(c) << 4)));
+    }
+}
+
 template <typename R, int KC, int RB, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
     k_fused_sweep(typename Cx<R>::type* __restrict__ psi, const unsigned char* __restrict__ prog, uint32_t progBytes, uint64_t nTiles)
@@ -383,9 +427,7 @@ __global__ void __launch_bounds__(NT, MINB)
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* tileB = smem;
     unsigned char* sprog = smem + ((size_t)16 << KC);
-    __shared__ uint64_t uOff[(1 << KC) / NT];
-    __shared__ uint32_t ballots[4];
-    __shared__ R tileScale[2 * MAX_SLOTS]; // [0..1] tile scalar, then the DIAG register-bit phases
+    __shared__ uint32_t ballots[2][4]; // double-buffered by tile parity (like tileTab) so that one barrier per tile is enough
 
     const int tid = threadIdx.x;
     for (uint32_t i = tid; i < progBytes / 16; i += NT) {
@@ -398,10 +440,13 @@ __global__ void __launch_bounds__(NT, MINB)
     const uint32_t nChunk = 1U << kc;
     const int lcb = sw.lowAmpBits - (APC == 2 ? 1 : 0); // low (contiguous) chunk bits
     const uint32_t colMask = (1U << lcb) - 1U;
-    // global amplitude offset of each chunk row (depends only on the sweep's high qubits); the tile area is free
-    // scratch until the first load
-    uint64_t* rowOff = reinterpret_cast<uint64_t*>(smem);
-    for (uint32_t r = tid; r < (nChunk >> lcb); r += NT) {
+    // scratch behind the program: global amplitude offset of each chunk row of the tile (depends only on the sweep's high
+    // qubits), then the per-tile phase table ([0..1] tile scalar, then the DIAG register-bit phases), double-buffered
+    const uint32_t nRows = nChunk >> lcb;
+    uint64_t* const rowOff = reinterpret_cast<uint64_t*>(sprog + progBytes);
+    R* const tileTab = reinterpret_cast<R*>(rowOff + nRows);
+    const uint32_t tabStride = 2U * (uint32_t)sw.nSlots;
+    for (uint32_t r = tid; r < nRows; r += NT) {
         uint64_t off = 0;
         for (int h = 0; h < sw.nHigh; ++h) {
             if ((r >> h) & 1U) {
@@ -410,39 +455,32 @@ __global__ void __launch_bounds__(NT, MINB)
         }
         rowOff[r] = off;
     }
-    __syncthreads();
-    // Thread `tid` moves chunks c = tid + NT*u.  Because NT is a power of two, the global offset of chunk c separates
-    // into a per-thread part and a per-iteration (uniform) part, and the swizzled smem slot is swz(tid) + NT*u.
-    constexpr int NU = (1 << KC) / NT; // chunks per thread for a full tile
-    if (tid < NU) {
-        const uint32_t cu = (uint32_t)tid * NT;
-        uOff[tid] = (cu < nChunk) ? rowOff[cu >> lcb] + (uint64_t)(cu & colMask) * APC : 0;
-    }
-    const uint32_t nU = (nChunk >= (uint32_t)NT) ? (nChunk / NT) : 1U; // iterations actually needed
-    const bool mover = (uint32_t)tid < nChunk;
-    const uint64_t tOff = mover ? rowOff[(uint32_t)tid >> lcb] + (uint64_t)((uint32_t)tid & colMask) * APC : 0;
-    unsigned char* const tSlot = tileB + ((size_t)swz((uint32_t)tid) << 4);
-    __syncthreads();
     const uint32_t nSub = nChunk >> RB;
     const int nOps = sw.nOps;
     const int nOuter = sw.nOuter;
+    const int nPass = sw.nPass;
     const DevOuterPhase<R>* outer = reinterpret_cast<const DevOuterPhase<R>*>(sprog + sw.outerOff);
+    __syncthreads();
 
-    for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
+    uint32_t par = 0;
+    for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x, par ^= 1U) {
         uint64_t base = t << sw.lowAmpBits;
         for (int h = 0; h < sw.nHigh; ++h) {
             const uint64_t lo = base & sw.highLow[h];
             base = ((base ^ lo) << 1) | lo;
         }
-        // ---- per-tile preamble (consumed after the load's barrier) -----------------------------------------------
+        C* const tilePsi = psi + base;
+        R* const tileScale = tileTab + par * tabStride;
+        // ---- per-tile preamble ------------------------------------------------------------------------------------
         // warps 0..2: which ops act on this tile (predicates on qubits outside the tile are uniform per tile)
         // warp 3   : product of the outer-only phases that fire for this tile, times the deferred Hadamard scale
+        // warps 4..: one thread per DIAG table slot
         if (tid < 96) {
             const DevOp<R>& aop = ops[tid < nOps ? tid : 0];
             const bool act = (tid < nOps) && ((base & aop.omask) == aop.oval);
             const uint32_t bal = __ballot_sync(0xffffffffU, act);
             if ((tid & 31) == 0) {
-                ballots[tid >> 5] = bal;
+                ballots[par][tid >> 5] = bal;
             }
         } else if (tid < 128) {
             R fx = (R)1, fy = (R)0;
@@ -466,7 +504,7 @@ __global__ void __launch_bounds__(NT, MINB)
                 tileScale[1] = fy * (R)sw.scale;
             }
         } else if (tid - 127 < sw.nSlots) {
-            // one thread per DIAG table slot: product (in double) of the member phases that fire for this tile
+            // product (in double) of the member phases that fire for this tile
             const int sl = tid - 127;
             double fx = 1.0, fy = 0.0;
             for (int i = sw.slotBeg[sl], e = sw.slotBeg[sl + 1]; i < e; ++i) {
@@ -480,50 +518,32 @@ __global__ void __launch_bounds__(NT, MINB)
             tileScale[2 * sl] = (R)fx;
             tileScale[2 * sl + 1] = (R)fy;
         }
-        // ---- load: global -> swizzled smem ----------------------------------------------------------------------
-        if (mover) {
-            const uint4* gp = reinterpret_cast<const uint4*>(psi + base + tOff);
-            if (nU == NU) {
-#pragma unroll
-                for (int u0 = 0; u0 < NU; u0 += 8) {
-                    uint4 v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        v[u] = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const C*>(gp) + uOff[u0 + u]));
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        *reinterpret_cast<uint4*>(tSlot + (size_t)(u0 + u) * NT * 16) = v[u];
-                    }
-                }
-            } else {
-                for (uint32_t u = 0; u < nU; ++u) {
-                    *reinterpret_cast<uint4*>(tSlot + (size_t)u * NT * 16) =
-                        ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const C*>(gp) + uOff[u]));
-                }
-            }
-        }
-        __syncthreads();
-        if (sw.prefetch && (t + gridDim.x < nTiles) && mover && ((tid & 7) == 0)) {
-            // one 128-byte line per 8 movers: the next tile of this CTA streams into L2 under the passes below
+        if (sw.prefetch && (t + gridDim.x < nTiles) && ((tid & 7) == 0)) {
+            // one 128-byte line per 8 chunks: the CTA's next tile streams into L2 under the passes below
             uint64_t nb = (t + gridDim.x) << sw.lowAmpBits;
             for (int h = 0; h < sw.nHigh; ++h) {
                 const uint64_t lo = nb & sw.highLow[h];
                 nb = ((nb ^ lo) << 1) | lo;
             }
-            const C* np = psi + nb + tOff;
-            for (uint32_t u = 0; u < nU; ++u) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(np + uOff[u]));
+            for (uint32_t c = (uint32_t)tid; c < nChunk; c += NT) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(psi + nb + rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC));
             }
         }
-        // ---- passes ----------------------------------------------------------------------------------------------
-        for (int p = 0; p < sw.nPass; ++p) {
+        if (!sw.directIn) {
+            // staged input (register bits of the first pass sit on low chunk bits, where per-thread HBM access would
+            // split sectors): coalesced copy global -> swizzled smem.  The extra barrier keeps slow warps of the
+            // previous tile from still reading the tile area.
+            __syncthreads();
+            stage_in<R, NT>(tilePsi, tileB, rowOff, nChunk, lcb, colMask, tid);
+        }
+        // The barrier publishes the tables (and the staged tile) and closes the previous tile: nobody still reads the
+        // tile area of smem.
+        __syncthreads();
+        // ---- passes: the first one reads its sub-blocks straight from HBM, the last one writes straight back; only the
+        // hand-over between passes goes through the (swizzled) tile in shared memory --------------------------------------
+        for (int p = 0; p < nPass; ++p) {
             const DevPass& ps = sw.pass[p];
-            uint32_t po[NCH];
-#pragma unroll
-            for (int e = 0; e < NCH; ++e) {
-                po[e] = ps.pswzB[e];
-            }
+            const bool fromGlobal = (p == 0) && sw.directIn, toGlobal = (p == nPass - 1) && sw.directOut;
             uint32_t dep = 0;
             {
                 const int nb = ps.nsb < 8 ? ps.nsb : 8;
@@ -536,7 +556,7 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
             for (int w = 0; w < 3; ++w) {
                 const int lo = ps.opBegin - 32 * w, hi = ps.opEnd - 32 * w;
-                uint32_t m = ballots[w];
+                uint32_t m = ballots[par][w];
                 m = (lo > 0) ? ((lo >= 32) ? 0U : (m & (0xffffffffU << lo))) : m;
                 m = (hi < 32) ? ((hi <= 0) ? 0U : (m & (0xffffffffU >> (32 - hi)))) : m;
                 pm[w] = m;
@@ -548,11 +568,20 @@ __global__ void __launch_bounds__(NT, MINB)
                 }
                 const uint32_t sbc = dep | ps.itoffC[it];
                 const uint32_t swb = swz(sbc) << 4;
+                C* const gsub = tilePsi + rowOff[sbc >> lcb] + (uint64_t)(sbc & colMask) * APC;
                 A a[NA];
+                if (fromGlobal) {
 #pragma unroll
-                for (int e = 0; e < NCH; ++e) {
-                    const Chunk c = *reinterpret_cast<const Chunk*>(tileB + (swb ^ po[e]));
-                    O::get(c, &a[e * APC]);
+                    for (int e = 0; e < NCH; ++e) {
+                        const uint4 v = ld_stream(reinterpret_cast<const uint4*>(gsub + ps.goff[e]));
+                        O::get(*reinterpret_cast<const Chunk*>(&v), &a[e * APC]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < NCH; ++e) {
+                        const Chunk c = *reinterpret_cast<const Chunk*>(tileB + (swb ^ ps.pswzB[e]));
+                        O::get(c, &a[e * APC]);
+                    }
                 }
                 const uint32_t xsb = sbc * APC;
 #pragma unroll 1
@@ -564,30 +593,27 @@ __global__ void __launch_bounds__(NT, MINB)
                         exec_op<R, NA>(a, ops[o], xsb, tileScale);
                     }
                 }
+                if (toGlobal) {
 #pragma unroll
-                for (int e = 0; e < NCH; ++e) {
-                    *reinterpret_cast<Chunk*>(tileB + (swb ^ po[e])) = O::put(&a[e * APC]);
+                    for (int e = 0; e < NCH; ++e) {
+                        const Chunk c = O::put(&a[e * APC]);
+                        st_stream(reinterpret_cast<uint4*>(gsub + ps.goff[e]), *reinterpret_cast<const uint4*>(&c));
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < NCH; ++e) {
+                        *reinterpret_cast<Chunk*>(tileB + (swb ^ ps.pswzB[e])) = O::put(&a[e * APC]);
+                    }
                 }
             }
-            __syncthreads();
-        }
-        // ---- store: swizzled smem -> global ------------------------------------------------------------------------
-        if (mover) {
-            uint4* gp = reinterpret_cast<uint4*>(psi + base + tOff);
-            if (nU == NU) {
-#pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    st_stream(reinterpret_cast<uint4*>(reinterpret_cast<C*>(gp) + uOff[u]),
-                        *reinterpret_cast<const uint4*>(tSlot + (size_t)u * NT * 16));
-                }
-            } else {
-                for (uint32_t u = 0; u < nU; ++u) {
-                    st_stream(reinterpret_cast<uint4*>(reinterpret_cast<C*>(gp) + uOff[u]),
-                        *reinterpret_cast<const uint4*>(tSlot + (size_t)u * NT * 16));
-                }
+            if (!toGlobal) {
+                __syncthreads();
             }
         }
-        __syncthreads();
+        if (!sw.directOut) {
+            // staged output: swizzled smem -> global, coalesced (the barrier above closed the last pass)
+            stage_out<R, NT>(tilePsi, tileB, rowOff, nChunk, lcb, colMask, tid);
+        }
     }
 }
 
@@ -802,11 +828,13 @@ static int tile_bit(const TileCfg& cfg, const std::vector<int>& highQ, int q)
 }
 
 // Encoded size limits of one sweep program (must fit beside the tile in shared memory with 3 CTAs/SM)
-constexpr size_t MAX_PROG_BYTES_3CTA = 7168;
+constexpr size_t MAX_PROG_BYTES_3CTA = 10240; // (227 KB / 3) - 64 KB tile - 1 KB reserved - static
 constexpr size_t MAX_PROG_BYTES_2CTA = 24576;
 
 static int knob_prefetch();
-template <typename R> static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<unsigned char>& buf)
+static int knob_direct_low();
+template <typename R>
+static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<unsigned char>& buf, size_t* scratchOut)
 {
     const int kc = cfg.kA - cfg.apcLog;
     const int APC = 1 << cfg.apcLog;
@@ -902,6 +930,15 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
                 }
             }
             dp.pswzB[e] = (unsigned short)(swz(off) << 4);
+            {
+                // the same chunk as a global amplitude offset relative to the tile base
+                uint64_t g = 0;
+                for (uint32_t ab = off << cfg.apcLog; ab; ab &= ab - 1U) {
+                    const int tb = __builtin_ctz(ab);
+                    g |= (tb < cfg.L) ? bitq(tb) : bitq(sp.highQ[tb - cfg.L]);
+                }
+                dp.goff[e] = g;
+            }
             for (int w = 0; w < APC; ++w) {
                 roffA[e * APC + w] = (off << cfg.apcLog) | (uint32_t)w;
             }
@@ -1091,6 +1128,21 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
         }
         dp.opEnd = (int)dops.size();
     }
+    {
+        auto lowRegBits = [&](const PassPlan& pp) {
+            int cnt = 0;
+            for (int q : pp.regQ) {
+                const int cb = tile_bit(cfg, sp.highQ, q) - cfg.apcLog;
+                if (cb >= 0 && cb < 3) {
+                    ++cnt;
+                }
+            }
+            return cnt;
+        };
+        const int dlow = knob_direct_low();
+        ds.directIn = (lowRegBits(sp.passes.front()) <= dlow) ? 1 : 0;
+        ds.directOut = (lowRegBits(sp.passes.back()) <= dlow) ? 1 : 0;
+    }
     ds.scale = scale;
     if (getenv("B200SV_FUSED_DEBUG")) {
         static const char* names[] = { "HAD", "XSWAP", "GEN_U", "GEN_P", "PHREG1", "PHUNI", "PHGEN" };
@@ -1124,6 +1176,11 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
     ds.nOuter = (int)outerList.size();
     // table slots: slot 0 = the outer-only phases (tile scalar), then one slot per (DIAG op, register bit)
     ds.nSlots = 1 + (int)slotMembers.size();
+    {
+        const int lcb = cfg.L - cfg.apcLog;
+        const size_t rows = (size_t)1 << (kc > lcb ? kc - lcb : 0);
+        ds.scratchBytes = (int)((rows * 8U + (size_t)4 * (size_t)ds.nSlots * sizeof(R) + 15U) & ~(size_t)15U);
+    }
     ds.slotBeg[0] = 0;
     ds.slotBeg[1] = (unsigned short)outerList.size();
     for (size_t k = 0; k < slotMembers.size(); ++k) {
@@ -1135,6 +1192,9 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
     ds.outerOff = (int)(sizeof(DevSweep) + opsBytes);
     const size_t start = buf.size();
     size_t bytes = ((sizeof(DevSweep) + opsBytes + outerBytes) + 15U) & ~(size_t)15U;
+    if (scratchOut) {
+        *scratchOut = (size_t)ds.scratchBytes;
+    }
     if (dops.size() > (size_t)MAX_OPS || outerList.size() > 60000U) {
         bytes = (size_t)1 << 30; // does not fit the descriptor: the caller retries with a smaller window
         return bytes;
@@ -1154,7 +1214,7 @@ template <typename R> static size_t encode_sweep(const SweepPlan& sp, const Tile
 // further ahead than that), and retries with fewer ops if the encoded program would not fit beside the tile.
 constexpr size_t PLAN_WINDOW = 1024;
 static int plan_and_encode(std::vector<HostOp>& pending, const TileCfg& cfg0, int prec, std::vector<unsigned char>& buf, size_t* bytesOut,
-    size_t* nOpsOut, int* nPassOut)
+    size_t* scratchOut, size_t* nOpsOut, int* nPassOut)
 {
     const size_t wsz = std::min(pending.size(), PLAN_WINDOW);
     TileCfg cfg = cfg0;
@@ -1167,9 +1227,11 @@ static int plan_and_encode(std::vector<HostOp>& pending, const TileCfg& cfg0, in
             return B200SV_ESTATE;
         }
         const size_t mark = buf.size();
-        const size_t bytes = (prec == 32) ? encode_sweep<float>(sp, cfg, buf) : encode_sweep<double>(sp, cfg, buf);
+        size_t scratch = 0;
+        const size_t bytes =
+            (prec == 32) ? encode_sweep<float>(sp, cfg, buf, &scratch) : encode_sweep<double>(sp, cfg, buf, &scratch);
         const size_t limit = (cfg.RB >= 4) ? MAX_PROG_BYTES_2CTA : MAX_PROG_BYTES_3CTA;
-        if (bytes > limit) {
+        if (bytes + scratch > limit) {
             if (cfg.maxOps <= 4) {
                 set_error("fused sweep program does not fit");
                 return B200SV_ESTATE;
@@ -1182,6 +1244,7 @@ static int plan_and_encode(std::vector<HostOp>& pending, const TileCfg& cfg0, in
         window.insert(window.end(), pending.begin() + wsz, pending.end());
         pending.swap(window);
         *bytesOut = bytes;
+        *scratchOut = scratch;
         *nOpsOut = sp.nOps;
         *nPassOut = (int)sp.passes.size();
         return B200SV_OK;
@@ -1246,10 +1309,10 @@ struct KernelCfg {
 };
 
 template <typename R, int KC, int RB, int NT, int MINB>
-static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes, uint64_t nTiles)
+static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes, uint32_t scratchBytes, uint64_t nTiles)
 {
     auto kern = k_fused_sweep<R, KC, RB, NT, MINB>;
-    const size_t shm = ((size_t)16 << KC) + progBytes;
+    const size_t shm = ((size_t)16 << KC) + progBytes + scratchBytes;
     static unsigned long long attr_set_mask = 0; // per device: the attribute is per-context
     if (!(attr_set_mask & (1ULL << s->dev))) {
         SV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1271,6 +1334,7 @@ struct FusedKnobs {
     int RB64 = 3; // fp64: 8 double2 amplitudes per sub-block keep 3 CTAs/SM resident
     int bundle = 3; // bit 0: merge Hadamards on distinct register bits into one LAYER op; bit 1: DIAG phase groups
     int pf = 0;     // 1: L2 prefetch of the CTA's next tile during the passes
+    int dlow = 1;   // first/last pass go straight HBM<->registers when at most this many of their register bits are chunk bits 0..2
 };
 static const FusedKnobs& knobs()
 {
@@ -1278,8 +1342,11 @@ static const FusedKnobs& knobs()
         FusedKnobs v;
         const char* e = getenv("B200SV_FUSED");
         if (e) {
-            int rb = 0, l32 = 0, l64 = 0, bn = 1, rb64 = 0, cp = 0, pf = 0;
-            const int got = sscanf(e, "%d,%d,%d,%d,%d,%d,%d", &rb, &l32, &l64, &bn, &rb64, &cp, &pf);
+            int rb = 0, l32 = 0, l64 = 0, bn = 1, rb64 = 0, cp = 0, pf = 0, dlow = 1;
+            const int got = sscanf(e, "%d,%d,%d,%d,%d,%d,%d,%d", &rb, &l32, &l64, &bn, &rb64, &cp, &pf, &dlow);
+            if (got >= 8) {
+                v.dlow = dlow;
+            }
             if (got >= 7) {
                 v.pf = pf;
             }
@@ -1304,6 +1371,7 @@ static const FusedKnobs& knobs()
     return k;
 }
 static int knob_prefetch() { return knobs().pf; }
+static int knob_direct_low() { return knobs().dlow; }
 constexpr int FUSED_KC = 12;
 constexpr int FUSED_NT = 256;
 
@@ -1338,13 +1406,16 @@ int fused_flush(State* s)
     }
     // build every sweep of this flush
     std::vector<unsigned char> buf;
-    std::vector<std::pair<size_t, size_t>> segs; // (offset, bytes)
+    struct Seg {
+        size_t off, bytes, scratch;
+    };
+    std::vector<Seg> segs;
     while (!pending.empty()) {
         const size_t off = buf.size();
-        size_t bytes = 0, nops = 0;
+        size_t bytes = 0, scratch = 0, nops = 0;
         int npass = 0;
-        SV_TRY(plan_and_encode(pending, cfg, s->prec, buf, &bytes, &nops, &npass));
-        segs.push_back({ off, bytes });
+        SV_TRY(plan_and_encode(pending, cfg, s->prec, buf, &bytes, &scratch, &nops, &npass));
+        segs.push_back({ off, bytes, scratch });
     }
     const uint64_t nTiles = s->dim() >> cfg.kA;
     if (ar->pending) {
@@ -1363,19 +1434,19 @@ int fused_flush(State* s)
     memcpy(ar->host, buf.data(), buf.size());
     SV_CUDA(cudaMemcpyAsync(ar->dev, ar->host, buf.size(), cudaMemcpyHostToDevice, s->stream));
     for (size_t i = 0; i < segs.size(); ++i) {
-        const unsigned char* dp = ar->dev + segs[i].first;
-        const uint32_t pb = (uint32_t)segs[i].second;
+        const unsigned char* dp = ar->dev + segs[i].off;
+        const uint32_t pb = (uint32_t)segs[i].bytes, sb = (uint32_t)segs[i].scratch;
         if (s->prec == 32) {
             if (cfg.RB == 4) {
-                SV_TRY((launch_sweep<float, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, nTiles)));
+                SV_TRY((launch_sweep<float, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles)));
             } else {
-                SV_TRY((launch_sweep<float, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, nTiles)));
+                SV_TRY((launch_sweep<float, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles)));
             }
         } else {
             if (cfg.RB == 4) {
-                SV_TRY((launch_sweep<double, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, nTiles)));
+                SV_TRY((launch_sweep<double, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles)));
             } else {
-                SV_TRY((launch_sweep<double, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, nTiles)));
+                SV_TRY((launch_sweep<double, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles)));
             }
         }
         s->stats.kernel_launches++;
@@ -1427,7 +1498,8 @@ int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targ
         size_t bytes = 0, nops = 0;
         int npass = 0;
         buf.clear();
-        SV_TRY(plan_and_encode(pending, cfg, precision, buf, &bytes, &nops, &npass));
+        size_t scratch = 0;
+        SV_TRY(plan_and_encode(pending, cfg, precision, buf, &bytes, &scratch, &nops, &npass));
         ++sweeps;
         passes += npass;
     }

@@ -83,6 +83,8 @@ struct State {
     int prec = 32;
     void* amps = nullptr; // device buffer (nullptr == the zero state)
     bool external = false;
+    void* spare = nullptr; // second state-sized buffer kept by the out-of-place QAlu sweeps (ping-pong with amps)
+    size_t spare_bytes = 0;
     cudaStream_t stream = nullptr;
     bool ownStream = true;
     double* d_scratch = nullptr; // small device scratch for reductions

@@ -350,6 +350,69 @@ __global__ void __launch_bounds__(256) k_uniformly_controlled(typename Cx<R>::ty
 // ---------------------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------------------
+// All single-qubit marginals in ONE sweep: out[b] += sum of |psi_i|^2 over i with bit b set (b < nq), out[64] += total.
+// Each thread walks groups of 8 consecutive amplitudes: bits 0..2 are resolved inside the group, every higher bit adds the
+// group total once.  Accumulators are doubles in registers; one shuffle tree + one atomic per (block, bit) at the end.
+template <typename R>
+__global__ void __launch_bounds__(256) k_prob_all_bits(const typename Cx<R>::type* __restrict__ psi, uint64_t n, int nq, double* __restrict__ out)
+{
+    typedef typename Cx<R>::type C;
+    double acc[40];
+#pragma unroll
+    for (int b = 0; b < 40; ++b) {
+        acc[b] = 0.0;
+    }
+    double tot = 0.0;
+    const uint64_t groups = n >> 3;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        const C* p = psi + (g << 3);
+        R pr[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const C a = p[k];
+            pr[k] = a.x * a.x + a.y * a.y;
+        }
+        const R s01 = pr[0] + pr[1], s23 = pr[2] + pr[3], s45 = pr[4] + pr[5], s67 = pr[6] + pr[7];
+        const double gsum = (double)((s01 + s23) + (s45 + s67));
+        tot += gsum;
+        acc[0] += (double)((pr[1] + pr[3]) + (pr[5] + pr[7]));
+        acc[1] += (double)(s23 + s67);
+        acc[2] += (double)(s45 + s67);
+#pragma unroll
+        for (int b = 3; b < 40; ++b) {
+            if (b < nq && ((g >> (b - 3)) & 1U)) {
+                acc[b] += gsum;
+            }
+        }
+    }
+    __shared__ double red[8][41];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int b = 0; b < 41; ++b) {
+        double v = (b < 40) ? acc[b < 40 ? b : 0] : tot;
+        if (b < 40 && b >= nq) {
+            continue;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            v += __shfl_xor_sync(0xffffffffU, v, d);
+        }
+        if (lane == 0) {
+            red[warp][b] = v;
+        }
+    }
+    __syncthreads();
+    const int b = threadIdx.x;
+    if (b < 41 && (b == 40 || b < nq)) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            v += red[w][b];
+        }
+        atomicAdd(out + (b == 40 ? 64 : b), v);
+    }
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256) k_prob_mask(const typename Cx<R>::type* __restrict__ psi, uint64_t n, uint64_t mask,
     uint64_t perm, double* out)
@@ -840,12 +903,17 @@ static int flush_queue(State* s)
 
 using namespace b200sv;
 
-#define SV_ENTER(s)                                                                                                    \
+// read-only entry: keeps the memoised marginals
+#define SV_ENTER_RO(s)                                                                                                 \
     if (!(s)) {                                                                                                        \
         set_error("null state handle");                                                                                \
         return B200SV_EINVAL;                                                                                          \
     }                                                                                                                  \
     DevGuard guard__((s)->dev)
+// default entry: anything that is not explicitly read-only invalidates the memoised marginals
+#define SV_ENTER(s)                                                                                                    \
+    SV_ENTER_RO(s);                                                                                                    \
+    (s)->margValid = false
 
 #define DISPATCH_PREC(s, expr32, expr64)                                                                               \
     if ((s)->prec == 32) {                                                                                             \
@@ -1147,13 +1215,13 @@ int b200sv_set_stream(b200sv_t s, void* stream, int adopt)
 
 int b200sv_flush(b200sv_t s)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     return flush_queue(s);
 }
 
 int b200sv_finish(b200sv_t s)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     SV_TRY(flush_queue(s));
     SV_CUDA(cudaStreamSynchronize(s->stream));
     return B200SV_OK;
@@ -1322,7 +1390,7 @@ int b200sv_set_state(b200sv_t s, const void* host)
 
 int b200sv_get_state(b200sv_t s, void* host)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     if (!host) {
         return einval("null host pointer");
     }
@@ -1339,7 +1407,7 @@ int b200sv_get_state(b200sv_t s, void* host)
 
 int b200sv_get_probs(b200sv_t s, void* host)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     if (!host) {
         return einval("null host pointer");
     }
@@ -1474,6 +1542,7 @@ int b200sv_shuffle(b200sv_t a, b200sv_t b)
     if (!b) {
         return einval("null handle");
     }
+    b->margValid = false;
     if (a->nq != b->nq || a->prec != b->prec) {
         return einval("ShuffleBuffers argument size differs from this");
     }
@@ -1524,6 +1593,7 @@ int b200sv_copy_state(b200sv_t dst, b200sv_t src)
     if (!dst || !src) {
         return einval("null handle");
     }
+    dst->margValid = false;
     if (dst->nq != src->nq) {
         return einval("CopyStateVec argument size differs from this");
     }
@@ -1536,7 +1606,7 @@ int b200sv_copy_state(b200sv_t dst, b200sv_t src)
 
 int b200sv_get_amplitude(b200sv_t s, uint64_t perm, double* re, double* im)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     if (perm >= s->dim()) {
         return einval("GetAmplitude argument out-of-bounds");
     }
@@ -1866,7 +1936,7 @@ int b200sv_collapse_parity(b200sv_t s, uint64_t mask, int result, double* kept)
 
 int b200sv_prob_mask(b200sv_t s, uint64_t mask, uint64_t perm, double* out)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     if (!out) {
         return einval("null out pointer");
     }
@@ -1879,6 +1949,24 @@ int b200sv_prob_mask(b200sv_t s, uint64_t mask, uint64_t perm, double* out)
         return B200SV_OK;
     }
     const uint64_t n = s->dim();
+    if (mask && !(mask & (mask - 1U)) && !s->external && s->nq >= 3 && s->nq <= 40) {
+        // single-qubit probability: served from the memoised marginals (one sweep computes every qubit's; callers
+        // such as QUnit or a measurement loop ask for many qubits between two state changes)
+        if (!s->margValid) {
+            SV_CUDA(cudaMemsetAsync(s->d_scratch, 0, 65 * sizeof(double), s->stream));
+            const unsigned grid = std::min<unsigned>(stream_grid(s->dev, n >> 3, 256), (unsigned)sm_count(s->dev) * 8U);
+            DISPATCH_PREC(s, (k_prob_all_bits<float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, n, s->nq, s->d_scratch)),
+                (k_prob_all_bits<double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, n, s->nq, s->d_scratch)));
+            SV_CUDA(cudaGetLastError());
+            s->stats.kernel_launches++;
+            SV_TRY(read_scratch(s, 65));
+            memcpy(s->marg, s->h_scratch, 65 * sizeof(double));
+            s->margValid = true;
+        }
+        const int bit = __builtin_ctzll(mask);
+        *out = perm ? s->marg[bit] : (s->marg[64] - s->marg[bit]);
+        return B200SV_OK;
+    }
     SV_CUDA(cudaMemsetAsync(s->d_scratch, 0, sizeof(double), s->stream));
     // subset iteration when every mask bit is >= 2^4 (reads stay >= 128 B contiguous); else predicate scan
     if (mask && !(mask & 15U)) {
@@ -1905,7 +1993,7 @@ int b200sv_prob_mask(b200sv_t s, uint64_t mask, uint64_t perm, double* out)
 
 int b200sv_prob_parity(b200sv_t s, uint64_t mask, double* out)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     if (!out) {
         return einval("null out pointer");
     }
@@ -1931,7 +2019,7 @@ int b200sv_prob_parity(b200sv_t s, uint64_t mask, double* out)
 
 int b200sv_prob_mask_all(b200sv_t s, uint64_t mask, void* host_probs)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     if (!host_probs) {
         return einval("null out pointer");
     }
@@ -1980,7 +2068,7 @@ int b200sv_prob_mask_all(b200sv_t s, uint64_t mask, void* host_probs)
 
 int b200sv_norm(b200sv_t s, double thresh, double* out)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     if (!out) {
         return einval("null out pointer");
     }
@@ -2065,7 +2153,7 @@ int b200sv_inner(b200sv_t a, b200sv_t b, double* re, double* im)
 
 int b200sv_expectation(b200sv_t s, int start, int length, double* out)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     if (!out || start < 0 || length < 0 || start + length > s->nq) {
         return einval("GetExpectation range is out-of-bounds!");
     }
@@ -2089,7 +2177,7 @@ int b200sv_expectation(b200sv_t s, int start, int length, double* out)
 
 int b200sv_highest_prob(b200sv_t s, uint64_t* perm)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     if (!perm) {
         return einval("null out pointer");
     }
@@ -2303,6 +2391,9 @@ int b200sv_dispose_perm(b200sv_t s, int start, int length, uint64_t perm)
 int b200sv_decompose(b200sv_t s, int start, int length, b200sv_t dest)
 {
     SV_ENTER(s);
+    if (dest) {
+        dest->margValid = false;
+    }
     if (start < 0 || length < 0 || start + length > s->nq) {
         return einval("DecomposeDispose range is out-of-bounds!");
     }
@@ -2444,14 +2535,14 @@ int b200sv_reset_stats(b200sv_t s)
 
 int b200sv_timer_begin(b200sv_t s)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     SV_TRY(flush_queue(s));
     SV_CUDA(cudaEventRecord(s->ev0, s->stream));
     return B200SV_OK;
 }
 int b200sv_timer_end(b200sv_t s, double* ms)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     if (!ms) {
         return einval("null out pointer");
     }
@@ -2475,7 +2566,7 @@ int b200sv_plan_dry_run(int n_qubits, int precision, int n_gates, const int* tar
 
 int b200sv_flush_l2(b200sv_t s, uint64_t bytes)
 {
-    SV_ENTER(s);
+    SV_ENTER_RO(s);
     bytes = (bytes + 15U) & ~15ULL;
     if (s->flush_bytes < bytes) {
         if (s->d_flush) {

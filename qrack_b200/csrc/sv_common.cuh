@@ -96,6 +96,10 @@ struct State {
     int fusion = 1;
     std::vector<GateOp> queue;
     b200sv_stats stats{};
+    // memoised single-qubit marginals: marg[b] = sum |psi_i|^2 over i with bit b set, marg[64] = sum over all i.
+    // Filled by ONE sweep on the first Prob(q) after a change; every mutating ABI call clears `margValid`.
+    bool margValid = false;
+    double marg[65];
 
     size_t amp_bytes() const { return prec == 32 ? 8 : 16; }
     uint64_t dim() const { return 1ULL << nq; }

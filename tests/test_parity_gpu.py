@@ -370,3 +370,68 @@ def test_alu_full_size_properties_28q():
     assert q.HighestProbAll() == 15
     q.INCC((1 << 27) + 3, 0, 27, 27)   # no carry out: 15 + 2^27+3 wraps inside 27 bits? 2^27 is masked off -> +3
     assert q.HighestProbAll() == 18
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+def test_memoised_marginals_follow_every_state_change(prec):
+    """Prob(q) is served from marginals computed in one sweep and memoised until the state changes: interleave every
+    kind of mutating call with full rounds of Prob(q) and compare each round with the oracle."""
+    n = 11
+    g = QEngineCUDA(n, 0, random.Random(1), 1.0 + 0j, False, False, precision=prec)
+    o = QEngineRestate(n, 0, random.Random(1), 1.0 + 0j, False, False, precision=prec)
+    rng = np.random.default_rng(3)
+    tol = util.PROB_TOL[prec]
+
+    def marginals(e):
+        # exact (float64) marginals of the oracle's state: the oracle's own fp32 Prob() is a single-accumulator sum
+        # (state.cpp:1751-1810 per thread) and drifts by ~1e-5 at 2^10 terms, which is not what is being tested here
+        st = e.GetQuantumState().astype(np.complex128)
+        pr = np.abs(st) ** 2
+        idx = np.arange(pr.size)
+        # QEngine::Prob clamps to [0, 1] (qinterface.hpp:158-167); ShuffleBuffers below leaves un-normalised states
+        return [min(1.0, float(pr[((idx >> q) & 1) == 1].sum())) for q in range(e.GetQubitCount())], min(1.0, float(pr[3]))
+
+    def check(tag):
+        want, want3 = marginals(o)
+        for q in range(g.GetQubitCount()):
+            assert abs(g.Prob(q) - want[q]) <= tol, (tag, q)
+        assert abs(g.ProbAll(3) - want3) <= tol, tag
+
+    steps = [
+        ("H layer", lambda e: [e.H(q) for q in range(n)]),
+        ("T + CNOT (fused queue)", lambda e: (e.T(2), e.CNOT(2, 7), e.U(5, 0.3, 0.2, 0.1))),
+        ("SetAmplitude", lambda e: e.SetAmplitude(5, 0.25 + 0.1j)),
+        ("ForceM", lambda e: e.ForceM(4, True, True, True)),
+        ("XMask", lambda e: e.XMask(0b1011)),
+        ("PhaseParity", lambda e: e.PhaseParity(0.7, 0b110)),
+        ("INC (QAlu sweep, buffer swap)", lambda e: e.INC(5, 1, 6)),
+        ("Swap", lambda e: e.Swap(0, 9)),
+        ("NormalizeState", lambda e: e.NormalizeState()),
+        ("SetQuantumState", lambda e: e.SetQuantumState(psi)),
+        ("SetPermutation", lambda e: e.SetPermutation(77)),
+        ("H again", lambda e: [e.H(q) for q in (0, 3, 10)]),
+        ("Dispose", lambda e: e.Dispose(10, 1)),
+        ("Allocate", lambda e: e.Allocate(0, 1)),
+        ("ForceMParity", lambda e: e.ForceMParity(0b1100, True, True)),
+    ]
+    psi = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)).astype(np.complex64 if prec == 32 else np.complex128)
+    psi /= np.linalg.norm(psi)
+    for tag, fn in steps:
+        fn(g)
+        fn(o)
+        check(tag)
+        check(tag + " (cached)")
+    # two-handle mutators
+    g2, o2 = g.Clone(), o.Clone()
+    g2.H(1)
+    o2.H(1)
+    check("clone source untouched")
+    g.ShuffleBuffers(g2)
+    o.ShuffleBuffers(o2)
+    check("shuffle a")
+    for q, w in enumerate(marginals(o2)[0]):
+        assert abs(g2.Prob(q) - w) <= tol
+    g2.CopyStateVec(g)
+    o2.CopyStateVec(o)
+    for q, w in enumerate(marginals(o2)[0]):
+        assert abs(g2.Prob(q) - w) <= tol

@@ -5,13 +5,13 @@
 // Shape of one sweep:
 //   * tile  = 2^KC 16-byte chunks (64 KB) living in shared memory.  Its index bits are the low L qubits (so every
 //     global access is a >= 2^L-amplitude contiguous run) plus up to H arbitrary "high" qubits chosen by the scheduler.
-//   * load  : coalesced 128-bit loads, stored to smem in the TMA SWIZZLE_128B layout (16-B chunk index ^= row index),
-//             so the in-tile butterflies are bank-conflict free for any target bit.
-//   * passes: each pass picks RB "register" chunk bits; every thread pulls a 2^RB-chunk sub-block into registers
-//             (fp32: +qubit 0 inside the chunk), applies every queued gate whose target is one of those bits (controls
-//             anywhere: tile-local bits become a per-amplitude predicate, outside bits a per-tile predicate) and
-//             writes the sub-block back.  Diagonal gates are index-only and ride along in any pass, on any qubit.
-//   * store : swizzled smem -> coalesced 128-bit streaming stores.
+//   * passes: each pass picks RB "register" chunk bits; every thread holds a 2^RB-chunk sub-block in registers
+//             (fp32: +qubit 0 inside the chunk) and applies every queued gate whose target is one of those bits (controls
+//             anywhere: tile-local bits become a per-amplitude predicate, outside bits a per-tile predicate).  Diagonal
+//             gates are index-only and ride along in any pass, on any qubit.
+//   * data  : the first pass reads its sub-blocks straight from HBM and the last one writes straight back (128-bit
+//             streaming accesses); between passes the sub-blocks are handed over through the tile in shared memory, in an
+//             XOR-swizzled layout that keeps the butterflies bank-conflict free for any choice of register bits.
 // The host-side scheduler below reorders only gates that commute (disjoint qubits, or shared qubits used diagonally by
 // both) and never changes the product of the gate sequence.
 #include "sv_common.cuh"
@@ -96,8 +96,10 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4 v)
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// TMA SWIZZLE_128B layout on 16-byte chunks: chunk index bits [0..2] ^= bits [3..5] (XOR-linear in the index)
-__host__ __device__ __forceinline__ uint32_t swz(uint32_t c) { return c ^ ((c >> 3) & 7U); }
+// smem slot of tile chunk c: the 128-byte bank group (chunk bits 0..2) is XORed with every higher 3-bit field, so any
+// three chunk bits from distinct classes {0,3,6,9}, {1,4,7,10}, {2,5,8,11} address eight different bank groups.  Linear over
+// XOR: swz(a | b) = swz(a) ^ swz(b) for disjoint a, b (the passes combine a thread part and a register part that way).
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t c) { return c ^ ((c >> 3) & 7U) ^ ((c >> 6) & 7U) ^ ((c >> 9) & 7U); }
 
 // ---------------------------------------------------------------------------------------------------------
 // register representation of amplitudes.
@@ -879,11 +881,11 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
             }
         }
         std::sort(rb.begin(), rb.end());
-        // sub-block index bits: lanes first take one free bit from each bank class {0,3},{1,4},{2,5}
+        // sub-block index bits: lanes first take one free bit from each bank class {0,3,6,9},{1,4,7,10},{2,5,8,11}
         std::vector<int> sb;
         uint32_t taken = used;
         for (int pcl = 0; pcl < 3; ++pcl) {
-            for (int cand : { pcl, pcl + 3 }) {
+            for (int cand : { pcl, pcl + 3, pcl + 6, pcl + 9 }) {
                 if (cand < kc && !(taken & (1U << cand))) {
                     sb.push_back(cand);
                     taken |= 1U << cand;

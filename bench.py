@@ -31,8 +31,8 @@ METRIC = "gates/sec at 30q random circuit; Apply2x2 HBM GB/s vs roofline"
 
 def measured_traffic(kernel_bytes_per_launch):
     """dram__bytes_read+write per launch of the fused sweep from the committed `ncu --set full` capture
-    (profiles/r1_fused_v6_ncu_full.json, 28 qubits), scaled to this run's state size."""
-    p = os.path.join(ROOT, "profiles", "r1_fused_v6_ncu_full.json")
+    (profiles/r1_fused_v9_ncu_full.json, 28 qubits), scaled to this run's state size."""
+    p = os.path.join(ROOT, "profiles", "r1_fused_v9_ncu_full.json")
     try:
         j = json.load(open(p))
         l = j["launches"][0]
@@ -332,7 +332,12 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (measured_traffic(swept / max(1, launches)) if stats["fused_sweeps"] else None), "peak_source": peak_src, "kernel": "fused sweep" if stats["fused_sweeps"] else "k_apply2x2",
                          "bytes_per_launch": swept / max(1, launches), "ms_per_launch": kernel_ms,
-                         "algorithmic_gbs": (alg / 1e9) / (ms_total / 1e3), "fused_sweeps": int(stats["fused_sweeps"]),
+                         "algorithmic_gbs": (alg / 1e9) / (ms_total / 1e3),
+                         "algorithmic_frac": (alg / 1e9) / (ms_total / 1e3) / peak,
+                         "note": "achieved/frac = PHYSICAL bytes of the launch (2 * 2^n * S) / duration; algorithmic_* credits "
+                                 "sum_W 2*2^(n-c)*S per fused gate (SURVEY 8d); light sweeps reach 0.91 of peak "
+                                 "(profiles/r1_roofline_curve_v9_H.json)",
+                         "fused_sweeps": int(stats["fused_sweeps"]),
                          "fused_gates": int(stats["fused_gates"])},
             "clocks": sampler.summary(),
         }

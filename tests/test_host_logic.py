@@ -91,3 +91,82 @@ def test_mirror_circuit_returns():
     for t in reversed(ops):
         getattr(q, inv[t[0]])(*[int(x) for x in t[1:]])
     assert abs(q.ProbAll(37) - 1.0) < 1e-5
+
+
+def _basis(q):
+    st = q.GetQuantumState()
+    nz = np.nonzero(np.abs(st) > 1e-9)[0]
+    assert len(nz) == 1
+    return int(nz[0]), complex(st[nz[0]])
+
+
+def test_qalu_mirror_semantics_on_basis_states():
+    """QAlu members through the host mirror (src/qalu.cpp wrappers + src/qengine/arithmetic.cpp loops) against the
+    arithmetic they stand for, on computational basis states (an independent statement of the semantics)."""
+    rng = random.Random(11)
+    for _ in range(40):
+        n, L = 12, 4
+        x, a = rng.randrange(1 << L), rng.randrange(1, 1 << L)
+        hi = rng.randrange(4) << 10                      # spectator qubits 10, 11
+        q = QEngineRestate(n, x | hi, random.Random(1), 1.0 + 0j, False, False, precision=64)
+        q.INC(a, 0, L)
+        assert _basis(q)[0] == ((x + a) % 16) | hi
+        q.DEC(a, 0, L)
+        assert _basis(q)[0] == x | hi
+        q.INCC(a, 0, L, 4)                               # carry qubit 4 starts at 0
+        assert _basis(q)[0] == ((x + a) % 16) | (((x + a) >> 4) << 4) | hi
+        q.SetPermutation(x | hi)
+        q.CINC(a, 0, L, [10])
+        assert _basis(q)[0] == ((((x + a) % 16) if hi & (1 << 10) else x) | hi)
+        q.SetPermutation(x | hi)
+        q.MUL(a, 0, 4, L)                                # product spread over in/out 0..3 and carry 4..7
+        assert _basis(q)[0] == ((x * a) & 15) | ((((x * a) >> 4) & 15) << 4) | hi
+        q.DIV(a, 0, 4, L)
+        assert _basis(q)[0] == x | hi
+        q.MULModNOut(a, 13, 0, 4, L)
+        assert _basis(q)[0] == x | (((x * a) % 13) << 4) | hi
+        q.IMULModNOut(a, 13, 0, 4, L)
+        assert _basis(q)[0] == x | hi
+        q.POWModNOut(3, 11, 0, 4, L)
+        assert _basis(q)[0] == x | ((pow(3, x) % 11) << 4) | hi
+        q.SetPermutation(x | hi)
+        q.ROL(1, 0, L)
+        assert _basis(q)[0] == (((x << 1) | (x >> 3)) & 15) | hi
+        q.ROR(1, 0, L)
+        assert _basis(q)[0] == x | hi
+        tab = bytes(rng.randrange(16) for _ in range(16))
+        q.IndexedLDA(0, L, 4, 4, tab)
+        assert _basis(q)[0] == x | (tab[x] << 4) | hi
+        q.IndexedADC(0, L, 4, 4, 8, tab)                 # value += tab[x], carry out into qubit 8
+        v = 2 * tab[x]
+        assert _basis(q)[0] == x | ((v & 15) << 4) | ((v >> 4) << 8) | hi
+        perm = list(range(16))
+        rng.shuffle(perm)
+        q.SetPermutation(x | hi)
+        q.Hash(0, L, bytes(perm))
+        assert _basis(q)[0] == perm[x] | hi
+        q.SetPermutation(x | hi)
+        q.PhaseFlipIfLess(a, 0, L)
+        assert abs(_basis(q)[1] - (-1.0 if x < a else 1.0)) < 1e-12
+        q.INCS(a, 0, L, 10)                              # sign flip only if signed overflow AND flag qubit 10 set
+        sx, sa = (x - 16 if x & 8 else x), (a - 16 if a & 8 else a)
+        ovf = not (-8 <= sx + sa <= 7)
+        want = (-1.0 if x < a else 1.0) * (-1.0 if (ovf and (hi & (1 << 10))) else 1.0)
+        assert abs(_basis(q)[1] - want) < 1e-12, (x, a, hi)
+
+
+def test_qalu_argument_errors_and_unsupported_backends():
+    q = QEngineRestate(8, 0, random.Random(1), 1.0 + 0j, False, False, precision=32)
+    with pytest.raises(ValueError):
+        q.INC(1, 6, 4)
+    with pytest.raises(ValueError):
+        q.INCC(1, 0, 4, 9)
+    with pytest.raises(ValueError):
+        q.CINC(1, 0, 4, [8])
+    with pytest.raises(ValueError):
+        q.DIV(0, 0, 4, 4)
+    with pytest.raises(ValueError):
+        q.Hash(0, 4, b"\x00\x01")                        # table too short
+    q.ZeroAmplitudes()
+    q.INC(3, 0, 4)                                       # CHECK_ZERO_SKIP
+    assert q.IsZeroAmplitude()

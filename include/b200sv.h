@@ -184,6 +184,13 @@ int b200sv_phase_flip_if_less(b200sv_t s, uint64_t greater_perm, int start, int 
 int b200sv_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks,
     const int* kinds, int* n_sweeps, int* n_passes);
 
+/* Test hook (no device needed, never on the engine's path): plan + encode the gate list exactly as b200sv_apply2x2 /
+ * the fused flush would, then interpret every encoded sweep program on a HOST state vector (n_qubits <= 30;
+ * interleaved re/im of the given precision).  Gate i is Apply2x2(off1[i], off2[i], mats8 + 8 i, powers = bits of
+ * pmasks[i]) in its single-target form.  `pytest -m "not gpu"` checks scheduler + encoder against the oracle with it. */
+int b200sv_emulate_fused(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,
+    const uint64_t* pmasks, const double* mats8, void* host_state);
+
 typedef struct b200sv_stats {
     uint64_t gates_submitted;  /* apply2x2-class calls accepted */
     uint64_t kernel_launches;  /* CUDA kernels launched by this state */

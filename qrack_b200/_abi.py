@@ -95,6 +95,8 @@ SIGNATURES = {
     "b200sv_set_fusion": [H, c_int],
     "b200sv_plan_dry_run": [c_int, c_int, c_int, POINTER(c_int), POINTER(c_uint64), POINTER(c_int), POINTER(c_int),
                             POINTER(c_int)],
+    "b200sv_emulate_fused": [c_int, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double),
+                             c_void_p],
     "b200sv_get_stats": [H, POINTER(Stats)],
     "b200sv_reset_stats": [H],
     "b200sv_timer_begin": [H],

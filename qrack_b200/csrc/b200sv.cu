@@ -1656,6 +1656,30 @@ int b200sv_set_amplitude(b200sv_t s, uint64_t perm, double re, double im)
     return B200SV_OK;
 }
 
+// (offset1, offset2, powers) single-target form -> queued gate (shared by b200sv_apply2x2 and the emulation hook)
+static void make_gate_op(int prec, uint64_t off1, uint64_t off2, uint64_t pmask, const double* m8, double nrm, GateOp& g)
+{
+    const uint64_t diff = off1 ^ off2;
+    g.target = __builtin_ctzll(diff);
+    g.cmask = pmask & ~diff;
+    g.cval = off1 & ~diff;
+    const bool swapped = (off1 & diff) != 0; // off1 holds the |1> branch: reorder the matrix
+    const int ord[4] = { 3, 2, 1, 0 };
+    for (int k = 0; k < 4; ++k) {
+        const int src = swapped ? ord[k] : k;
+        g.m[2 * k] = m8[2 * src] * nrm;
+        g.m[2 * k + 1] = m8[2 * src + 1] * nrm;
+    }
+    if (prec == 32) {
+        for (int k = 0; k < 8; ++k) {
+            g.m[k] = (double)(float)g.m[k];
+        }
+    }
+    const bool z1 = g.m[2] == 0 && g.m[3] == 0, z2 = g.m[4] == 0 && g.m[5] == 0;
+    const bool z0 = g.m[0] == 0 && g.m[1] == 0, z3 = g.m[6] == 0 && g.m[7] == 0;
+    g.kind = (z1 && z2) ? 1 : ((z0 && z3) ? 2 : 0);
+}
+
 // ---- gates -----------------------------------------------------------------------------------------------------------
 
 int b200sv_apply2x2(b200sv_t s, uint64_t off1, uint64_t off2, const double* m8, int bit_count, const uint64_t* pows,
@@ -1696,24 +1720,7 @@ int b200sv_apply2x2(b200sv_t s, uint64_t off1, uint64_t off2, const double* m8, 
     const uint64_t diff = off1 ^ off2;
     if (!norm_out && s->fusion && diff && !(diff & (diff - 1U))) {
         GateOp g;
-        g.target = __builtin_ctzll(diff);
-        g.cmask = pmask & ~diff;
-        g.cval = off1 & ~diff;
-        const bool swapped = (off1 & diff) != 0; // off1 holds the |1> branch: reorder the matrix
-        const int ord[4] = { 3, 2, 1, 0 };
-        for (int k = 0; k < 4; ++k) {
-            const int src = swapped ? ord[k] : k;
-            g.m[2 * k] = m8[2 * src] * nrm;
-            g.m[2 * k + 1] = m8[2 * src + 1] * nrm;
-        }
-        if (s->prec == 32) {
-            for (int k = 0; k < 8; ++k) {
-                g.m[k] = (double)(float)g.m[k];
-            }
-        }
-        const bool z1 = g.m[2] == 0 && g.m[3] == 0, z2 = g.m[4] == 0 && g.m[5] == 0;
-        const bool z0 = g.m[0] == 0 && g.m[1] == 0, z3 = g.m[6] == 0 && g.m[7] == 0;
-        g.kind = (z1 && z2) ? 1 : ((z0 && z3) ? 2 : 0);
+        make_gate_op(s->prec, off1, off2, pmask, m8, nrm, g);
         if (fused_accepts(s, g)) {
             s->queue.push_back(g);
             if (s->queue.size() >= 4096) {
@@ -2562,6 +2569,25 @@ int b200sv_plan_dry_run(int n_qubits, int precision, int n_gates, const int* tar
         return einval("plan_dry_run: bad arguments");
     }
     return fused_plan_dry_run(n_qubits, precision, n_gates, targets, cmasks, kinds, n_sweeps, n_passes);
+}
+
+int b200sv_emulate_fused(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2, const uint64_t* pmasks,
+    const double* mats8, void* host_state)
+{
+    if (n_gates < 0 || (n_gates && (!off1 || !off2 || !pmasks || !mats8)) || !host_state || (precision != 32 && precision != 64) ||
+        n_qubits < 5 || n_qubits > 30) {
+        return einval("emulate_fused: bad arguments");
+    }
+    std::vector<GateOp> q((size_t)n_gates);
+    const uint64_t dim = 1ULL << n_qubits;
+    for (int i = 0; i < n_gates; ++i) {
+        const uint64_t diff = off1[i] ^ off2[i];
+        if (!diff || (diff & (diff - 1U)) || pmasks[i] >= dim || ((off1[i] | off2[i]) & ~pmasks[i])) {
+            return einval("emulate_fused: not a single-target gate");
+        }
+        make_gate_op(precision, off1[i], off2[i], pmasks[i], mats8 + 8 * (size_t)i, 1.0, q[(size_t)i]);
+    }
+    return fused_emulate(n_qubits, precision, q, host_state);
 }
 
 int b200sv_flush_l2(b200sv_t s, uint64_t bytes)

@@ -1461,6 +1461,260 @@ int fused_flush(State* s)
     return B200SV_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Host emulation of the sweep programs (TEST HOOK, never on the engine's path): runs the planner + encoder on a gate
+// list and then interprets every encoded sweep on a HOST state vector, following the device kernel table by table —
+// tile base (push-apart), active-op ballots, outer/DIAG phase slots, per-pass thread -> sub-block map (sbit / itoffC),
+// register-chunk tables (goff for the HBM side, swizzled pswzB for the smem tile), staged vs direct first/last pass and
+// the op semantics of exec_op.  `pytest -m "not gpu"` uses it to check scheduler and encoder against the oracle
+// without a device (tests/test_fused_emulation.py).
+// ---------------------------------------------------------------------------------------------------------
+template <typename R> struct EmuC {
+    R x, y;
+};
+template <typename R> static inline EmuC<R> emu_mul(EmuC<R> a, R px, R py) { return EmuC<R>{ a.x * px - a.y * py, a.x * py + a.y * px }; }
+
+template <typename R>
+static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xsb, const R* tileScale, int NA)
+{
+    const uint32_t code = op.code, emask = op.emask, lmaskSb = op.lmaskSb, lvalSb = op.lvalSb;
+    bool tp = true;
+    if (code & CODE_HAS_SB) {
+        tp = (xsb & lmaskSb) == lvalSb;
+    }
+    const uint32_t em = tp ? emask : 0U;
+    const uint32_t c = code & 0xffU;
+    auto had = [&](int J) {
+        for (int e = 0; e < NA; ++e) {
+            if (!(e & (1 << J))) {
+                const EmuC<R> x = a[e], y = a[e | (1 << J)];
+                a[e] = EmuC<R>{ x.x + y.x, x.y + y.y };
+                a[e | (1 << J)] = EmuC<R>{ x.x - y.x, x.y - y.y };
+            }
+        }
+    };
+    auto phase_reg = [&](int J, R px, R py) {
+        for (int e = 0; e < NA; ++e) {
+            if (e & (1 << J)) {
+                a[e] = emu_mul(a[e], px, py);
+            }
+        }
+    };
+    if (c == OPC_LAYER) {
+        for (int J = 0; (1 << J) < NA; ++J) {
+            if ((emask >> J) & 1U) {
+                had(J);
+            }
+        }
+        return;
+    }
+    if (c == OPC_DIAG) {
+        for (int J = 0; (1 << J) < NA; ++J) {
+            if ((emask >> J) & 1U) {
+                const uint32_t slot = lmaskSb + (uint32_t)__builtin_popcount(emask & ((1U << J) - 1U));
+                const R px = tileScale[2 * slot], py = tileScale[2 * slot + 1];
+                if (px != (R)1 || py != (R)0) {
+                    phase_reg(J, px, py);
+                }
+            }
+        }
+        return;
+    }
+    if (c == OPC_SCALE) {
+        for (int e = 0; e < NA; ++e) {
+            a[e] = emu_mul(a[e], tileScale[0], tileScale[1]);
+        }
+        return;
+    }
+    const uint32_t kind = c / 5U;
+    const int J = (int)(c % 5U);
+    const R* m = op.m;
+    switch (kind) {
+    case K_HAD:
+        had(J);
+        break;
+    case K_XSWAP:
+        for (int e = 0; e < NA; ++e) {
+            if (!(e & (1 << J)) && ((em >> e) & 1U)) {
+                std::swap(a[e], a[e | (1 << J)]);
+            }
+        }
+        break;
+    case K_GEN_U:
+    case K_GEN_P:
+        for (int e = 0; e < NA; ++e) {
+            if (!(e & (1 << J)) && (kind == K_GEN_U || ((em >> e) & 1U))) {
+                const EmuC<R> x = a[e], y = a[e | (1 << J)];
+                const EmuC<R> x0 = emu_mul(x, m[0], m[1]), y1 = emu_mul(y, m[2], m[3]);
+                const EmuC<R> x2 = emu_mul(x, m[4], m[5]), y3 = emu_mul(y, m[6], m[7]);
+                a[e] = EmuC<R>{ x0.x + y1.x, x0.y + y1.y };
+                a[e | (1 << J)] = EmuC<R>{ x2.x + y3.x, x2.y + y3.y };
+            }
+        }
+        break;
+    case K_PHREG1:
+        if (tp) {
+            phase_reg(J, m[0], m[1]);
+        }
+        break;
+    case K_PHUNI:
+        if (tp) {
+            for (int e = 0; e < NA; ++e) {
+                a[e] = emu_mul(a[e], m[0], m[1]);
+            }
+        }
+        break;
+    case K_PHGEN:
+        for (int e = 0; e < NA; ++e) {
+            if ((em >> e) & 1U) {
+                a[e] = emu_mul(a[e], m[0], m[1]);
+            }
+        }
+        break;
+    default:
+        break;
+    }
+}
+
+template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<R>* psi, int nq, const TileCfg& cfg)
+{
+    const DevSweep& sw = *reinterpret_cast<const DevSweep*>(prog);
+    const DevOp<R>* ops = reinterpret_cast<const DevOp<R>*>(prog + sizeof(DevSweep));
+    const DevOuterPhase<R>* outer = reinterpret_cast<const DevOuterPhase<R>*>(prog + sw.outerOff);
+    const int APC = 1 << cfg.apcLog, NCH = 1 << cfg.RB, NA = NCH * APC, NT = cfg.NT;
+    const int kc = sw.kc;
+    const uint32_t nChunk = 1U << kc;
+    const int lcb = sw.lowAmpBits - cfg.apcLog;
+    const uint32_t colMask = (1U << lcb) - 1U;
+    const uint32_t nRows = nChunk >> lcb;
+    std::vector<uint64_t> rowOff(nRows);
+    for (uint32_t r = 0; r < nRows; ++r) {
+        uint64_t off = 0;
+        for (int h = 0; h < sw.nHigh; ++h) {
+            if ((r >> h) & 1U) {
+                off |= sw.highPow[h];
+            }
+        }
+        rowOff[r] = off;
+    }
+    const uint32_t nSub = nChunk >> cfg.RB;
+    const uint64_t nTiles = (1ULL << nq) >> cfg.kA;
+    std::vector<EmuC<R>> tile((size_t)nChunk * APC); // indexed by swizzled chunk slot
+    std::vector<R> tab((size_t)2 * std::max(1, sw.nSlots));
+    std::vector<EmuC<R>> a((size_t)NA);
+    for (uint64_t t = 0; t < nTiles; ++t) {
+        uint64_t base = t << sw.lowAmpBits;
+        for (int h = 0; h < sw.nHigh; ++h) {
+            const uint64_t lo = base & sw.highLow[h];
+            base = ((base ^ lo) << 1) | lo;
+        }
+        EmuC<R>* const tilePsi = psi + base;
+        // preamble: ballots, tile scalar, DIAG slots
+        std::vector<bool> act((size_t)std::max(1, sw.nOps));
+        for (int o = 0; o < sw.nOps; ++o) {
+            act[o] = (base & ops[o].omask) == ops[o].oval;
+        }
+        {
+            double fx = 1.0, fy = 0.0;
+            for (int i = 0; i < sw.nOuter; ++i) {
+                if ((base & outer[i].omask) == outer[i].oval) {
+                    const double nx = fx * (double)outer[i].ph[0] - fy * (double)outer[i].ph[1];
+                    fy = fx * (double)outer[i].ph[1] + fy * (double)outer[i].ph[0];
+                    fx = nx;
+                }
+            }
+            tab[0] = (R)(fx * sw.scale);
+            tab[1] = (R)(fy * sw.scale);
+        }
+        for (int sl = 1; sl < sw.nSlots; ++sl) {
+            double fx = 1.0, fy = 0.0;
+            for (int i = sw.slotBeg[sl]; i < sw.slotBeg[sl + 1]; ++i) {
+                if ((base & outer[i].omask) == outer[i].oval) {
+                    const double nx = fx * (double)outer[i].ph[0] - fy * (double)outer[i].ph[1];
+                    fy = fx * (double)outer[i].ph[1] + fy * (double)outer[i].ph[0];
+                    fx = nx;
+                }
+            }
+            tab[2 * sl] = (R)fx;
+            tab[2 * sl + 1] = (R)fy;
+        }
+        if (!sw.directIn) {
+            for (uint32_t c = 0; c < nChunk; ++c) {
+                for (int w = 0; w < APC; ++w) {
+                    tile[(size_t)swz(c) * APC + w] = tilePsi[rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC + w];
+                }
+            }
+        }
+        for (int p = 0; p < sw.nPass; ++p) {
+            const DevPass& ps = sw.pass[p];
+            const bool fromGlobal = (p == 0) && sw.directIn, toGlobal = (p == sw.nPass - 1) && sw.directOut;
+            for (int tid = 0; tid < NT; ++tid) {
+                uint32_t dep = 0;
+                const int nb = ps.nsb < 8 ? ps.nsb : 8;
+                for (int i = 0; i < nb; ++i) {
+                    dep |= (((uint32_t)tid >> i) & 1U) << ps.sbit[i];
+                }
+                for (int it = 0; it < ps.nIt; ++it) {
+                    if ((uint32_t)(it * NT + tid) >= nSub) {
+                        break;
+                    }
+                    const uint32_t sbc = dep | ps.itoffC[it];
+                    const uint32_t swb = swz(sbc) << 4;
+                    EmuC<R>* const gsub = tilePsi + rowOff[sbc >> lcb] + (uint64_t)(sbc & colMask) * APC;
+                    for (int e = 0; e < NCH; ++e) {
+                        for (int w = 0; w < APC; ++w) {
+                            a[(size_t)e * APC + w] =
+                                fromGlobal ? gsub[ps.goff[e] + w] : tile[(size_t)((swb ^ ps.pswzB[e]) >> 4) * APC + w];
+                        }
+                    }
+                    const uint32_t xsb = sbc * (uint32_t)APC;
+                    for (int o = ps.opBegin; o < ps.opEnd; ++o) {
+                        if (act[o]) {
+                            emu_exec_op<R>(a, ops[o], xsb, tab.data(), NA);
+                        }
+                    }
+                    for (int e = 0; e < NCH; ++e) {
+                        for (int w = 0; w < APC; ++w) {
+                            if (toGlobal) {
+                                gsub[ps.goff[e] + w] = a[(size_t)e * APC + w];
+                            } else {
+                                tile[(size_t)((swb ^ ps.pswzB[e]) >> 4) * APC + w] = a[(size_t)e * APC + w];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!sw.directOut) {
+            for (uint32_t c = 0; c < nChunk; ++c) {
+                for (int w = 0; w < APC; ++w) {
+                    tilePsi[rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC + w] = tile[(size_t)swz(c) * APC + w];
+                }
+            }
+        }
+    }
+}
+
+int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state)
+{
+    std::vector<HostOp> pending;
+    lower_queue(q, pending);
+    const TileCfg cfg = state_cfg(n_qubits, precision);
+    std::vector<unsigned char> buf;
+    while (!pending.empty()) {
+        size_t bytes = 0, scratch = 0, nops = 0;
+        int npass = 0;
+        buf.clear();
+        SV_TRY(plan_and_encode(pending, cfg, precision, buf, &bytes, &scratch, &nops, &npass));
+        if (precision == 32) {
+            emulate_sweep<float>(buf.data(), reinterpret_cast<EmuC<float>*>(host_state), n_qubits, cfg);
+        } else {
+            emulate_sweep<double>(buf.data(), reinterpret_cast<EmuC<double>*>(host_state), n_qubits, cfg);
+        }
+    }
+    return B200SV_OK;
+}
+
 int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks, const int* kinds,
     int* n_sweeps, int* n_passes)
 {

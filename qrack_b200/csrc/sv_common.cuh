@@ -128,6 +128,7 @@ int sm_count(int dev);
 int fused_flush(State* s);
 bool fused_accepts(const State* s, const GateOp& g);
 void fused_release(State* s);
+int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state);
 int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks, const int* kinds,
     int* n_sweeps, int* n_passes);
 

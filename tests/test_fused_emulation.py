@@ -1,0 +1,83 @@
+"""CPU tests of the fused-sweep scheduler and program encoder: the real planner/encoder of libb200sv.so + the host
+interpreter of the encoded programs (b200sv_emulate_fused, no device) against the oracle restatement and the golden
+fixtures of the compiled reference.  Same tolerances as the GPU parity tests."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle.restate_engine import QEngineRestate
+from qrack_b200 import qscript
+
+import util
+from emu_engine import QEngineEmu
+
+
+def run_emu(text, prec):
+    regs, results = qscript.run(text, util.make_factory(QEngineEmu, prec))
+    return {k: v.GetQuantumState() for k, v in regs.items()}, results, regs
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", [n for n in util.golden_names() if not n.startswith("alu_")])
+def test_emulated_sweeps_reproduce_golden_fixtures(name, prec):
+    text, regs, results = util.load_golden(name, prec)
+    got, gres, _ = run_emu(text, prec)
+    util.assert_states_close(got, regs, prec, name)
+    util.assert_results_close(gres, results, prec, name)
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("gen", ["htcnot", "u3", "qft", "qv", "grover"])
+def test_emulated_sweeps_vs_oracle_multi_tile(gen, prec):
+    """16-17 qubits: 8-16 tiles per sweep, high tile qubits, outer controls (ballots), DIAG slots, several passes."""
+    n = 16 if prec == 32 else 15
+    text = {"htcnot": lambda: qscript.random_htcnot(n, 12, seed=5, timed=False),
+            "u3": lambda: qscript.random_u3_cnot(n, 5, seed=6),
+            "qft": lambda: "qubits %d\nSetPermutation 12345\nH 3\nH 9\nQFT 0 %d\nT 2\nIQFT 1 %d\n" % (n, n, n - 2),
+            "qv": lambda: qscript.quantum_volume(n, depth=5, seed=8, timed=False),
+            "grover": lambda: qscript.grover(n, 2, target=77, timed=False)}[gen]()
+    want, _ = util.run_engine(text, QEngineRestate, prec)
+    got, _, regs = run_emu(text, prec)
+    util.assert_states_close(got, want, prec, gen)
+    assert regs[0].be.flushes >= 1          # the gates really went through the planner + emulator
+
+
+@pytest.mark.parametrize("knobs", ["3,5,4,3,3", "4,7,7,3,4", "4,6,6,0,3", "3,9,8,1,3", "4,6,6,3,3,0,0,0", "4,6,6,3,3,0,0,3"])
+def test_emulated_sweeps_under_every_tile_shape(knobs):
+    """The tile-shape / bundling knobs (B200SV_FUSED) change pass tables and DIAG/LAYER grouping; each setting must
+    still reproduce the oracle.  Runs in a subprocess because the library reads the knobs once."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, random; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from oracle.restate_engine import QEngineRestate\n"
+        "from qrack_b200 import qscript\n"
+        "import util\n"
+        "from emu_engine import QEngineEmu\n"
+        "for prec in (32, 64):\n"
+        "    text = qscript.random_htcnot(15, 8, seed=3, timed=False) + 'QFT 2 9\\nCCNOT 1 14 7\\nMCPhase 2 3 13 8 0.6 0.8 1 0\\n'\n"
+        "    want, _ = util.run_engine(text, QEngineRestate, prec)\n"
+        "    regs, _ = qscript.run(text, util.make_factory(QEngineEmu, prec))\n"
+        "    util.assert_states_close({k: v.GetQuantumState() for k, v in regs.items()}, want, prec, 'knobs')\n"
+        "print('ok')\n"
+    ) % (util.ROOT, os.path.join(util.ROOT, "tests"))
+    env = dict(os.environ, B200SV_FUSED=knobs)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_emulation_hook_rejects_bad_arguments():
+    import ctypes
+    from qrack_b200 import _abi
+    lib = _abi.load()
+    st = np.zeros(32, dtype=np.complex64)
+    one = (ctypes.c_uint64 * 1)(3)
+    two = (ctypes.c_uint64 * 1)(0)
+    pm = (ctypes.c_uint64 * 1)(3)
+    m = (ctypes.c_double * 8)(1, 0, 0, 0, 0, 0, 1, 0)
+    # off1 ^ off2 has two bits: not a single-target gate
+    assert lib.b200sv_emulate_fused(5, 32, 1, one, two, pm, m, st.ctypes.data_as(ctypes.c_void_p)) == _abi.B200SV_EINVAL
+    assert lib.b200sv_emulate_fused(3, 32, 0, None, None, None, None, st.ctypes.data_as(ctypes.c_void_p)) == _abi.B200SV_EINVAL

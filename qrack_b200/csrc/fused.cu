@@ -17,9 +17,11 @@
 #include "sv_common.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 
 namespace b200sv {
@@ -1261,9 +1263,11 @@ struct Arena {
     cudaEvent_t done = nullptr;
     bool pending = false;
 };
-static std::vector<std::pair<State*, Arena>>& arenas()
+// Registry state -> arena.  The arenas live on the heap (stable addresses): QPager drives its page engines from several
+// host threads, so one thread may register or release a state while another still holds its own arena pointer.
+static std::vector<std::pair<State*, std::unique_ptr<Arena>>>& arenas()
 {
-    static std::vector<std::pair<State*, Arena>> a;
+    static std::vector<std::pair<State*, std::unique_ptr<Arena>>> a;
     return a;
 }
 static std::mutex& arena_mutex()
@@ -1276,30 +1280,35 @@ static Arena* get_arena(State* s)
     std::lock_guard<std::mutex> lk(arena_mutex());
     for (auto& kv : arenas()) {
         if (kv.first == s) {
-            return &kv.second;
+            return kv.second.get();
         }
     }
-    arenas().push_back({ s, Arena() });
-    return &arenas().back().second;
+    arenas().emplace_back(s, std::unique_ptr<Arena>(new Arena()));
+    return arenas().back().second.get();
 }
 void fused_release(State* s)
 {
-    std::lock_guard<std::mutex> lk(arena_mutex());
-    auto& v = arenas();
-    for (size_t i = 0; i < v.size(); ++i) {
-        if (v[i].first == s) {
-            Arena& a = v[i].second;
-            if (a.dev) {
-                cudaFree(a.dev);
+    std::unique_ptr<Arena> mine;
+    {
+        std::lock_guard<std::mutex> lk(arena_mutex());
+        auto& v = arenas();
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (v[i].first == s) {
+                mine = std::move(v[i].second);
+                v.erase(v.begin() + i);
+                break;
             }
-            if (a.host) {
-                cudaFreeHost(a.host);
-            }
-            if (a.done) {
-                cudaEventDestroy(a.done);
-            }
-            v.erase(v.begin() + i);
-            return;
+        }
+    }
+    if (mine) {
+        if (mine->dev) {
+            cudaFree(mine->dev);
+        }
+        if (mine->host) {
+            cudaFreeHost(mine->host);
+        }
+        if (mine->done) {
+            cudaEventDestroy(mine->done);
         }
     }
 }
@@ -1315,11 +1324,11 @@ static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes
 {
     auto kern = k_fused_sweep<R, KC, RB, NT, MINB>;
     const size_t shm = ((size_t)16 << KC) + progBytes + scratchBytes;
-    static unsigned long long attr_set_mask = 0; // per device: the attribute is per-context
-    if (!(attr_set_mask & (1ULL << s->dev))) {
+    static std::atomic<unsigned long long> attr_set_mask{ 0 }; // per device: the attribute is per-context
+    if (!(attr_set_mask.load() & (1ULL << s->dev))) {
         SV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int)(((size_t)16 << KC) + (MINB >= 3 ? MAX_PROG_BYTES_3CTA : MAX_PROG_BYTES_2CTA))));
-        attr_set_mask |= 1ULL << s->dev;
+        attr_set_mask.fetch_or(1ULL << s->dev);
     }
     const uint64_t maxGrid = (uint64_t)sm_count(s->dev) * MINB;
     const unsigned grid = (unsigned)std::min<uint64_t>(nTiles, maxGrid);

@@ -42,6 +42,32 @@ def measured_traffic(kernel_bytes_per_launch):
         return None
 
 
+def fused_single_qubit_sweep_probe(q, n, amp_bytes, peak, reps=5, warm=2):
+    """The north-star's own roofline target, measured live: ONE fused sweep of single-qubit gates (H on qubits 0 and 1)
+    over the resident 2^n state; physical bytes 2 * 2^n * S / CUDA-event time on the engine's stream.  Never fatal."""
+    try:
+        def layer():
+            q.H(0)
+            q.H(1)
+            q.be.flush()
+        for _ in range(warm):
+            layer()
+        q.Finish()
+        s0 = q.be.stats()
+        q.be.timer_begin()
+        for _ in range(reps):
+            layer()
+        ms = q.be.timer_end() / reps
+        s1 = q.be.stats()
+        sweeps = (s1["fused_sweeps"] - s0["fused_sweeps"]) / float(reps)
+        if ms <= 0 or sweeps != 1.0:
+            return {"gates": 2, "ms": ms, "sweeps": sweeps, "physical_gbs": None, "frac": None}
+        gbs = 2.0 * (1 << n) * amp_bytes / (ms * 1e-3) / 1e9
+        return {"gates": 2, "ms": ms, "sweeps": sweeps, "physical_gbs": gbs, "frac": gbs / peak}
+    except Exception as e:  # diagnostic only: the headline numbers above are already taken
+        return {"error": repr(e)[:200]}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -341,6 +367,8 @@ def main():
                          "fused_gates": int(stats["fused_gates"])},
             "clocks": sampler.summary(),
         }
+        if world == 1 and stats["fused_sweeps"]:
+            line["roofline"]["fused_single_qubit_sweep"] = fused_single_qubit_sweep_probe(q, n, amp_bytes, peak)
         if world == 1 and not args.skip_cpu_baseline:
             cb = cpu_reference_sample(n, depth, args.seed, prec, args.cpu_sample_gates)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

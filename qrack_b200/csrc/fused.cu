@@ -1078,8 +1078,15 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                 }
                 continue;
             }
-            // everything else is a single op and closes the open bundle
-            close_bundle();
+            // everything else is a single op.  The open layer is emitted later than this op, so it has to be closed first
+            // if the op touches one of its qubits in any way (target, control or phase); with the conservative setting
+            // (bundle bit 2 clear) every single op closes it.
+            {
+                const uint64_t touch = hop.cmask | (hop.tq >= 0 ? bitq(hop.tq) : 0);
+                if (!(cfg.bundle & 4) || (touch & ndq)) {
+                    close_bundle();
+                }
+            }
             DevOp<R> d;
             memset(&d, 0, sizeof(d));
             d.omask = hop.cmask & ~tileMask;
@@ -1343,7 +1350,8 @@ struct FusedKnobs {
     int L32 = 6;
     int L64 = 6;
     int RB64 = 3; // fp64: 8 double2 amplitudes per sub-block keep 3 CTAs/SM resident
-    int bundle = 3; // bit 0: merge Hadamards on distinct register bits into one LAYER op; bit 1: DIAG phase groups
+    int bundle = 3; // bit 0: merge Hadamards on distinct register bits into one LAYER op; bit 1: DIAG phase groups;
+                    // bit 2 (off by default, unmeasured): a LAYER stays open across ops that do not touch its qubits
     int pf = 0;     // 1: L2 prefetch of the CTA's next tile during the passes
     int dlow = 1;   // first/last pass go straight HBM<->registers when at most this many of their register bits are chunk bits 0..2
 };

@@ -44,7 +44,7 @@ def test_emulated_sweeps_vs_oracle_multi_tile(gen, prec):
     assert regs[0].be.flushes >= 1          # the gates really went through the planner + emulator
 
 
-@pytest.mark.parametrize("knobs", ["3,5,4,3,3", "4,7,7,3,4", "4,6,6,0,3", "3,9,8,1,3", "4,6,6,3,3,0,0,0", "4,6,6,3,3,0,0,3"])
+@pytest.mark.parametrize("knobs", ["3,5,4,3,3", "4,6,6,7,3", "4,7,7,3,4", "4,6,6,0,3", "3,9,8,1,3", "4,6,6,3,3,0,0,0", "4,6,6,3,3,0,0,3"])
 def test_emulated_sweeps_under_every_tile_shape(knobs):
     """The tile-shape / bundling knobs (B200SV_FUSED) change pass tables and DIAG/LAYER grouping; each setting must
     still reproduce the oracle.  Runs in a subprocess because the library reads the knobs once."""

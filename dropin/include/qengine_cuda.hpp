@@ -50,108 +50,108 @@ public:
         real1_f ignored3 = _qrack_qunit_sep_thresh);
     ~QEngineCUDA();
 
-    bool isOpenCL() { return true; }
-    void SetDevice(int64_t dID);
-    int64_t GetDevice() { return deviceID; }
+    bool isOpenCL() override { return true; }
+    void SetDevice(int64_t dID) override;
+    int64_t GetDevice() override { return deviceID; }
     bitCapIntOcl GetMaxSize();
     b200sv_state* Handle() { return sv; }
 
-    void SetQubitCount(bitLenInt qb);
-    void Finish();
-    bool isFinished();
-    void Dump() {}
+    void SetQubitCount(bitLenInt qb) override;
+    void Finish() override;
+    bool isFinished() override;
+    void Dump() override {}
 
     // ---- QEngine page / buffer virtuals (qengine.hpp:127-152) ----
-    void ZeroAmplitudes();
-    void CopyStateVec(QEnginePtr src);
-    bool IsZeroAmplitude();
-    void GetAmplitudePage(complex* pagePtr, bitCapIntOcl offset, bitCapIntOcl length);
-    void SetAmplitudePage(const complex* pagePtr, bitCapIntOcl offset, bitCapIntOcl length);
-    void SetAmplitudePage(QEnginePtr pageEnginePtr, bitCapIntOcl srcOffset, bitCapIntOcl dstOffset, bitCapIntOcl length);
-    void ShuffleBuffers(QEnginePtr engine);
-    QEnginePtr CloneEmpty();
-    QInterfacePtr Clone();
-    void QueueSetDoNormalize(bool doNorm) { doNormalize = doNorm; }
-    void QueueSetRunningNorm(real1_f runningNrm) { runningNorm = (real1)runningNrm; }
+    void ZeroAmplitudes() override;
+    void CopyStateVec(QEnginePtr src) override;
+    bool IsZeroAmplitude() override;
+    void GetAmplitudePage(complex* pagePtr, bitCapIntOcl offset, bitCapIntOcl length) override;
+    void SetAmplitudePage(const complex* pagePtr, bitCapIntOcl offset, bitCapIntOcl length) override;
+    void SetAmplitudePage(QEnginePtr pageEnginePtr, bitCapIntOcl srcOffset, bitCapIntOcl dstOffset, bitCapIntOcl length) override;
+    void ShuffleBuffers(QEnginePtr engine) override;
+    QEnginePtr CloneEmpty() override;
+    QInterfacePtr Clone() override;
+    void QueueSetDoNormalize(bool doNorm) override { doNormalize = doNorm; }
+    void QueueSetRunningNorm(real1_f runningNrm) override { runningNorm = (real1)runningNrm; }
 
     // ---- state access (qinterface.hpp:313-344) ----
-    void SetQuantumState(const complex* inputState);
-    void GetQuantumState(complex* outputState);
-    void GetProbs(real1* outputProbs);
-    complex GetAmplitude(const bitCapInt& perm);
-    void SetAmplitude(const bitCapInt& perm, const complex& amp);
-    void SetPermutation(const bitCapInt& perm, const complex& phaseFac = CMPLX_DEFAULT_ARG);
+    void SetQuantumState(const complex* inputState) override;
+    void GetQuantumState(complex* outputState) override;
+    void GetProbs(real1* outputProbs) override;
+    complex GetAmplitude(const bitCapInt& perm) override;
+    void SetAmplitude(const bitCapInt& perm, const complex& amp) override;
+    void SetPermutation(const bitCapInt& perm, const complex& phaseFac = CMPLX_DEFAULT_ARG) override;
 
     // ---- the gate hot path ----
     void Apply2x2(bitCapInt offset1, bitCapInt offset2, const complex* mtrx, bitLenInt bitCount, bitCapInt const* qPowersSorted,
         bool doCalcNorm, real1_f norm_thresh = REAL1_DEFAULT_ARG);
     using QEngine::ApplyM;
-    void ApplyM(const bitCapInt& regMask, const bitCapInt& result, const complex& nrm);
-    void XMask(const bitCapInt& mask);
-    void PhaseParity(real1_f radians, const bitCapInt& mask);
-    void PhaseRootNMask(bitLenInt n, const bitCapInt& mask);
+    void ApplyM(const bitCapInt& regMask, const bitCapInt& result, const complex& nrm) override;
+    void XMask(const bitCapInt& mask) override;
+    void PhaseParity(real1_f radians, const bitCapInt& mask) override;
+    void PhaseRootNMask(bitLenInt n, const bitCapInt& mask) override;
     using QEngine::UniformlyControlledSingleBit;
     void UniformlyControlledSingleBit(const std::vector<bitLenInt>& controls, bitLenInt qubitIndex, const complex* mtrxs,
         const std::vector<bitCapInt>& mtrxSkipPowers, const bitCapInt& mtrxSkipValueMask);
-    void UniformParityRZ(const bitCapInt& mask, real1_f angle);
-    void CUniformParityRZ(const std::vector<bitLenInt>& controls, const bitCapInt& mask, real1_f angle);
+    void UniformParityRZ(const bitCapInt& mask, real1_f angle) override;
+    void CUniformParityRZ(const std::vector<bitLenInt>& controls, const bitCapInt& mask, real1_f angle) override;
 
     // ---- probabilities / measurement ----
-    real1_f Prob(bitLenInt qubit);
-    real1_f CtrlOrAntiProb(bool controlState, bitLenInt control, bitLenInt target);
-    real1_f ProbReg(bitLenInt start, bitLenInt length, const bitCapInt& permutation);
-    real1_f ProbMask(const bitCapInt& mask, const bitCapInt& permutation);
-    void ProbMaskAll(const bitCapInt& mask, real1* probsArray);
-    void ProbRegAll(bitLenInt start, bitLenInt length, real1* probsArray);
-    real1_f ProbParity(const bitCapInt& mask);
-    bool ForceMParity(const bitCapInt& mask, bool result, bool doForce = true);
-    bitCapInt MAll();
+    real1_f Prob(bitLenInt qubit) override;
+    real1_f CtrlOrAntiProb(bool controlState, bitLenInt control, bitLenInt target) override;
+    real1_f ProbReg(bitLenInt start, bitLenInt length, const bitCapInt& permutation) override;
+    real1_f ProbMask(const bitCapInt& mask, const bitCapInt& permutation) override;
+    void ProbMaskAll(const bitCapInt& mask, real1* probsArray) override;
+    void ProbRegAll(bitLenInt start, bitLenInt length, real1* probsArray) override;
+    real1_f ProbParity(const bitCapInt& mask) override;
+    bool ForceMParity(const bitCapInt& mask, bool result, bool doForce = true) override;
+    bitCapInt MAll() override;
     using QInterface::HighestProbAll;
     bitCapInt HighestProbAll(); // device arg-max; the QInterface default asks ProbAll() for every permutation
-    real1_f FirstNonzeroPhase() { return IsZeroAmplitude() ? ZERO_R1_F : QInterface::FirstNonzeroPhase(); }
-    real1_f GetExpectation(bitLenInt valueStart, bitLenInt valueLength);
+    real1_f FirstNonzeroPhase() override { return IsZeroAmplitude() ? ZERO_R1_F : QInterface::FirstNonzeroPhase(); }
+    real1_f GetExpectation(bitLenInt valueStart, bitLenInt valueLength) override;
 
     // ---- structure ----
     using QEngine::Compose;
     bitLenInt Compose(QEngineCUDAPtr toCopy);
-    bitLenInt Compose(QInterfacePtr toCopy) { return Compose(Cast(toCopy, "Compose")); }
+    bitLenInt Compose(QInterfacePtr toCopy) override { return Compose(Cast(toCopy, "Compose")); }
     bitLenInt Compose(QEngineCUDAPtr toCopy, bitLenInt start);
-    bitLenInt Compose(QInterfacePtr toCopy, bitLenInt start) { return Compose(Cast(toCopy, "Compose"), start); }
+    bitLenInt Compose(QInterfacePtr toCopy, bitLenInt start) override { return Compose(Cast(toCopy, "Compose"), start); }
     using QEngine::Decompose;
-    void Decompose(bitLenInt start, QInterfacePtr dest);
-    void Dispose(bitLenInt start, bitLenInt length);
-    void Dispose(bitLenInt start, bitLenInt length, const bitCapInt& disposedPerm);
+    void Decompose(bitLenInt start, QInterfacePtr dest) override;
+    void Dispose(bitLenInt start, bitLenInt length) override;
+    void Dispose(bitLenInt start, bitLenInt length, const bitCapInt& disposedPerm) override;
     using QEngine::Allocate;
-    bitLenInt Allocate(bitLenInt start, bitLenInt length);
+    bitLenInt Allocate(bitLenInt start, bitLenInt length) override;
 
     // ---- norm ----
-    real1_f SumSqrDiff(QInterfacePtr toCompare);
+    real1_f SumSqrDiff(QInterfacePtr toCompare) override;
     void NormalizeState(
         real1_f nrm = REAL1_DEFAULT_ARG, real1_f norm_thresh = REAL1_DEFAULT_ARG, real1_f phaseArg = ZERO_R1_F);
-    void UpdateRunningNorm(real1_f norm_thresh = REAL1_DEFAULT_ARG);
+    void UpdateRunningNorm(real1_f norm_thresh = REAL1_DEFAULT_ARG) override;
 
-    void ROL(bitLenInt shift, bitLenInt start, bitLenInt length);
-    void ROR(bitLenInt shift, bitLenInt start, bitLenInt length);
+    void ROL(bitLenInt shift, bitLenInt start, bitLenInt length) override;
+    void ROR(bitLenInt shift, bitLenInt start, bitLenInt length) override;
 
 #if ENABLE_ALU
     // ---- QAlu (include/qalu.hpp): one device sweep each (include/b200sv.h "QAlu family") ----
-    void INC(const bitCapInt& toAdd, bitLenInt start, bitLenInt length);
-    void CINC(const bitCapInt& toAdd, bitLenInt start, bitLenInt length, const std::vector<bitLenInt>& controls);
-    void INCDECC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt carryIndex);
-    void INCS(const bitCapInt& toAdd, bitLenInt start, bitLenInt length, bitLenInt overflowIndex);
-    void MULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length);
-    void IMULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length);
+    void INC(const bitCapInt& toAdd, bitLenInt start, bitLenInt length) override;
+    void CINC(const bitCapInt& toAdd, bitLenInt start, bitLenInt length, const std::vector<bitLenInt>& controls) override;
+    void INCDECC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt carryIndex) override;
+    void INCS(const bitCapInt& toAdd, bitLenInt start, bitLenInt length, bitLenInt overflowIndex) override;
+    void MULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length) override;
+    void IMULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length) override;
     void CMULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length,
         const std::vector<bitLenInt>& controls);
     void CIMULModNOut(const bitCapInt& toMod, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length,
         const std::vector<bitLenInt>& controls);
-    void PhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length);
-    void CPhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length, bitLenInt flagIndex);
-    void INCDECSC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt carryIndex);
-    void INCDECSC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt overflowIndex, bitLenInt carryIndex);
-    void MUL(const bitCapInt& toMul, bitLenInt start, bitLenInt carryStart, bitLenInt length);
-    void DIV(const bitCapInt& toDiv, bitLenInt start, bitLenInt carryStart, bitLenInt length);
-    void POWModNOut(const bitCapInt& base, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length);
+    void PhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length) override;
+    void CPhaseFlipIfLess(const bitCapInt& greaterPerm, bitLenInt start, bitLenInt length, bitLenInt flagIndex) override;
+    void INCDECSC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt carryIndex) override;
+    void INCDECSC(const bitCapInt& toMod, bitLenInt start, bitLenInt length, bitLenInt overflowIndex, bitLenInt carryIndex) override;
+    void MUL(const bitCapInt& toMul, bitLenInt start, bitLenInt carryStart, bitLenInt length) override;
+    void DIV(const bitCapInt& toDiv, bitLenInt start, bitLenInt carryStart, bitLenInt length) override;
+    void POWModNOut(const bitCapInt& base, const bitCapInt& modN, bitLenInt inStart, bitLenInt outStart, bitLenInt length) override;
     void CMUL(const bitCapInt& toMul, bitLenInt start, bitLenInt carryStart, bitLenInt length,
         const std::vector<bitLenInt>& controls);
     void CDIV(const bitCapInt& toDiv, bitLenInt start, bitLenInt carryStart, bitLenInt length,
@@ -164,7 +164,7 @@ public:
         bitLenInt carryIndex, const unsigned char* values);
     bitCapInt IndexedSBC(bitLenInt indexStart, bitLenInt indexLength, bitLenInt valueStart, bitLenInt valueLength,
         bitLenInt carryIndex, const unsigned char* values);
-    void Hash(bitLenInt start, bitLenInt length, const unsigned char* values);
+    void Hash(bitLenInt start, bitLenInt length, const unsigned char* values) override;
 #endif
 };
 

@@ -194,6 +194,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
+    shard_bits = max(0, args.gpus).bit_length() - 1 if args.gpus > 1 else 0
+    if args.impl == "reference" and shard_bits:
+        # same configuration as the b200 arm at this N (weak scaling: 2^qubits amplitudes per GPU => qubits + log2 N in all);
+        # the sample shrinks with the state so that the run stays within minutes
+        args.qubits += shard_bits
+        args.cpu_sample_gates = max(12, args.cpu_sample_gates >> shard_bits)
     n, depth, prec = args.qubits, args.depth, args.precision
     amp_bytes = 8 if prec == 32 else 16
     if args.workload == "qft":

@@ -19,6 +19,7 @@ NCCL on the GPU box; the oracle restatement over a torch CPU buffer + gloo in th
 from __future__ import annotations
 
 import math
+import os
 import random
 from typing import Callable, List, Optional, Sequence
 
@@ -221,6 +222,7 @@ class _ShardedBackend:
         self.real = np.float32 if precision == 32 else np.float64
         self.perm = list(range(n_qubits))  # logical qubit -> physical index bit (>= nl: rank bit)
         self.pending: List[_Gate] = []
+        self.defer_exchanges = os.environ.get("B200SV_SHARD_DEFER", "1") != "0"
         self.exchanges = 0
         self.exchange_bytes = 0
         self.local_swaps = 0
@@ -405,16 +407,37 @@ class _ShardedBackend:
 
     # ---- scheduling -------------------------------------------------------------------------------------------------
     def flush(self):
+        """Run the queued gates.  Gates whose target is a rank-bit qubit need an exchange; instead of exchanging at the
+        first one, it is DEFERRED together with everything that does not commute with a deferred gate, and the scan goes
+        on executing every later gate that does commute (shared qubits used diagonally — as control or phase — by both,
+        the rule of the fused scheduler).  One exchange then serves the whole deferred set; the reference's QPager pays
+        a swap-compute-swap per such gate (src/qpager.cpp:425-432).  ``defer_exchanges = False`` restores in-order
+        execution (exchange at the first blocked gate)."""
         ops, self.pending = self.pending, []
-        i = 0
-        while i < len(ops):
-            g = ops[i]
-            if self.perm[g.t] < self.nl or g.diag:
-                self._run_local(g)
-                i += 1
-                continue
-            self._exchange(ops, i)
-        return
+        while ops:
+            deferred: List[_Gate] = []
+            blocked_t = blocked_d = 0
+            for idx, g in enumerate(ops):
+                if g.diag:
+                    uses_t, uses_d = 0, g.cmask | (1 << g.t)
+                else:
+                    uses_t, uses_d = 1 << g.t, g.cmask
+                runnable = g.diag or self.perm[g.t] < self.nl
+                conflict = bool((uses_t & (blocked_t | blocked_d)) or (uses_d & blocked_t))
+                if runnable and not conflict:
+                    self._run_local(g)
+                    continue
+                if not self.defer_exchanges:
+                    deferred = ops[idx:]
+                    break
+                deferred.append(g)
+                blocked_t |= uses_t
+                blocked_d |= uses_d
+            if not deferred:
+                break
+            # the first deferred gate is blocked only by its rank-bit target: after the exchange it can run
+            self._exchange(deferred, 0)
+            ops = deferred
 
     def _run_local(self, g: _Gate):
         nl = self.nl

@@ -44,9 +44,11 @@ def test_emulated_sweeps_vs_oracle_multi_tile(gen, prec):
     assert regs[0].be.flushes >= 1          # the gates really went through the planner + emulator
 
 
-@pytest.mark.parametrize("knobs", ["3,5,4,3,3", "4,6,6,7,3", "4,7,7,3,4", "4,6,6,0,3", "3,9,8,1,3", "4,6,6,3,3,0,0,0", "4,6,6,3,3,0,0,3"])
-def test_emulated_sweeps_under_every_tile_shape(knobs):
-    """The tile-shape / bundling knobs (B200SV_FUSED) change pass tables and DIAG/LAYER grouping; each setting must
+@pytest.mark.parametrize("knobs,search", [("3,5,4,3,3", "0"), ("4,6,6,7,3", "2"), ("4,7,7,3,4", "1"), ("4,6,6,0,3", "0"),
+                                          ("3,9,8,1,3", "4"), ("4,6,6,3,3,0,0,0", "2"), ("4,6,6,3,3,0,0,3", "0")])
+def test_emulated_sweeps_under_every_tile_shape(knobs, search):
+    """The tile-shape / bundling knobs (B200SV_FUSED) and the tile-qubit search (B200SV_PLAN_SEARCH) change the choice of
+    high qubits, pass tables and DIAG/LAYER grouping; each setting must
     still reproduce the oracle.  Runs in a subprocess because the library reads the knobs once."""
     import subprocess
     import sys
@@ -64,7 +66,7 @@ def test_emulated_sweeps_under_every_tile_shape(knobs):
         "    util.assert_states_close({k: v.GetQuantumState() for k, v in regs.items()}, want, prec, 'knobs')\n"
         "print('ok')\n"
     ) % (util.ROOT, os.path.join(util.ROOT, "tests"))
-    env = dict(os.environ, B200SV_FUSED=knobs)
+    env = dict(os.environ, B200SV_FUSED=knobs, B200SV_PLAN_SEARCH=search)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 

@@ -877,6 +877,53 @@ static void plan_sweep(std::vector<HostOp>& pending, const TileCfg& cfg, SweepPl
         PassPlan pp;
         uint64_t regSet = cfg.apcLog ? 1ULL : 0ULL; // fp32: qubit 0 is always register-resident
         int freeReg = cfg.RB;
+        if (searchRounds > 0) {
+            // same hill climbing for the pass's register qubits (targets must be register-resident, everything else rides along)
+            const uint64_t fixed = regSet;
+            uint64_t cur = fixed;
+            {
+                int fr = cfg.RB;
+                uint64_t bT = 0, bD = 0;
+                for (size_t i = 0; i < sel.size() && fr > 0; ++i) {
+                    const HostOp& op = sel[i];
+                    const uint64_t uT = op.tq >= 0 ? bitq(op.tq) : 0, uD = op.cmask;
+                    if ((uT & (bT | bD)) || (uD & bT)) {
+                        bT |= uT;
+                        bD |= uD;
+                    } else if (uT & ~cur) {
+                        cur |= uT;
+                        --fr;
+                    }
+                }
+                if (fr == 0) { // only worth searching when the pass is register-limited
+                    size_t best = greedy_count(sel, (size_t)cfg.maxOps, 4096, cur);
+                    for (int round = 0; round < searchRounds; ++round) {
+                        uint64_t bestSet = cur;
+                        for (uint64_t hm = cur & ~fixed; hm; hm &= hm - 1U) {
+                            const uint64_t hbit = hm & (~hm + 1U);
+                            for (uint64_t cm = inTile & ~cur; cm; cm &= cm - 1U) {
+                                const uint64_t cbit = cm & (~cm + 1U);
+                                const uint64_t cand = (cur & ~hbit) | cbit;
+                                const size_t got = greedy_count(sel, (size_t)cfg.maxOps, 4096, cand);
+                                if (got > best) {
+                                    best = got;
+                                    bestSet = cand;
+                                }
+                            }
+                        }
+                        if (bestSet == cur) {
+                            break;
+                        }
+                        cur = bestSet;
+                    }
+                    regSet = cur;
+                    freeReg = 0;
+                    for (uint64_t m = cur & ~fixed; m; m &= m - 1U) {
+                        pp.regQ.push_back(__builtin_ctzll(m));
+                    }
+                }
+            }
+        }
         greedy_select(sel, pp.ops, (size_t)cfg.maxOps, 4096, [&](const HostOp& op) {
             if (op.tq < 0 || (regSet & bitq(op.tq))) {
                 return true;

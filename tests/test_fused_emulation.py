@@ -83,3 +83,56 @@ def test_emulation_hook_rejects_bad_arguments():
     # off1 ^ off2 has two bits: not a single-target gate
     assert lib.b200sv_emulate_fused(5, 32, 1, one, two, pm, m, st.ctypes.data_as(ctypes.c_void_p)) == _abi.B200SV_EINVAL
     assert lib.b200sv_emulate_fused(3, 32, 0, None, None, None, None, st.ctypes.data_as(ctypes.c_void_p)) == _abi.B200SV_EINVAL
+
+
+def _random_mixed_circuit(rng, n, ngates):
+    import math
+    L = ["qubits %d" % n] + ["H %d" % q for q in range(n) if rng.random() < 0.7]
+
+    def cx():
+        a = rng.uniform(0, 2 * math.pi)
+        return "%.17g %.17g" % (math.cos(a), math.sin(a))
+
+    def unitary():
+        th, ph, la = (rng.uniform(-math.pi, math.pi) for _ in range(3))
+        c, s = math.cos(th / 2), math.sin(th / 2)
+        m = [c, -s * complex(math.cos(la), math.sin(la)), s * complex(math.cos(ph), math.sin(ph)),
+             c * complex(math.cos(ph + la), math.sin(ph + la))]
+        return " ".join("%.17g %.17g" % (complex(z).real, complex(z).imag) for z in m)
+
+    for _ in range(ngates):
+        r, qs = rng.random(), rng.sample(range(n), 4)
+        if r < 0.2:
+            L.append("%s %d" % (rng.choice(["H", "T", "X", "S", "Z", "Y", "IT", "SqrtX"]), qs[0]))
+        elif r < 0.4:
+            L.append("%s %d %d" % (rng.choice(["CNOT", "CZ", "AntiCNOT", "CY"]), qs[0], qs[1]))
+        elif r < 0.5:
+            L.append("CCNOT %d %d %d" % tuple(qs[:3]))
+        elif r < 0.6:
+            L.append("U %d %.17g %.17g %.17g" % (qs[0], rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-3, 3)))
+        elif r < 0.7:
+            L.append("MCMtrx 2 %d %d %d %s" % (qs[0], qs[1], qs[2], unitary()))
+        elif r < 0.78:
+            L.append("MACMtrx 2 %d %d %d %s" % (qs[0], qs[1], qs[2], unitary()))
+        elif r < 0.86:
+            L.append("MCPhase 2 %d %d %d %s %s" % (qs[0], qs[1], qs[2], cx(), cx()))
+        elif r < 0.92:
+            L.append("MACInvert 1 %d %d %s %s" % (qs[0], qs[1], cx(), cx()))
+        elif r < 0.96:
+            L.append("CPhaseRootN %d %d %d" % (rng.randrange(1, 6), qs[0], qs[1]))
+        else:
+            L.append("UCMtrx 3 %d %d %d %d %d %s" % (qs[0], qs[1], qs[2], qs[3], rng.randrange(8), unitary()))
+    return "\n".join(L) + "\n"
+
+
+def test_emulated_sweeps_fuzz_mixed_gates():
+    """Random circuits mixing every single-target form the dispatch produces (controls, anti-controls, phases, inverts,
+    uniformly-controlled selections) on 13-17 qubits, both precisions, through planner + encoder + interpreter."""
+    rng = random.Random(2025)
+    for trial in range(10):
+        prec = rng.choice([32, 64])
+        n = rng.randrange(13, 18) if prec == 32 else rng.randrange(13, 17)
+        text = _random_mixed_circuit(rng, n, rng.randrange(60, 300))
+        want, _ = util.run_engine(text, QEngineRestate, prec)
+        got, _, _ = run_emu(text, prec)
+        util.assert_states_close(got, want, prec, "fuzz %d" % trial)

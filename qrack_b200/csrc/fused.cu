@@ -708,7 +708,7 @@ static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref, int NT = 256
     }
     c.H = c.kA - c.L;
     c.maxOps = MAX_HOST_OPS;
-    c.bundle = 3;
+    c.bundle = 7;
     return c;
 }
 
@@ -1480,8 +1480,8 @@ struct FusedKnobs {
     int L32 = 6;
     int L64 = 6;
     int RB64 = 3; // fp64: 8 double2 amplitudes per sub-block keep 3 CTAs/SM resident
-    int bundle = 3; // bit 0: merge Hadamards on distinct register bits into one LAYER op; bit 1: DIAG phase groups;
-                    // bit 2 (off by default, unmeasured): a LAYER stays open across ops that do not touch its qubits
+    int bundle = 7; // bit 0: merge Hadamards on distinct register bits into one LAYER op; bit 1: DIAG phase groups;
+                    // bit 2: a LAYER stays open across ops that do not touch its qubits
     int pf = 0;     // 1: L2 prefetch of the CTA's next tile during the passes
     int dlow = 1;   // first/last pass go straight HBM<->registers when at most this many of their register bits are chunk bits 0..2
 };

@@ -39,3 +39,17 @@ def test_no_cpu_fallback_without_library(tmp_path, monkeypatch):
     import pytest
     with pytest.raises(RuntimeError):
         _abi.load()
+
+
+def test_reference_c_api_links_against_the_dropin():
+    """dropin/Makefile also links the reference's own C API (src/pinvoke_api.cpp — what PyQrack and the other language
+    bindings dlopen) on top of the drop-in QEngineCUDA: the shared object must load and export the binding surface."""
+    import ctypes
+    import os
+    import pytest
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dropin", "_build", "f32", "libqrack_pinvoke.so")
+    if not os.path.exists(so):
+        pytest.skip("dropin/_build not built (needs /root/reference)")
+    lib = ctypes.CDLL(so)
+    for name in ("init_count_type", "destroy", "seed", "H", "MCX", "MCMtrx", "Prob", "M", "MAll", "Compose", "Decompose", "QFT", "ADD", "MUL"):
+        assert hasattr(lib, name), name

@@ -35,12 +35,23 @@ constexpr int MAX_NCH = 16; // register chunks per sub-block (RB <= 4)
 constexpr int MAX_NA = 32;  // register amplitudes per sub-block
 
 // device op codes.  Single-gate ops: kind * 5 + jr (jr = register-bit index of the target; dense so that the dispatch is a
-// shallow branch tree).  OPC_LAYER = Hadamard butterflies on several register bits; OPC_SCALE = per-tile scalar.
+// shallow branch tree).  OPC_STAGE = per-bit phases + Hadamard butterflies; OPC_SCALE = per-tile scalar.
 // bit 8 = the op has a sub-block predicate.
-enum { K_HAD = 0, K_XSWAP = 1, K_GEN_U = 2, K_GEN_P = 3, K_PHREG1 = 4, K_PHUNI = 5, K_PHGEN = 6 };
-constexpr uint32_t OPC_LAYER = 40U;
-constexpr uint32_t OPC_SCALE = 41, OPC_DIAG = 42U; // multiply every amplitude by the per-tile scalar (outer phases x Hadamard scale)
+enum { K_XSWAP = 0, K_GEN_U = 1, K_GEN_P = 2 };
+constexpr uint32_t OPC_PHGEN = 15U; // phase on the register amplitudes selected by emask (any register-bit predicate)
+constexpr uint32_t OPC_SCALE = 16U; // multiply every amplitude by the per-tile scalar (outer phases x Hadamard scale)
+// OPC_STAGE (r2): for every register bit J, in this order: [phase on the bit-J=1 half] then [Hadamard butterfly on J].
+//   The phase of bit J is the product of (a) one per-tile table slot (members whose predicate is outer qubits AND bit J) and
+//   (b) thread-level members (predicate: outer qubits AND thread bits AND bit J), tested per thread against the per-tile
+//   "effective" (mask, val) table.  Group 0 = members without a register bit (thread-uniform phase on the whole sub-block).
+//   header: emask = hmask | slotMask << 5 | anyMembers << 10; lmaskSb = first table slot; lvalSb = first member;
+//   m[0] (as uint32) = six 5-bit member counts (group 0, then bits 0..4).
+constexpr uint32_t OPC_STAGE = 17U;
+// OPC_PH2 + pair: phase on the 2^(J-2)... register amplitudes that have BOTH register bits of the pair set (CZ / CPhase whose
+// two qubits are register-resident); pair index = k * (k - 1) / 2 + j for bits j < k.
+constexpr uint32_t OPC_PH2 = 18U; // .. 27
 constexpr uint32_t CODE_HAS_SB = 0x100U;
+constexpr int MAX_MEMBERS = 320; // thread-level phase members per sweep (8 bytes each in the double-buffered per-tile table)
 // host (scheduler) op kinds
 enum { OP_GENERAL = 0, OP_HAD = 1, OP_XSWAP = 2, OP_PHASE = 3 };
 
@@ -49,7 +60,7 @@ template <typename R> struct alignas(16) DevOp {
     // --- one 16-byte group, fetched with a single LDS.128 ---
     uint32_t code;    // opcode | CODE_HAS_SB
     uint32_t emask;   // single ops: bit e set = register amplitude e satisfies the register-resident controls
-                      // OPC_LAYER: mask of register bits that get a Hadamard butterfly
+                      // OPC_STAGE: hmask | slotMask << 5 | anyMembers << 10
     uint32_t lmaskSb; // predicate on the sub-block base (tile-local amplitude bits outside the register set)
     uint32_t lvalSb;
     R m[8];           // inline, so that its loads do not wait for the header
@@ -81,6 +92,8 @@ struct alignas(16) DevSweep {
     int scratchBytes; // shared memory behind the program: chunk-row offsets + the double-buffered phase table
     int directIn;  // 1: the first pass reads its sub-blocks straight from HBM; 0: coalesced copy into the smem tile first
     int directOut; // 1: the last pass writes straight to HBM; 0: through the smem tile
+    int nMem;      // thread-level phase members (DevMember records at memOff)
+    int memOff;
     unsigned short slotBeg[MAX_SLOTS + 1]; // slot s multiplies the outer records [slotBeg[s], slotBeg[s+1])
     uint64_t highLow[MAX_HIGH]; // (2^q - 1) for push_apart of the tile base, ascending
     uint64_t highPow[MAX_HIGH]; // 2^q
@@ -266,8 +279,27 @@ __device__ __forceinline__ void app_phase_reg(typename AmpOps<R>::A (&a)[NA], co
     }
 }
 
+template <typename R, int JA, int JB, int NA>
+__device__ __forceinline__ void app_phase_pair(typename AmpOps<R>::A (&a)[NA], const typename AmpOps<R>::Ph& ph)
+{
+#pragma unroll
+    for (int e = 0; e < NA; ++e) {
+        if ((e & (1 << JA)) && (e & (1 << JB))) {
+            a[e] = AmpOps<R>::mulc(a[e], ph);
+        }
+    }
+}
+
+// thread-level phase member of a STAGE group
+template <typename R> struct alignas(16) DevMember {
+    uint64_t omask, oval; // outer predicate, evaluated once per tile (preamble) into the effective (mask, val) table
+    uint32_t lmask, lval; // predicate on the sub-block base (thread bits)
+    R ph[2];
+};
+
 template <typename R, int NA>
-__device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const DevOp<R>& op, uint32_t xsb, const R* __restrict__ tileScale)
+__device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const DevOp<R>& op, uint32_t xsb, const R* __restrict__ tileScale,
+    const DevMember<R>* __restrict__ members, const uint2* __restrict__ eff)
 {
     typedef AmpOps<R> O;
     typedef typename O::A A;
@@ -280,9 +312,6 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
     const uint32_t em = tp ? hd.y : 0U;
 #define SV_J(J) (((1 << (J)) < NA) ? (J) : 0)
 #define SV_CASES(J)                                                                                                    \
-    case K_HAD * 5 + J:                                                                                                \
-        app_had<R, SV_J(J), NA>(a);                                                                                    \
-        break;                                                                                                         \
     case K_XSWAP * 5 + J:                                                                                              \
         app_xswap<R, SV_J(J), NA>(a, em);                                                                              \
         break;                                                                                                         \
@@ -291,43 +320,69 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         break;                                                                                                         \
     case K_GEN_P * 5 + J:                                                                                              \
         app_general<R, SV_J(J), NA, true>(a, m, em);                                                                   \
-        break;                                                                                                         \
-    case K_PHREG1 * 5 + J:                                                                                             \
-        if (tp) {                                                                                                      \
-            app_phase_reg<R, SV_J(J), NA>(a, O::mkph(m[0], m[1]));                                                     \
+        break;
+#define SV_PAIR(K, J)                                                                                                  \
+    case OPC_PH2 + (K) * ((K)-1) / 2 + (J):                                                                            \
+        if (tp && ((1 << (K)) < NA)) {                                                                                 \
+            app_phase_pair<R, SV_J(J), SV_J(K), NA>(a, O::mkph(m[0], m[1]));                                           \
         }                                                                                                              \
         break;
     switch (hd.x & 0xffU) {
-    case OPC_LAYER: {
-        // Hadamard butterflies on several register bits in one dispatch (hd.y = mask of register bits)
-#define SV_LAYER_BIT(J)                                                                                                \
-    if (((1 << (J)) < NA) && ((hd.y >> (J)) & 1U)) {                                                                   \
-        app_had<R, SV_J(J), NA>(a);                                                                                    \
-    }
-        SV_LAYER_BIT(0)
-        SV_LAYER_BIT(1)
-        SV_LAYER_BIT(2)
-        SV_LAYER_BIT(3)
-        SV_LAYER_BIT(4)
-#undef SV_LAYER_BIT
-    } break;
-    case OPC_DIAG: {
-        // per-tile phases on several register bits (hd.y = mask of register bits, hd.z = first table slot); each phase
-        // is the product of the group's members whose outer predicate holds for this tile, 1 if none does
-#define SV_DIAG_BIT(J)                                                                                                 \
-    if (((1 << (J)) < NA) && ((hd.y >> (J)) & 1U)) {                                                                   \
-        const R* tp2 = tileScale + 2U * (hd.z + __popc(hd.y & ((1U << (J)) - 1U)));                                    \
-        const R px = tp2[0], py = tp2[1];                                                                              \
-        if (px != (R)1 || py != (R)0) {                                                                                \
-            app_phase_reg<R, SV_J(J), NA>(a, O::mkph(px, py));                                                         \
+    case OPC_STAGE: {
+        const uint32_t hm = hd.y & 31U, sm = (hd.y >> 5) & 31U;
+        uint32_t slot = hd.z, mk = hd.w;
+        const uint32_t cnts = (hd.y & (1U << 10)) ? *reinterpret_cast<const uint32_t*>(op.m) : 0U;
+        // product of the thread-level members [mk, mk + c) that fire for this thread, times (px, py)
+#define SV_MEMBERS(c)                                                                                                  \
+    for (uint32_t k = 0; k < (c); ++k, ++mk) {                                                                         \
+        const uint2 e = eff[mk];                                                                                       \
+        const R qx = members[mk].ph[0], qy = members[mk].ph[1];                                                        \
+        if ((xsb & e.x) == e.y) {                                                                                      \
+            const R nx = px * qx - py * qy;                                                                            \
+            py = px * qy + py * qx;                                                                                    \
+            px = nx;                                                                                                   \
         }                                                                                                              \
     }
-        SV_DIAG_BIT(0)
-        SV_DIAG_BIT(1)
-        SV_DIAG_BIT(2)
-        SV_DIAG_BIT(3)
-        SV_DIAG_BIT(4)
-#undef SV_DIAG_BIT
+        {
+            const uint32_t c = cnts & 31U;
+            if (c) {
+                R px = (R)1, py = (R)0;
+                SV_MEMBERS(c)
+                if (px != (R)1 || py != (R)0) {
+                    const typename O::Ph ph = O::mkph(px, py);
+#pragma unroll
+                    for (int e = 0; e < NA; ++e) {
+                        a[e] = O::mulc(a[e], ph);
+                    }
+                }
+            }
+        }
+#define SV_STAGE_BIT(J)                                                                                                \
+    if ((1 << (J)) < NA) {                                                                                             \
+        const uint32_t c = (cnts >> (5 * ((J) + 1))) & 31U;                                                            \
+        if (((sm >> (J)) & 1U) | c) {                                                                                  \
+            R px = (R)1, py = (R)0;                                                                                    \
+            if ((sm >> (J)) & 1U) {                                                                                    \
+                px = tileScale[2U * slot];                                                                             \
+                py = tileScale[2U * slot + 1U];                                                                        \
+                ++slot;                                                                                                \
+            }                                                                                                          \
+            SV_MEMBERS(c)                                                                                              \
+            if (px != (R)1 || py != (R)0) {                                                                            \
+                app_phase_reg<R, SV_J(J), NA>(a, O::mkph(px, py));                                                     \
+            }                                                                                                          \
+        }                                                                                                              \
+        if ((hm >> (J)) & 1U) {                                                                                        \
+            app_had<R, SV_J(J), NA>(a);                                                                                \
+        }                                                                                                              \
+    }
+        SV_STAGE_BIT(0)
+        SV_STAGE_BIT(1)
+        SV_STAGE_BIT(2)
+        SV_STAGE_BIT(3)
+        SV_STAGE_BIT(4)
+#undef SV_STAGE_BIT
+#undef SV_MEMBERS
     } break;
     case OPC_SCALE: {
         const typename O::Ph sc = O::mkph(tileScale[0], tileScale[1]);
@@ -341,16 +396,17 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         SV_CASES(2)
         SV_CASES(3)
         SV_CASES(4)
-    case K_PHUNI * 5:
-        if (tp) {
-            const typename O::Ph ph = O::mkph(m[0], m[1]);
-#pragma unroll
-            for (int e = 0; e < NA; ++e) {
-                a[e] = O::mulc(a[e], ph);
-            }
-        }
-        break;
-    case K_PHGEN * 5: {
+        SV_PAIR(1, 0)
+        SV_PAIR(2, 0)
+        SV_PAIR(2, 1)
+        SV_PAIR(3, 0)
+        SV_PAIR(3, 1)
+        SV_PAIR(3, 2)
+        SV_PAIR(4, 0)
+        SV_PAIR(4, 1)
+        SV_PAIR(4, 2)
+        SV_PAIR(4, 3)
+    case OPC_PHGEN: {
         const typename O::Ph ph = O::mkph(m[0], m[1]);
 #pragma unroll
         for (int e = 0; e < NA; ++e) {
@@ -361,6 +417,7 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
     default:
         break;
     }
+#undef SV_PAIR
 #undef SV_CASES
 #undef SV_J
 }
@@ -464,6 +521,11 @@ __global__ void __launch_bounds__(NT, MINB)
     const int nOuter = sw.nOuter;
     const int nPass = sw.nPass;
     const DevOuterPhase<R>* outer = reinterpret_cast<const DevOuterPhase<R>*>(sprog + sw.outerOff);
+    // thread-level phase members of the STAGE ops: static records in the program, per-tile effective (mask, val) pairs
+    // (double-buffered by tile parity like the phase table) behind it
+    const int nMem = sw.nMem;
+    const DevMember<R>* members = reinterpret_cast<const DevMember<R>*>(sprog + sw.memOff);
+    uint2* const effTab = reinterpret_cast<uint2*>(tileTab + 2U * tabStride);
     __syncthreads();
 
     uint32_t par = 0;
@@ -521,6 +583,15 @@ __global__ void __launch_bounds__(NT, MINB)
             }
             tileScale[2 * sl] = (R)fx;
             tileScale[2 * sl + 1] = (R)fy;
+        }
+        {
+            // members whose outer predicate fails on this tile can never match: (mask 0, val 1)
+            uint2* const eff = effTab + par * (uint32_t)nMem;
+            for (int i = tid; i < nMem; i += NT) {
+                const DevMember<R>& mb = members[i];
+                const bool ok = (base & mb.omask) == mb.oval;
+                eff[i] = ok ? make_uint2(mb.lmask, mb.lval) : make_uint2(0U, 1U);
+            }
         }
         if (sw.prefetch && (t + gridDim.x < nTiles) && ((tid & 7) == 0)) {
             // one 128-byte line per 8 chunks: the CTA's next tile streams into L2 under the passes below
@@ -594,7 +665,7 @@ __global__ void __launch_bounds__(NT, MINB)
                     while (m) {
                         const int o = 32 * w + __ffs(m) - 1;
                         m &= m - 1U;
-                        exec_op<R, NA>(a, ops[o], xsb, tileScale);
+                        exec_op<R, NA>(a, ops[o], xsb, tileScale, members, effTab + par * (uint32_t)nMem);
                     }
                 }
                 if (toGlobal) {
@@ -634,6 +705,8 @@ struct HostOp {
 
 static inline uint64_t bitq(int q) { return 1ULL << q; }
 
+static void rewrite_ops(std::vector<HostOp>& ops);
+static int knob_rewrite();
 static void lower_queue(const std::vector<GateOp>& q, std::vector<HostOp>& out)
 {
     out.clear();
@@ -643,6 +716,27 @@ static void lower_queue(const std::vector<GateOp>& q, std::vector<HostOp>& out)
         memset(&h, 0, sizeof(h));
         if (g.kind == 1) { // diagonal: one predicated phase per non-unit diagonal entry
             const bool one0 = (g.m[0] == 1.0 && g.m[1] == 0.0), one3 = (g.m[6] == 1.0 && g.m[7] == 0.0);
+            const double n0 = g.m[0] * g.m[0] + g.m[1] * g.m[1];
+            if (knob_rewrite() && !one0 && n0 > 0.0) {
+                // diag(d0, d3) under controls C  =  [C -> d0] . [C and target=1 -> d3 / d0]: every register-bit predicate the
+                // kernel sees then asks for value 1 (a stage member), and the first factor has one qubit less
+                h.kind = OP_PHASE;
+                h.tq = -1;
+                h.cmask = g.cmask;
+                h.cval = g.cval;
+                h.m[0] = g.m[0];
+                h.m[1] = g.m[1];
+                out.push_back(h);
+                const double qx = (g.m[6] * g.m[0] + g.m[7] * g.m[1]) / n0, qy = (g.m[7] * g.m[0] - g.m[6] * g.m[1]) / n0;
+                if (qx != 1.0 || qy != 0.0) {
+                    h.cmask = g.cmask | bitq(g.target);
+                    h.cval = g.cval | bitq(g.target);
+                    h.m[0] = qx;
+                    h.m[1] = qy;
+                    out.push_back(h);
+                }
+                continue;
+            }
             if (!one0) {
                 h.kind = OP_PHASE;
                 h.tq = -1;
@@ -677,6 +771,223 @@ static void lower_queue(const std::vector<GateOp>& q, std::vector<HostOp>& out)
         }
         out.push_back(h);
     }
+    if (knob_rewrite()) {
+        rewrite_ops(out);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Peephole rewrite of the lowered gate list (r2).  The sweep kernel is issue-bound, not HBM-bound, once a window holds
+// more than a few gates, and the dearest op by far is the conditional register swap of an X-type gate (CNOT: 64 SEL +
+// 32 MOV per 32-amplitude sub-block, and its target has to be a tile qubit).  Diagonal gates are index-only: they ride in
+// any pass on any qubit and are free when their qubits lie outside the tile.  So the list is rewritten to an equivalent one
+// with as few non-diagonal ops as possible:
+//   R1  X-type (any controls) on target b   ->  H_b . Z-type(controls + b) . H_b      (H X H = Z)
+//   R2  adjacent uncontrolled non-diagonal 1-qubit gates on the same qubit are multiplied (H.H = scalar, H.U / U.H / U.U' = one
+//       general gate), so the Hadamards of R1 cancel against, or are absorbed by, the neighbouring single-qubit gates
+//   R3  a general 1-qubit gate absorbs adjacent single-qubit phases on its qubit; equal-predicate phases are multiplied
+// "Adjacent" = no op in between touches the qubit at all (so the two ops may be brought together without reordering
+// anything that does not commute).  Products are taken in double.  The product of the whole list is unchanged.
+// BASELINE's H/T/CNOT circuit turns into Hadamards + T/CZ phases only; quantum-volume layers into one general gate per
+// qubit and layer + CZ phases.
+// ---------------------------------------------------------------------------------------------------------
+struct M22 {
+    double m[8];
+};
+static inline M22 m22_mul(const double* a, const double* b) // a . b  (b acts first)
+{
+    M22 r;
+    for (int i = 0; i < 2; ++i) {
+        for (int j = 0; j < 2; ++j) {
+            double re = 0, im = 0;
+            for (int k = 0; k < 2; ++k) {
+                const double ax = a[2 * (2 * i + k)], ay = a[2 * (2 * i + k) + 1];
+                const double bx = b[2 * (2 * k + j)], by = b[2 * (2 * k + j) + 1];
+                re += ax * bx - ay * by;
+                im += ax * by + ay * bx;
+            }
+            r.m[2 * (2 * i + j)] = re;
+            r.m[2 * (2 * i + j) + 1] = im;
+        }
+    }
+    return r;
+}
+static inline bool is_had_form(const double* m)
+{
+    return m[1] == 0.0 && m[3] == 0.0 && m[5] == 0.0 && m[7] == 0.0 && m[0] > 0.0 && m[0] == m[2] && m[0] == m[4] && m[6] == -m[0];
+}
+static int knob_rewrite();
+
+static void rewrite_ops(std::vector<HostOp>& ops)
+{
+    std::vector<HostOp> out;
+    std::vector<char> alive;
+    out.reserve(ops.size() * 3);
+    alive.reserve(ops.size() * 3);
+    std::vector<int> hist[64]; // per qubit: indices (into out) of the live ops that touch it, ascending
+    double gx = 1.0, gy = 0.0;  // global scalar (commutes with everything), emitted once at the end
+    auto touches = [](const HostOp& h) { return h.cmask | (h.tq >= 0 ? bitq(h.tq) : 0ULL); };
+    auto push = [&](const HostOp& h) {
+        const int idx = (int)out.size();
+        out.push_back(h);
+        alive.push_back(1);
+        for (uint64_t m = touches(h); m; m &= m - 1U) {
+            hist[__builtin_ctzll(m)].push_back(idx);
+        }
+    };
+    auto kill_last_on = [&](int b) { // the last live op touching b touches only b
+        alive[(size_t)hist[b].back()] = 0;
+        hist[b].pop_back();
+    };
+    auto is_u1 = [](const HostOp& h) { return (h.kind == OP_HAD || h.kind == OP_GENERAL || h.kind == OP_XSWAP) && !h.cmask; };
+    auto emit_phase1 = [&](int b, int val, double px, double py) {
+        if (px == 1.0 && py == 0.0) {
+            return;
+        }
+        if (!hist[b].empty()) {
+            HostOp& p = out[(size_t)hist[b].back()];
+            if (p.kind == OP_GENERAL && !p.cmask && p.tq == b) { // R3: row scaling of the general gate
+                for (int c = 0; c < 2; ++c) {
+                    double* e = &p.m[2 * (2 * val + c)];
+                    const double nx = e[0] * px - e[1] * py;
+                    e[1] = e[0] * py + e[1] * px;
+                    e[0] = nx;
+                }
+                return;
+            }
+            if (p.kind == OP_PHASE && p.cmask == bitq(b) && p.cval == (val ? bitq(b) : 0ULL)) {
+                const double nx = p.m[0] * px - p.m[1] * py;
+                p.m[1] = p.m[0] * py + p.m[1] * px;
+                p.m[0] = nx;
+                return;
+            }
+        }
+        HostOp h;
+        memset(&h, 0, sizeof(h));
+        h.kind = OP_PHASE;
+        h.tq = -1;
+        h.cmask = bitq(b);
+        h.cval = val ? bitq(b) : 0ULL;
+        h.m[0] = px;
+        h.m[1] = py;
+        push(h);
+    };
+    // emit an uncontrolled 1-qubit matrix on b, merging with what is already there
+    auto emit_u1 = [&](int b, const double* min) {
+        M22 cur;
+        memcpy(cur.m, min, sizeof(cur.m));
+        auto is_x_form = [](const double* m) {
+            return m[0] == 0 && m[1] == 0 && m[6] == 0 && m[7] == 0 && m[2] == 1.0 && m[3] == 0 && m[4] == 1.0 && m[5] == 0;
+        };
+        bool general = !is_had_form(cur.m) && !is_x_form(cur.m);
+        for (;;) {
+            if (hist[b].empty()) {
+                break;
+            }
+            const HostOp& p = out[(size_t)hist[b].back()];
+            if (is_u1(p) && p.tq == b) { // R2
+                if (p.kind == OP_XSWAP && is_had_form(cur.m) && !general) {
+                    // X then H  =  H then Z: keep the butterfly cheap instead of multiplying into a general gate
+                    out[(size_t)hist[b].back()].kind = OP_HAD;
+                    memcpy(out[(size_t)hist[b].back()].m, cur.m, sizeof(cur.m));
+                    emit_phase1(b, 1, -1.0, 0.0);
+                    return;
+                }
+                cur = m22_mul(cur.m, p.m);
+                kill_last_on(b);
+                general = !is_had_form(cur.m) && !is_x_form(cur.m);
+                continue;
+            }
+            if (general && p.kind == OP_PHASE && p.cmask == bitq(b)) { // R3: column scaling
+                const int val = p.cval ? 1 : 0;
+                for (int r = 0; r < 2; ++r) {
+                    double* e = &cur.m[2 * (2 * r + val)];
+                    const double nx = e[0] * p.m[0] - e[1] * p.m[1];
+                    e[1] = e[0] * p.m[1] + e[1] * p.m[0];
+                    e[0] = nx;
+                }
+                kill_last_on(b);
+                continue;
+            }
+            break;
+        }
+        const double* m = cur.m;
+        const bool z1 = m[2] == 0 && m[3] == 0, z2 = m[4] == 0 && m[5] == 0;
+        if (z1 && z2) { // diagonal
+            if (m[0] == m[6] && m[1] == m[7]) {
+                const double nx = gx * m[0] - gy * m[1];
+                gy = gx * m[1] + gy * m[0];
+                gx = nx;
+            } else {
+                emit_phase1(b, 0, m[0], m[1]);
+                emit_phase1(b, 1, m[6], m[7]);
+            }
+            return;
+        }
+        HostOp h;
+        memset(&h, 0, sizeof(h));
+        h.tq = b;
+        memcpy(h.m, m, sizeof(h.m));
+        const bool z0 = m[0] == 0 && m[1] == 0, z3 = m[6] == 0 && m[7] == 0;
+        if (is_had_form(m)) {
+            h.kind = OP_HAD;
+        } else if (z0 && z3 && m[2] == 1.0 && m[3] == 0.0 && m[4] == 1.0 && m[5] == 0.0) {
+            h.kind = OP_XSWAP; // a product that happens to be X: left as a swap (no second rewrite)
+        } else {
+            h.kind = OP_GENERAL;
+        }
+        push(h);
+    };
+    static const double HS = 0.70710678118654752440;
+    static const double HM[8] = { HS, 0, HS, 0, HS, 0, -HS, 0 };
+    for (const HostOp& op : ops) {
+        if (op.kind == OP_XSWAP && !op.cmask && (hist[op.tq].empty() || out[(size_t)hist[op.tq].back()].kind != OP_HAD ||
+                                                    out[(size_t)hist[op.tq].back()].tq != op.tq)) {
+            emit_u1(op.tq, op.m); // bare X next to a general gate (or to nothing): multiply / leave as a swap
+        } else if (op.kind == OP_XSWAP) { // R1
+            emit_u1(op.tq, HM);
+            HostOp z;
+            memset(&z, 0, sizeof(z));
+            z.kind = OP_PHASE;
+            z.tq = -1;
+            z.cmask = op.cmask | bitq(op.tq);
+            z.cval = op.cval | bitq(op.tq);
+            z.m[0] = -1.0;
+            if (!op.cmask) {
+                emit_phase1(op.tq, 1, -1.0, 0.0);
+            } else {
+                push(z);
+            }
+            emit_u1(op.tq, HM);
+        } else if (is_u1(op)) {
+            emit_u1(op.tq, op.m);
+        } else if (op.kind == OP_PHASE && op.cmask && !(op.cmask & (op.cmask - 1U))) {
+            emit_phase1(__builtin_ctzll(op.cmask), op.cval ? 1 : 0, op.m[0], op.m[1]);
+        } else if (op.kind == OP_PHASE && !op.cmask) {
+            const double nx = gx * op.m[0] - gy * op.m[1];
+            gy = gx * op.m[1] + gy * op.m[0];
+            gx = nx;
+        } else {
+            push(op);
+        }
+    }
+    std::vector<HostOp> res;
+    res.reserve(out.size() + 1);
+    for (size_t i = 0; i < out.size(); ++i) {
+        if (alive[i]) {
+            res.push_back(out[i]);
+        }
+    }
+    if (gx != 1.0 || gy != 0.0) {
+        HostOp h;
+        memset(&h, 0, sizeof(h));
+        h.kind = OP_PHASE;
+        h.tq = -1;
+        h.m[0] = gx;
+        h.m[1] = gy;
+        res.push_back(h);
+    }
+    ops.swap(res);
 }
 
 struct TileCfg {
@@ -982,7 +1293,8 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
     memset(&ds, 0, sizeof(ds));
     std::vector<DevOp<R>> dops;
     std::vector<DevOuterPhase<R>> outerList;
-    std::vector<std::vector<DevOuterPhase<R>>> slotMembers; // table slots 1.. (register-bit phases of the DIAG ops)
+    std::vector<std::vector<DevOuterPhase<R>>> slotMembers; // table slots 1.. (register-bit phases of the STAGE ops)
+    std::vector<DevMember<R>> memberList;                   // thread-level members of the STAGE ops
     ds.nHigh = (int)sp.highQ.size();
     ds.lowAmpBits = cfg.L;
     ds.kc = kc;
@@ -1099,86 +1411,74 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                 }
             }
         };
-        // ---- bundle state ----
-        struct LayerMember {
-            int kind; // 1 HAD, 2 GEN
-            double m[8];
-        };
-        LayerMember layer[5];
-        bool layerUsed[5] = { false, false, false, false, false };
-        int layerCount = 0;
-        uint64_t ndq = 0; // qubits with a (non-diagonal) layer member in the open bundle
-        auto close_bundle = [&]() {
-            if (layerCount) {
-                DevOp<R> d;
-                memset(&d, 0, sizeof(d));
-                uint32_t kinds = 0;
-                for (int b = 0; b < JRN; ++b) {
-                    if (layerUsed[b]) {
-                        kinds |= 1U << b;
-                    }
-                }
-                d.emask = kinds;
-                d.code = OPC_LAYER;
-                dops.push_back(d);
+        // ---- open STAGE: per register bit J [phase][Hadamard], plus thread-uniform phases (group 0).  Its members are
+        // diagonal except the butterflies, so a phase on bit J may join until the stage holds a butterfly on J; the stage is
+        // emitted (closed) before the first single op that does not commute with its contents, or at the end of the pass.
+        struct Stage {
+            bool h[5];
+            std::vector<DevOuterPhase<R>> slot[5]; // outer-only members of bit J's phase (per-tile product -> one table slot)
+            std::vector<DevMember<R>> thr[6];      // group 0 = thread-uniform, 1 + J = bit J
+            bool any;
+        } st;
+        auto stage_reset = [&]() {
+            for (int b = 0; b < 5; ++b) {
+                st.h[b] = false;
+                st.slot[b].clear();
             }
-            layerCount = 0;
-            for (bool& u : layerUsed) {
-                u = false;
+            for (int g = 0; g < 6; ++g) {
+                st.thr[g].clear();
             }
-            ndq = 0;
+            st.any = false;
         };
-        // ---- open DIAG group: phases whose predicate is (outer qubits) AND (one register bit), per register bit.
-        // Members are diagonal, so they commute with everything except a non-diagonal op on their register bit;
-        // the group is emitted just before the first such op (or at the end of the pass).
-        std::vector<DevOuterPhase<R>> diag[5];
-        uint32_t diagBits = 0;
-        auto close_diag = [&]() {
-            if (!diagBits) {
+        stage_reset();
+        auto stage_slots = [&]() {
+            int n = 0;
+            for (int b = 0; b < 5; ++b) {
+                n += st.slot[b].empty() ? 0 : 1;
+            }
+            return n;
+        };
+        auto stage_members = [&]() {
+            size_t n = 0;
+            for (int g = 0; g < 6; ++g) {
+                n += st.thr[g].size();
+            }
+            return n;
+        };
+        auto close_stage = [&]() {
+            if (!st.any) {
                 return;
             }
             DevOp<R> d;
             memset(&d, 0, sizeof(d));
-            d.code = OPC_DIAG;
-            d.emask = diagBits;
-            d.lmaskSb = (uint32_t)slotMembers.size() + 1U; // first table slot of this group
+            uint32_t hm = 0, sm = 0, cnts = 0;
+            d.lmaskSb = (uint32_t)slotMembers.size() + 1U; // first table slot of this stage
+            d.lvalSb = (uint32_t)memberList.size();        // first thread-level member
+            for (int g = 0; g < 6; ++g) {
+                cnts |= (uint32_t)st.thr[g].size() << (5 * g);
+                memberList.insert(memberList.end(), st.thr[g].begin(), st.thr[g].end());
+            }
             for (int b = 0; b < JRN; ++b) {
-                if (diagBits & (1U << b)) {
-                    slotMembers.push_back(diag[b]);
-                    diag[b].clear();
+                if (st.h[b]) {
+                    hm |= 1U << b;
+                }
+                if (!st.slot[b].empty()) {
+                    sm |= 1U << b;
+                    slotMembers.push_back(st.slot[b]);
                 }
             }
+            d.code = OPC_STAGE;
+            d.emask = hm | (sm << 5) | (cnts ? (1U << 10) : 0U);
+            memcpy(d.m, &cnts, sizeof(cnts));
             dops.push_back(d);
-            diagBits = 0;
+            stage_reset();
         };
         dp.opBegin = (int)dops.size();
         for (const HostOp& hop : pp.ops) {
             uint32_t lmask, lval;
             local_pred(hop, lmask, lval);
             const uint32_t lmr = lmask & regAmpMask, lvr = lval & regAmpMask;
-            if ((cfg.bundle & 2) && hop.kind == OP_PHASE && !(lmask & ~regAmpMask) && __builtin_popcount(lmr) == 1 && lvr == lmr &&
-                slotMembers.size() + (size_t)__builtin_popcount(diagBits) + 2U < (size_t)MAX_SLOTS) {
-                const int jr = reg_index(__builtin_ctz(lmr));
-                if (layerUsed[jr]) {
-                    close_bundle(); // the open layer has a butterfly on this bit: it must run first
-                }
-                DevOuterPhase<R> mem;
-                memset(&mem, 0, sizeof(mem));
-                mem.omask = hop.cmask & ~tileMask;
-                mem.oval = hop.cval & ~tileMask;
-                mem.ph[0] = (R)hop.m[0];
-                mem.ph[1] = (R)hop.m[1];
-                diag[jr].push_back(mem);
-                diagBits |= 1U << jr;
-                continue;
-            }
-            if (hop.kind != OP_PHASE && diagBits) {
-                // non-diagonal op: pending phases on its target register bit have to be applied before it
-                const int jt = reg_index(tile_bit(cfg, sp.highQ, hop.tq));
-                if (diagBits & (1U << jt)) {
-                    close_diag();
-                }
-            }
+            const int nreg = __builtin_popcount(lmr);
             if (hop.kind == OP_PHASE) {
                 if (!(hop.cmask & tileMask) && outerList.size() < (size_t)MAX_OUTER) {
                     // every qubit of the predicate is outside the tile: uniform per tile, commutes with the whole sweep
@@ -1191,29 +1491,76 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                     outerList.push_back(op);
                     continue;
                 }
-            } else if ((cfg.bundle & 1) && !hop.cmask && hop.kind == OP_HAD) {
-                // uncontrolled non-diagonal 1-qubit gate: layer member
-                const int jr = reg_index(tile_bit(cfg, sp.highQ, hop.tq));
-                if ((bitq(hop.tq) & ndq) || layerUsed[jr]) {
-                    close_bundle();
+                if ((cfg.bundle & 2) && nreg <= 1 && lvr == lmr) {
+                    // stage member: at most one register bit (value 1); thread bits and outer qubits anywhere
+                    const int jr = nreg ? reg_index(__builtin_ctz(lmr)) : -1;
+                    const bool threadPart = (lmask & ~regAmpMask) != 0;
+                    const bool asSlot = nreg == 1 && !threadPart;
+                    if (jr >= 0 && st.h[jr]) {
+                        close_stage(); // the stage has a butterfly on this bit: the phase comes after it
+                    }
+                    auto fits = [&]() {
+                        return asSlot ? (slotMembers.size() + (size_t)stage_slots() + (st.slot[jr].empty() ? 1U : 0U) + 2U < (size_t)MAX_SLOTS)
+                                      : (st.thr[jr + 1].size() < 31U && memberList.size() + stage_members() + 1U < (size_t)MAX_MEMBERS);
+                    };
+                    if (!fits()) {
+                        close_stage();
+                    }
+                    if (fits()) {
+                        if (asSlot) {
+                            DevOuterPhase<R> mem;
+                            memset(&mem, 0, sizeof(mem));
+                            mem.omask = hop.cmask & ~tileMask;
+                            mem.oval = hop.cval & ~tileMask;
+                            mem.ph[0] = (R)hop.m[0];
+                            mem.ph[1] = (R)hop.m[1];
+                            st.slot[jr].push_back(mem);
+                        } else {
+                            DevMember<R> mem;
+                            memset(&mem, 0, sizeof(mem));
+                            mem.omask = hop.cmask & ~tileMask;
+                            mem.oval = hop.cval & ~tileMask;
+                            mem.lmask = lmask & ~regAmpMask;
+                            mem.lval = lval & ~regAmpMask;
+                            mem.ph[0] = (R)hop.m[0];
+                            mem.ph[1] = (R)hop.m[1];
+                            st.thr[jr + 1].push_back(mem);
+                        }
+                        st.any = true;
+                        if (!(cfg.bundle & 4)) {
+                            close_stage();
+                        }
+                        continue;
+                    }
+                    // tables full: falls through to a single op
                 }
-                layer[jr].kind = (hop.kind == OP_HAD) ? 1 : 2;
-                memcpy(layer[jr].m, hop.m, sizeof(hop.m));
-                layerUsed[jr] = true;
-                ++layerCount;
-                ndq |= bitq(hop.tq);
-                if (hop.kind == OP_HAD) {
-                    scale *= hop.m[0];
+            } else if ((cfg.bundle & 1) && !hop.cmask && hop.kind == OP_HAD) {
+                // uncontrolled Hadamard: butterfly of the stage (after the stage's phase on that bit)
+                const int jr = reg_index(tile_bit(cfg, sp.highQ, hop.tq));
+                if (st.h[jr]) {
+                    close_stage();
+                }
+                st.h[jr] = true;
+                st.any = true;
+                scale *= hop.m[0];
+                if (!(cfg.bundle & 4)) {
+                    close_stage();
                 }
                 continue;
             }
-            // everything else is a single op.  The open layer is emitted later than this op, so it has to be closed first
-            // if the op touches one of its qubits in any way (target, control or phase); with the conservative setting
-            // (bundle bit 2 clear) every single op closes it.
+            // everything else is a single op, emitted at once: the open stage has to be closed first if the op does not
+            // commute with its contents (target bit: any member; register-bit controls / phased register bits: a butterfly)
             {
-                const uint64_t touch = hop.cmask | (hop.tq >= 0 ? bitq(hop.tq) : 0);
-                if (!(cfg.bundle & 4) || (touch & ndq)) {
-                    close_bundle();
+                bool conflict = !(cfg.bundle & 4);
+                if (hop.tq >= 0) {
+                    const int jt = reg_index(tile_bit(cfg, sp.highQ, hop.tq));
+                    conflict = conflict || st.h[jt] || !st.slot[jt].empty() || !st.thr[jt + 1].empty();
+                }
+                for (uint32_t m = lmr; m; m &= m - 1U) {
+                    conflict = conflict || st.h[reg_index(__builtin_ctz(m))];
+                }
+                if (conflict) {
+                    close_stage();
                 }
             }
             DevOp<R> d;
@@ -1233,33 +1580,34 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
             for (int k = 0; k < 8; ++k) {
                 d.m[k] = (R)hop.m[k];
             }
-            uint32_t kind = 0, jr = 0;
+            uint32_t code = 0;
             if (hop.kind == OP_PHASE) {
-                const int nreg = __builtin_popcount(lmr);
-                if (nreg == 0) {
-                    kind = K_PHUNI;
-                } else if (nreg == 1 && lvr == lmr) {
-                    kind = K_PHREG1;
-                    jr = (uint32_t)reg_index(__builtin_ctz(lmr));
+                if (nreg == 2 && lvr == lmr) {
+                    const int j = reg_index(__builtin_ctz(lmr)), k = reg_index(31 - __builtin_clz(lmr));
+                    code = OPC_PH2 + (uint32_t)(k * (k - 1) / 2 + j);
                 } else {
-                    kind = K_PHGEN;
+                    code = OPC_PHGEN;
                 }
             } else {
-                jr = (uint32_t)reg_index(tile_bit(cfg, sp.highQ, hop.tq));
+                const uint32_t jr = (uint32_t)reg_index(tile_bit(cfg, sp.highQ, hop.tq));
                 if (hop.kind == OP_HAD) {
-                    kind = K_HAD;
+                    // only with stage bundling switched off for butterflies: a stage of its own
+                    close_stage();
+                    st.h[jr] = true;
+                    st.any = true;
                     scale *= hop.m[0];
+                    close_stage();
+                    continue;
                 } else if (hop.kind == OP_XSWAP) {
-                    kind = K_XSWAP;
+                    code = K_XSWAP * 5U + jr;
                 } else {
-                    kind = uncond ? K_GEN_U : K_GEN_P;
+                    code = (uncond ? K_GEN_U : K_GEN_P) * 5U + jr;
                 }
             }
-            d.code = (kind * 5U + jr) | (d.lmaskSb ? CODE_HAS_SB : 0U);
+            d.code = code | (d.lmaskSb ? CODE_HAS_SB : 0U);
             dops.push_back(d);
         }
-        close_bundle();
-        close_diag();
+        close_stage();
         if (p == ds.nPass - 1 && (scale != 1.0 || !outerList.empty())) {
             DevOp<R> d;
             memset(&d, 0, sizeof(d));
@@ -1285,31 +1633,40 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
     }
     ds.scale = scale;
     if (getenv("B200SV_FUSED_DEBUG")) {
-        static const char* names[] = { "HAD", "XSWAP", "GEN_U", "GEN_P", "PHREG1", "PHUNI", "PHGEN" };
+        static const char* names[] = { "XSWAP", "GEN_U", "GEN_P" };
         for (int p = 0; p < ds.nPass; ++p) {
             fprintf(stderr, "  pass %d:", p);
             for (int o = ds.pass[p].opBegin; o < ds.pass[p].opEnd; ++o) {
                 const uint32_t c = dops[o].code & 0xffU;
-                if (c == OPC_LAYER) {
-                    fprintf(stderr, " LAYER(%x)", dops[o].emask);
-                } else if (c == OPC_SCALE) {
-                    fprintf(stderr, " SCALE");
-                } else if (c == OPC_DIAG) {
-                    int nm = 0;
+                const char* sfx = (dops[o].code & CODE_HAS_SB) ? "s" : "";
+                const char* ofx = dops[o].omask ? "o" : "";
+                if (c == OPC_STAGE) {
+                    uint32_t cnts = 0;
+                    memcpy(&cnts, dops[o].m, sizeof(cnts));
+                    int nm = 0, nsl = 0;
+                    for (int g = 0; g < 6; ++g) {
+                        nm += (int)((cnts >> (5 * g)) & 31U);
+                    }
                     for (int b = 0, sl = (int)dops[o].lmaskSb - 1; b < 5; ++b) {
-                        if (dops[o].emask & (1U << b)) {
-                            nm += (int)slotMembers[sl++].size();
+                        if ((dops[o].emask >> 5) & (1U << b)) {
+                            nsl += (int)slotMembers[sl++].size();
                         }
                     }
-                    fprintf(stderr, " DIAG(%x:%d)", dops[o].emask, nm);
+                    fprintf(stderr, " STAGE(h%x,s%x:%d,t%d)", dops[o].emask & 31U, (dops[o].emask >> 5) & 31U, nsl, nm);
+                } else if (c == OPC_SCALE) {
+                    fprintf(stderr, " SCALE");
+                } else if (c == OPC_PHGEN) {
+                    fprintf(stderr, " PHGEN%s%s", sfx, ofx);
+                } else if (c >= OPC_PH2) {
+                    fprintf(stderr, " PH2.%u%s%s", c - OPC_PH2, sfx, ofx);
                 } else {
-                    fprintf(stderr, " %s.%u%s%s", names[c / 5U], c % 5U, (dops[o].code & CODE_HAS_SB) ? "s" : "", dops[o].omask ? "o" : "");
+                    fprintf(stderr, " %s.%u%s%s", names[c / 5U], c % 5U, sfx, ofx);
                 }
             }
             fprintf(stderr, "\n");
         }
-        fprintf(stderr, "  sweep: %d ops, %d outer phases, directIn %d, directOut %d\n", (int)dops.size(), (int)outerList.size(),
-            ds.directIn, ds.directOut);
+        fprintf(stderr, "  sweep: %d ops, %d outer phases, %d thread members, directIn %d, directOut %d\n", (int)dops.size(),
+            (int)outerList.size(), (int)memberList.size(), ds.directIn, ds.directOut);
     }
     ds.prefetch = knob_prefetch();
     ds.hasScale = (scale != 1.0 || !outerList.empty()) ? 1 : 0;
@@ -1320,8 +1677,10 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
     {
         const int lcb = cfg.L - cfg.apcLog;
         const size_t rows = (size_t)1 << (kc > lcb ? kc - lcb : 0);
-        ds.scratchBytes = (int)((rows * 8U + (size_t)4 * (size_t)ds.nSlots * sizeof(R) + 15U) & ~(size_t)15U);
+        ds.scratchBytes =
+            (int)((rows * 8U + (size_t)4 * (size_t)ds.nSlots * sizeof(R) + (size_t)16 * memberList.size() + 15U) & ~(size_t)15U);
     }
+    ds.nMem = (int)memberList.size();
     ds.slotBeg[0] = 0;
     ds.slotBeg[1] = (unsigned short)outerList.size();
     for (size_t k = 0; k < slotMembers.size(); ++k) {
@@ -1330,9 +1689,11 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
     }
     const size_t opsBytes = ((dops.size() * sizeof(DevOp<R>)) + 15U) & ~(size_t)15U;
     const size_t outerBytes = ((outerList.size() * sizeof(DevOuterPhase<R>)) + 15U) & ~(size_t)15U;
+    const size_t memBytes = memberList.size() * sizeof(DevMember<R>); // multiple of 16
     ds.outerOff = (int)(sizeof(DevSweep) + opsBytes);
+    ds.memOff = (int)(sizeof(DevSweep) + opsBytes + outerBytes);
     const size_t start = buf.size();
-    size_t bytes = ((sizeof(DevSweep) + opsBytes + outerBytes) + 15U) & ~(size_t)15U;
+    size_t bytes = ((sizeof(DevSweep) + opsBytes + outerBytes + memBytes) + 15U) & ~(size_t)15U;
     if (scratchOut) {
         *scratchOut = (size_t)ds.scratchBytes;
     }
@@ -1347,6 +1708,9 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
     }
     if (!outerList.empty()) {
         memcpy(buf.data() + start + ds.outerOff, outerList.data(), outerList.size() * sizeof(DevOuterPhase<R>));
+    }
+    if (!memberList.empty()) {
+        memcpy(buf.data() + start + ds.memOff, memberList.data(), memBytes);
     }
     return bytes;
 }
@@ -1529,6 +1893,14 @@ static int knob_plan_search()
     return v;
 }
 static int knob_direct_low() { return knobs().dlow; }
+static int knob_rewrite()
+{
+    static const int v = [] {
+        const char* e = getenv("B200SV_REWRITE");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
 constexpr int FUSED_KC = 12;
 constexpr int FUSED_NT = 256;
 
@@ -1630,7 +2002,8 @@ template <typename R> struct EmuC {
 template <typename R> static inline EmuC<R> emu_mul(EmuC<R> a, R px, R py) { return EmuC<R>{ a.x * px - a.y * py, a.x * py + a.y * px }; }
 
 template <typename R>
-static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xsb, const R* tileScale, int NA)
+static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xsb, const R* tileScale, int NA,
+    const DevMember<R>* members, const uint2* eff)
 {
     const uint32_t code = op.code, emask = op.emask, lmaskSb = op.lmaskSb, lvalSb = op.lvalSb;
     bool tp = true;
@@ -1655,22 +2028,45 @@ static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xs
             }
         }
     };
-    if (c == OPC_LAYER) {
-        for (int J = 0; (1 << J) < NA; ++J) {
-            if ((emask >> J) & 1U) {
-                had(J);
+    if (c == OPC_STAGE) {
+        const uint32_t hm = emask & 31U, sm = (emask >> 5) & 31U;
+        uint32_t slot = lmaskSb, mk = lvalSb, cnts = 0;
+        if (emask & (1U << 10)) {
+            memcpy(&cnts, op.m, sizeof(cnts));
+        }
+        auto run_members = [&](uint32_t cN, R& px, R& py) {
+            for (uint32_t k = 0; k < cN; ++k, ++mk) {
+                if ((xsb & eff[mk].x) == eff[mk].y) {
+                    const R qx = members[mk].ph[0], qy = members[mk].ph[1];
+                    const R nx = px * qx - py * qy;
+                    py = px * qy + py * qx;
+                    px = nx;
+                }
+            }
+        };
+        {
+            R px = (R)1, py = (R)0;
+            run_members(cnts & 31U, px, py);
+            if (px != (R)1 || py != (R)0) {
+                for (int e = 0; e < NA; ++e) {
+                    a[e] = emu_mul(a[e], px, py);
+                }
             }
         }
-        return;
-    }
-    if (c == OPC_DIAG) {
         for (int J = 0; (1 << J) < NA; ++J) {
-            if ((emask >> J) & 1U) {
-                const uint32_t slot = lmaskSb + (uint32_t)__builtin_popcount(emask & ((1U << J) - 1U));
-                const R px = tileScale[2 * slot], py = tileScale[2 * slot + 1];
-                if (px != (R)1 || py != (R)0) {
-                    phase_reg(J, px, py);
-                }
+            const uint32_t cN = (cnts >> (5 * (J + 1))) & 31U;
+            R px = (R)1, py = (R)0;
+            if ((sm >> J) & 1U) {
+                px = tileScale[2 * slot];
+                py = tileScale[2 * slot + 1];
+                ++slot;
+            }
+            run_members(cN, px, py);
+            if (px != (R)1 || py != (R)0) {
+                phase_reg(J, px, py);
+            }
+            if ((hm >> J) & 1U) {
+                had(J);
             }
         }
         return;
@@ -1681,13 +2077,33 @@ static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xs
         }
         return;
     }
+    if (c == OPC_PHGEN) {
+        for (int e = 0; e < NA; ++e) {
+            if ((em >> e) & 1U) {
+                a[e] = emu_mul(a[e], op.m[0], op.m[1]);
+            }
+        }
+        return;
+    }
+    if (c >= OPC_PH2) {
+        int k = 1;
+        while ((k + 1) * k / 2 <= (int)(c - OPC_PH2)) {
+            ++k;
+        }
+        const int j = (int)(c - OPC_PH2) - k * (k - 1) / 2;
+        if (tp) {
+            for (int e = 0; e < NA; ++e) {
+                if ((e & (1 << j)) && (e & (1 << k))) {
+                    a[e] = emu_mul(a[e], op.m[0], op.m[1]);
+                }
+            }
+        }
+        return;
+    }
     const uint32_t kind = c / 5U;
     const int J = (int)(c % 5U);
     const R* m = op.m;
     switch (kind) {
-    case K_HAD:
-        had(J);
-        break;
     case K_XSWAP:
         for (int e = 0; e < NA; ++e) {
             if (!(e & (1 << J)) && ((em >> e) & 1U)) {
@@ -1704,25 +2120,6 @@ static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xs
                 const EmuC<R> x2 = emu_mul(x, m[4], m[5]), y3 = emu_mul(y, m[6], m[7]);
                 a[e] = EmuC<R>{ x0.x + y1.x, x0.y + y1.y };
                 a[e | (1 << J)] = EmuC<R>{ x2.x + y3.x, x2.y + y3.y };
-            }
-        }
-        break;
-    case K_PHREG1:
-        if (tp) {
-            phase_reg(J, m[0], m[1]);
-        }
-        break;
-    case K_PHUNI:
-        if (tp) {
-            for (int e = 0; e < NA; ++e) {
-                a[e] = emu_mul(a[e], m[0], m[1]);
-            }
-        }
-        break;
-    case K_PHGEN:
-        for (int e = 0; e < NA; ++e) {
-            if ((em >> e) & 1U) {
-                a[e] = emu_mul(a[e], m[0], m[1]);
             }
         }
         break;
@@ -1757,6 +2154,8 @@ template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<
     std::vector<EmuC<R>> tile((size_t)nChunk * APC); // indexed by swizzled chunk slot
     std::vector<R> tab((size_t)2 * std::max(1, sw.nSlots));
     std::vector<EmuC<R>> a((size_t)NA);
+    const DevMember<R>* members = reinterpret_cast<const DevMember<R>*>(prog + sw.memOff);
+    std::vector<uint2> eff((size_t)std::max(1, sw.nMem));
     for (uint64_t t = 0; t < nTiles; ++t) {
         uint64_t base = t << sw.lowAmpBits;
         for (int h = 0; h < sw.nHigh; ++h) {
@@ -1793,6 +2192,10 @@ template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<
             tab[2 * sl] = (R)fx;
             tab[2 * sl + 1] = (R)fy;
         }
+        for (int i = 0; i < sw.nMem; ++i) {
+            const bool ok = (base & members[i].omask) == members[i].oval;
+            eff[(size_t)i] = ok ? make_uint2(members[i].lmask, members[i].lval) : make_uint2(0U, 1U);
+        }
         if (!sw.directIn) {
             for (uint32_t c = 0; c < nChunk; ++c) {
                 for (int w = 0; w < APC; ++w) {
@@ -1825,7 +2228,7 @@ template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<
                     const uint32_t xsb = sbc * (uint32_t)APC;
                     for (int o = ps.opBegin; o < ps.opEnd; ++o) {
                         if (act[o]) {
-                            emu_exec_op<R>(a, ops[o], xsb, tab.data(), NA);
+                            emu_exec_op<R>(a, ops[o], xsb, tab.data(), NA, members, eff.data());
                         }
                     }
                     for (int e = 0; e < NCH; ++e) {

@@ -151,8 +151,9 @@ int main(int argc, char** argv)
     std::map<int, QInterfacePtr> regs;
     std::vector<std::string> results;
     char buf[256];
-    size_t gateCount = 0;
+    size_t gateCount = 0, totalGates = 0;
     double seconds = 0;
+    std::vector<std::pair<size_t, double>> segments; // (gates, seconds) of every TIC..TOC region
     auto t0 = std::chrono::high_resolution_clock::now();
     bool timing = false;
 
@@ -187,7 +188,10 @@ int main(int argc, char** argv)
             for (auto& kv : regs) {
                 kv.second->Finish();
             }
-            seconds += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+            const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+            seconds += dt;
+            totalGates += gateCount;
+            segments.push_back(std::make_pair(gateCount, dt));
             timing = false;
             continue;
         }
@@ -536,7 +540,10 @@ int main(int argc, char** argv)
         for (auto& kv : regs) {
             kv.second->Finish();
         }
-        seconds += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+        const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+        seconds += dt;
+        totalGates += gateCount;
+        segments.push_back(std::make_pair(gateCount, dt));
     }
 
     if (!resultsFile.empty()) {
@@ -558,8 +565,16 @@ int main(int argc, char** argv)
         }
     }
     if (doTime) {
-        printf("{\"ops\": %zu, \"seconds\": %.6f, \"threads\": %u, \"fp_bits\": %d, \"engine\": \"%s\"}\n", gateCount, seconds,
-            regs.empty() ? 0U : regs.begin()->second->GetConcurrencyLevel(), (int)(8 * sizeof(real1)), g_engine.c_str());
+        std::string seg = "[";
+        for (size_t i = 0; i < segments.size(); ++i) {
+            char b[64];
+            snprintf(b, sizeof(b), "%s[%zu, %.6f]", i ? ", " : "", segments[i].first, segments[i].second);
+            seg += b;
+        }
+        seg += "]";
+        printf("{\"ops\": %zu, \"seconds\": %.6f, \"threads\": %u, \"fp_bits\": %d, \"engine\": \"%s\", \"segments\": %s}\n", totalGates,
+            seconds, regs.empty() ? 0U : regs.begin()->second->GetConcurrencyLevel(), (int)(8 * sizeof(real1)), g_engine.c_str(),
+            seg.c_str());
     }
     return 0;
 }

@@ -12,8 +12,10 @@ rank-bit qubits are per-rank scalars or predicated local phases, controls on ran
 (QPager's meta-controlled cases, ``src/qpager.cpp:452-593``), scalars (Prob, norms) are one ``all_reduce``.
 
 ``QEngineSharded`` derives from ``QEngineHost`` — the same gate dispatch mirror as ``QEngineCUDA`` — and supplies a
-backend whose primitives are distributed, so every ``QInterface``-named method (H, T, CNOT, QFT, Prob, ForceM, …) works
-unchanged on top of it.  The local engine and the communicator are injected: ``QEngineCUDA`` over a torch CUDA buffer +
+backend whose primitives are distributed, so the gate-level ``QInterface`` methods (H, T, CNOT, MC/MAC gates, QFT, INC/DEC,
+ZeroPhaseFlip, Prob*, ForceM, M, MAll, HighestProbAll, ProbMaskAll, …) work unchanged on top of it.  Primitives that are not
+sharded (Compose/Decompose, ForceMParity, UniformParityRZ, SumSqrDiff, the native QAlu sweeps, page ops) raise
+``NotImplementedError`` identically on every rank.  The local engine and the communicator are injected: ``QEngineCUDA`` over a torch CUDA buffer +
 NCCL on the GPU box; the oracle restatement over a torch CPU buffer + gloo in the CPU tests.
 """
 from __future__ import annotations
@@ -405,6 +407,84 @@ class _ShardedBackend:
         s = self.get_state()
         return (s.real.astype(self.real) ** 2 + s.imag.astype(self.real) ** 2).astype(self.real)
 
+    # ---- sampling: on-device per rank, one small collective for the choice of rank -----------------------
+    def _logical_index(self, phys: int) -> int:
+        out = 0
+        for q in range(self.n):
+            if (phys >> self.perm[q]) & 1:
+                out |= 1 << q
+        return out
+
+    def _gather_scalars(self, vals: Sequence[float]) -> List[List[float]]:
+        """every rank's `vals`, indexed [rank][i] (an all_reduce of a one-hot-by-rank matrix)"""
+        w = len(vals)
+        flat = [0.0] * (self.world * w)
+        flat[self.rank * w:(self.rank + 1) * w] = list(vals)
+        red = self._allreduce(flat)
+        return [red[r * w:(r + 1) * w] for r in range(self.world)]
+
+    def sample(self, rnd: float) -> int:
+        """MAll's search (state.cpp:2026-2050) over the sharded vector: the pages are walked in PHYSICAL order (rank-major),
+        so for a given `rnd` the outcome is a valid sample of |psi|^2 but not index-for-index the single-engine one once the
+        qubit map has been permuted by exchanges."""
+        self.flush()
+        tots = [t[0] for t in self._gather_scalars([self.loc.be.norm(0.0)])]
+        cum, pick, last_nz = 0.0, None, None
+        for r in range(self.world):
+            if tots[r] > 0:
+                last_nz = r
+                if cum + tots[r] > rnd:
+                    pick = r
+                    break
+                cum += tots[r]
+        if pick is None:
+            if last_nz is None:
+                return (1 << self.n) - 1
+            pick, cum = last_nz, cum - tots[last_nz]
+        idx = 0.0
+        if self.rank == pick:
+            idx = float((pick << self.nl) | self.loc.be.sample(rnd - cum))
+        phys = int(round(self._allreduce([idx])[0]))
+        return self._logical_index(phys)
+
+    def highest_prob(self) -> int:
+        self.flush()
+        li = self.loc.be.highest_prob()
+        a = self.loc.GetAmplitude(li)
+        rows = self._gather_scalars([a.real * a.real + a.imag * a.imag, float((self.rank << self.nl) | li)])
+        best = max(range(self.world), key=lambda r: (rows[r][0], -r))
+        return self._logical_index(int(round(rows[best][1])))
+
+    def prob_mask_all(self, mask: int) -> np.ndarray:
+        self.flush()
+        qs = [q for q in range(self.n) if (mask >> q) & 1]           # logical mask qubits, ascending = output bit order
+        lm, _ = self._split(self._pmask(mask))
+        loc = self.loc.be.prob_mask_all(lm) if lm else np.array([self.loc.be.norm(0.0)])
+        lbits = [b for b in range(self.nl) if (lm >> b) & 1]          # physical local mask bits, ascending = loc's bit order
+        where = {self.perm[q]: j for j, q in enumerate(qs)}           # physical bit -> output bit
+        fixed = 0
+        for q in qs:
+            if self.perm[q] >= self.nl and (self.rank >> (self.perm[q] - self.nl)) & 1:
+                fixed |= 1 << where[self.perm[q]]
+        out = np.zeros(1 << len(qs), dtype=np.float64)
+        for j in range(loc.size):
+            o = fixed
+            for i, b in enumerate(lbits):
+                if (j >> i) & 1:
+                    o |= 1 << where[b]
+            out[o] += float(loc[j])
+        return np.asarray(self._allreduce(out.tolist()), dtype=self.real)
+
+    _UNSUPPORTED = ("collapse_parity", "uniform_parity_rz", "uniformly_controlled", "inner", "expectation", "compose", "decompose",
+                    "dispose_perm", "get_page", "set_page", "copy_page", "shuffle", "copy_state", "clone")
+
+    def __getattr__(self, name):
+        # primitives the sharded backend does not provide fail the same way on every rank, before any collective of theirs
+        if name in _ShardedBackend._UNSUPPORTED or name.startswith("alu_"):
+            raise NotImplementedError("QEngineSharded: backend primitive %r is not sharded (use the gate-level QInterface form, "
+                                      "or QPager over the drop-in)" % name)
+        raise AttributeError(name)
+
     # ---- scheduling -------------------------------------------------------------------------------------------------
     def flush(self):
         """Run the queued gates.  Gates whose target is a rank-bit qubit need an exchange; instead of exchanging at the
@@ -461,8 +541,12 @@ class _ShardedBackend:
         if d == 1:
             return
         if ctrls:
-            tq = next(q for q in range(nl) if q not in ctrls)
-            self.loc.UCMtrx(ctrls, [d, 0j, 0j, d], tq, cperm)
+            # a controlled scalar: fold the last control into the matrix (a phase on that qubit under the other controls)
+            last = ctrls[-1]
+            want_last = (cperm >> (len(ctrls) - 1)) & 1
+            rest_perm = cperm & ((1 << (len(ctrls) - 1)) - 1)
+            m = [1 + 0j, 0j, 0j, d] if want_last else [d, 0j, 0j, 1 + 0j]
+            self.loc.UCMtrx(ctrls[:-1], m, last, rest_perm)
         else:
             self.loc.Mtrx([d, 0j, 0j, d], 0)
 
@@ -518,6 +602,13 @@ class QEngineSharded(QEngineHost):
             raise ValueError("QEngineSharded: doNormalize is not supported (QPager forces it off as well)")
         self._dist, self._world, self._rank = dist, world, rank
         self._device, self._make_engine, self._p2p = device, make_engine, p2p
+        if rgp is None and world > 1:
+            # measurement outcomes are drawn per rank after an all-reduced probability: every rank must draw the SAME numbers.
+            # Rank 0 picks the seed, everybody adopts it.
+            import random as _random
+            box = [_random.SystemRandom().getrandbits(62) if rank == 0 else 0]
+            dist.broadcast_object_list(box, src=0)
+            rgp = _random.Random(box[0])
         super().__init__(qBitCount, initState, rgp, 1.0 + 0j if phaseFac is None else phaseFac, False, randomGlobalPhase,
                          precision=precision)
 
@@ -528,6 +619,9 @@ class QEngineSharded(QEngineHost):
         else:
             shard = ShardBuffers(n_qubits - k, self.precision, self._device, self._make_engine)
         return _ShardedBackend(n_qubits, self.precision, shard, self._dist, self._world, self._rank)
+
+    def _has_alu(self) -> bool:
+        return False  # INC/DEC take the gate-level QInterface form (src/qinterface/arithmetic.cpp:20-51); other QAlu members raise
 
     def flush(self):
         self.be.flush()

@@ -56,6 +56,19 @@ def test_b200_arm_json_contract():
     for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
         assert k in j["e2e"], k
     assert j["gpu_launches"] > 0
+    # self-checks computed in the run: norm, marginals, mirror-circuit return
+    assert j["check"]["ok"] is True and abs(j["check"]["norm_minus_1"]) < 1e-4 and abs(j["check"]["mirror_return_prob"] - 1) < 1e-3
+
+
+@pytest.mark.parametrize("workload,extra", [("grover", ["--depth", "2"]), ("qft", ["--precision", "64"]), ("qv", ["--depth", "3"])])
+def test_b200_arm_other_baseline_workloads(workload, extra):
+    shim = (SHIM % util.ROOT).replace("'--skip-cpu-baseline']", "'--skip-cpu-baseline', '--workload', %r] + %r" % (workload, extra))
+    r = subprocess.run([sys.executable, "-c", shim], capture_output=True, text=True, timeout=600, cwd=util.ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = _last_json(r.stdout)
+    assert j["check"]["ok"] is True, j["check"]
+    if workload == "grover":
+        assert abs(j["check"]["grover_success_prob"] - j["check"]["grover_law_sin2((2k+1)asin(2^-n/2))"]) < 1e-4
 
 
 def test_reference_arm_runs_on_host_cores():
@@ -68,6 +81,13 @@ def test_reference_arm_runs_on_host_cores():
     assert j["impl"] == "reference" and j["unit"] == "gates/s" and j["value"] > 0
     assert j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+    # the sample is a fixed prefix of the circuit (>= one full layer incl. CNOTs), whatever --steps is, and `config` is the b200 arm's
+    assert j["reference_sample"]["ops_total"] >= 60 and len(j["reference_sample"]["segment_seconds"]) == 2
+    r5 = subprocess.run([sys.executable, os.path.join(util.ROOT, "bench.py"), "--impl", "reference", "--qubits", "16", "--steps", "20",
+                         "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=util.ROOT)
+    j5 = _last_json(r5.stdout)
+    assert j5["reference_sample"]["ops_total"] == 60 and j5["config"] == j["config"]
+    assert set(j["config"]) == {"workload", "l2_policy", "fusion", "parallelism"}
     # other ranks of a torchrun launch do no work
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(util.ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--qubits", "16"],

@@ -84,6 +84,69 @@ def test_sharded_matches_single_engine(name, world, tmp_path):
         assert exchanges >= 1   # these circuits put non-diagonal gates on rank-bit qubits
 
 
+def _worker_sampling(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.sharded_cpu import restate_engine_factory
+        from qrack_b200.sharded import QEngineSharded
+        # rgp=None: the unseeded default must still draw the same numbers on every rank (seed broadcast from rank 0)
+        q = QEngineSharded(7, 0, None, 1.0 + 0j, precision=32, dist=dist, world=world, rank=rank, device="cpu",
+                           make_engine=restate_engine_factory(32))
+        for b in range(7):
+            q.H(b)
+        q.CNOT(6, 0)                      # exchange: the qubit map is permuted afterwards
+        q.T(5)
+        pma = q.ProbMaskAll(0b1100001)
+        hp_state = None
+        outcomes = [int(q.M(b)) for b in (6, 5, 0)]       # rank-bit and local qubits, unforced
+        perm = q.MAll()
+        amp = q.GetAmplitude(perm)
+        q.SetPermutation(0b1010101)
+        hp = q.HighestProbAll()
+        unsupported = 0
+        for call in (lambda: q.ForceMParity(3, True), lambda: q.INCC(1, 0, 3, 4)):
+            try:
+                call()
+            except NotImplementedError:
+                unsupported += 1
+        np.savez(out_path + ".%d.npz" % rank, pma=pma, outcomes=np.array(outcomes), perm=perm, amp=np.array([amp.real, amp.imag]),
+                 hp=hp, unsupported=unsupported)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sampling_and_unseeded_rng_are_rank_consistent(tmp_path):
+    world = 4
+    out = str(tmp_path / "samp")
+    mp.spawn(_worker_sampling, args=(world, _free_port(), out), nprocs=world, join=True)
+    z = [np.load(out + ".%d.npz" % r) for r in range(world)]
+    for r in range(1, world):
+        assert (z[r]["outcomes"] == z[0]["outcomes"]).all() and int(z[r]["perm"]) == int(z[0]["perm"])
+    # uniform superposition (CNOT permutes it, T is a phase): every 3-qubit marginal entry is 1/8
+    assert np.allclose(z[0]["pma"], 1.0 / 8, atol=1e-6)
+    perm = int(z[0]["perm"])
+    o = z[0]["outcomes"]
+    assert ((perm >> 6) & 1, (perm >> 5) & 1, perm & 1) == (int(o[0]), int(o[1]), int(o[2]))   # MAll respects the collapsed qubits
+    assert abs(complex(*z[0]["amp"])) > 0.99                                                   # and leaves |perm>
+    assert int(z[0]["hp"]) == 0b1010101
+    assert int(z[0]["unsupported"]) == 2
+
+
+def test_grover_on_sharded_engine_follows_success_law(tmp_path):
+    """BASELINE configs[4] at test size: gate-level INC/DEC + ZeroPhaseFlip across rank bits (8 qubits over 4 ranks)."""
+    import math
+    n, it = 8, 3
+    text = qscript.grover(n, it, target=3, timed=False)
+    want, wres = util.run_engine(text, QEngineRestate, 32)
+    got, gres, exchanges = run_sharded(text, 4, 32, tmp_path)
+    d = float(np.abs(got.astype(np.complex128) - want[0].astype(np.complex128)).max())
+    assert d <= util.AMP_TOL[32], d
+    law = math.sin((2 * it + 1) * math.asin(2.0 ** (-n / 2.0))) ** 2
+    assert abs(float(gres[0]) - law) < 1e-5
+
+
 @pytest.mark.parametrize("defer", ["0", "1"])
 def test_deep_circuit_in_order_and_deferred_exchanges(defer, tmp_path, monkeypatch):
     """40 gate layers on 10 qubits over 4 ranks: both exchange policies (in-order, and deferral of the gates blocked by a

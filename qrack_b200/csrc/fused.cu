@@ -51,6 +51,7 @@ constexpr uint32_t OPC_STAGE = 17U;
 // two qubits are register-resident); pair index = k * (k - 1) / 2 + j for bits j < k.
 constexpr uint32_t OPC_PH2 = 18U; // .. 27
 constexpr uint32_t CODE_HAS_SB = 0x100U;
+constexpr uint32_t CODE_HAS_OUTER = 0x200U; // the op has a predicate on qubits outside the tile: consult the per-tile ballot
 constexpr int MAX_MEMBERS = 320; // thread-level phase members per sweep (8 bytes each in the double-buffered per-tile table)
 // host (scheduler) op kinds
 enum { OP_GENERAL = 0, OP_HAD = 1, OP_XSWAP = 2, OP_PHASE = 3 };
@@ -94,6 +95,8 @@ struct alignas(16) DevSweep {
     int directOut; // 1: the last pass writes straight to HBM; 0: through the smem tile
     int nMem;      // thread-level phase members (DevMember records at memOff)
     int memOff;
+    int needFull;  // 1: the program holds XSWAP / general-matrix ops (launch the FULL kernel variant); 0: STAGE / phase ops only
+    int pad0;
     unsigned short slotBeg[MAX_SLOTS + 1]; // slot s multiplies the outer records [slotBeg[s], slotBeg[s+1])
     uint64_t highLow[MAX_HIGH]; // (2^q - 1) for push_apart of the tile base, ascending
     uint64_t highPow[MAX_HIGH]; // 2^q
@@ -297,19 +300,13 @@ template <typename R> struct alignas(16) DevMember {
     R ph[2];
 };
 
-template <typename R, int NA>
-__device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const DevOp<R>& op, uint32_t xsb, const R* __restrict__ tileScale,
-    const DevMember<R>* __restrict__ members, const uint2* __restrict__ eff)
+template <typename R, int NA, bool FULL>
+__device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const DevOp<R>& op, const uint4 hd, uint32_t xsb,
+    const R* __restrict__ tileScale, const DevMember<R>* __restrict__ members, const uint2* __restrict__ eff)
 {
     typedef AmpOps<R> O;
     typedef typename O::A A;
-    const uint4 hd = *reinterpret_cast<const uint4*>(&op.code);
     const R* m = op.m;
-    bool tp = true;
-    if (hd.x & CODE_HAS_SB) {
-        tp = (xsb & hd.z) == hd.w;
-    }
-    const uint32_t em = tp ? hd.y : 0U;
 #define SV_J(J) (((1 << (J)) < NA) ? (J) : 0)
 #define SV_CASES(J)                                                                                                    \
     case K_XSWAP * 5 + J:                                                                                              \
@@ -327,14 +324,13 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
             app_phase_pair<R, SV_J(J), SV_J(K), NA>(a, O::mkph(m[0], m[1]));                                           \
         }                                                                                                              \
         break;
-    switch (hd.x & 0xffU) {
-    case OPC_STAGE: {
-        const uint32_t hm = hd.y & 31U, sm = (hd.y >> 5) & 31U;
+    if ((hd.x & 0xffU) == OPC_STAGE) {
+        const uint32_t hm = hd.y & 31U, sm = (hd.y >> 5) & 31U, act = hd.y >> 11;
         uint32_t slot = hd.z, mk = hd.w;
         const uint32_t cnts = (hd.y & (1U << 10)) ? *reinterpret_cast<const uint32_t*>(op.m) : 0U;
         // product of the thread-level members [mk, mk + c) that fire for this thread, times (px, py)
 #define SV_MEMBERS(c)                                                                                                  \
-    for (uint32_t k = 0; k < (c); ++k, ++mk) {                                                                         \
+    _Pragma("unroll 1") for (uint32_t k = 0; k < (c); ++k, ++mk) {                                                                         \
         const uint2 e = eff[mk];                                                                                       \
         const R qx = members[mk].ph[0], qy = members[mk].ph[1];                                                        \
         if ((xsb & e.x) == e.y) {                                                                                      \
@@ -358,7 +354,7 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
             }
         }
 #define SV_STAGE_BIT(J)                                                                                                \
-    if ((1 << (J)) < NA) {                                                                                             \
+    if (((1 << (J)) < NA) && ((act >> (J)) & 1U)) {                                                                    \
         const uint32_t c = (cnts >> (5 * ((J) + 1))) & 31U;                                                            \
         if (((sm >> (J)) & 1U) | c) {                                                                                  \
             R px = (R)1, py = (R)0;                                                                                    \
@@ -383,7 +379,26 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         SV_STAGE_BIT(4)
 #undef SV_STAGE_BIT
 #undef SV_MEMBERS
-    } break;
+        return;
+    }
+    bool tp = true;
+    if (hd.x & CODE_HAS_SB) {
+        tp = (xsb & hd.z) == hd.w;
+    }
+    const uint32_t em = tp ? hd.y : 0U;
+    if (FULL && (hd.x & 0xffU) < OPC_PHGEN) {
+        switch (hd.x & 0xffU) {
+            SV_CASES(0)
+            SV_CASES(1)
+            SV_CASES(2)
+            SV_CASES(3)
+            SV_CASES(4)
+        default:
+            break;
+        }
+        return;
+    }
+    switch (hd.x & 0xffU) {
     case OPC_SCALE: {
         const typename O::Ph sc = O::mkph(tileScale[0], tileScale[1]);
 #pragma unroll
@@ -391,11 +406,6 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
             a[e] = O::mulc(a[e], sc);
         }
     } break;
-        SV_CASES(0)
-        SV_CASES(1)
-        SV_CASES(2)
-        SV_CASES(3)
-        SV_CASES(4)
         SV_PAIR(1, 0)
         SV_PAIR(2, 0)
         SV_PAIR(2, 1)
@@ -430,7 +440,7 @@ template <typename R> struct DevOuterPhase {
     R pad[(sizeof(R) == 4) ? 2 : 2];
 };
 
-constexpr int MAX_OUTER = 64;
+constexpr int MAX_OUTER = 192;
 
 // Staged tile copies (used when the first / last pass has register bits on low chunk bits): coalesced HBM <-> swizzled
 // smem.  Kept out of line so that their registers do not weigh on the pass loop.
@@ -472,7 +482,7 @@ __device__ __noinline__ void stage_out(typename Cx<R>::type* __restrict__ tilePs
     }
 }
 
-template <typename R, int KC, int RB, int NT, int MINB>
+template <typename R, int KC, int RB, int NT, int MINB, bool FULL>
 __global__ void __launch_bounds__(NT, MINB)
     k_fused_sweep(typename Cx<R>::type* __restrict__ psi, const unsigned char* __restrict__ prog, uint32_t progBytes, uint64_t nTiles)
 {
@@ -626,17 +636,8 @@ __global__ void __launch_bounds__(NT, MINB)
                     dep |= ((tid >> i) & 1U) << ps.sbit[i];
                 }
             }
-            // active ops of this pass as (up to 3) 32-bit words
-            uint32_t pm[3];
-#pragma unroll
-            for (int w = 0; w < 3; ++w) {
-                const int lo = ps.opBegin - 32 * w, hi = ps.opEnd - 32 * w;
-                uint32_t m = ballots[par][w];
-                m = (lo > 0) ? ((lo >= 32) ? 0U : (m & (0xffffffffU << lo))) : m;
-                m = (hi < 32) ? ((hi <= 0) ? 0U : (m & (0xffffffffU >> (32 - hi)))) : m;
-                pm[w] = m;
-            }
-            const int wBegin = ps.opBegin >> 5, wEnd = (ps.opEnd > ps.opBegin) ? ((ps.opEnd - 1) >> 5) : (wBegin - 1);
+            const int opBegin = ps.opBegin, opEnd = ps.opEnd;
+            const uint2* const effCur = effTab + par * (uint32_t)nMem;
             for (int it = 0; it < ps.nIt; ++it) {
                 if ((uint32_t)(it * NT + tid) >= nSub) {
                     break;
@@ -659,14 +660,14 @@ __global__ void __launch_bounds__(NT, MINB)
                     }
                 }
                 const uint32_t xsb = sbc * APC;
+                // linear walk over the pass's ops; only ops with a predicate on outer qubits look at the per-tile ballot
 #pragma unroll 1
-                for (int w = wBegin; w <= wEnd; ++w) {
-                    uint32_t m = (w == 0) ? pm[0] : ((w == 1) ? pm[1] : pm[2]);
-                    while (m) {
-                        const int o = 32 * w + __ffs(m) - 1;
-                        m &= m - 1U;
-                        exec_op<R, NA>(a, ops[o], xsb, tileScale, members, effTab + par * (uint32_t)nMem);
+                for (int o = opBegin; o < opEnd; ++o) {
+                    const uint4 hd = *reinterpret_cast<const uint4*>(&ops[o].code);
+                    if ((hd.x & CODE_HAS_OUTER) && !((ballots[par][o >> 5] >> (o & 31)) & 1U)) {
+                        continue;
                     }
+                    exec_op<R, NA, FULL>(a, ops[o], hd, xsb, tileScale, members, effCur);
                 }
                 if (toGlobal) {
 #pragma unroll
@@ -773,6 +774,20 @@ static void lower_queue(const std::vector<GateOp>& q, std::vector<HostOp>& out)
     }
     if (knob_rewrite()) {
         rewrite_ops(out);
+    }
+    if (getenv("B200SV_FUSED_DEBUG")) {
+        int cnt[4] = { 0, 0, 0, 0 };
+        for (const HostOp& h : out) {
+            cnt[h.kind]++;
+        }
+        fprintf(stderr, "lowered: %zu gates -> %zu ops (general %d, hadamard %d, xswap %d, phase %d)\n", q.size(), out.size(), cnt[0], cnt[1],
+            cnt[2], cnt[3]);
+        if (atoi(getenv("B200SV_FUSED_DEBUG")) >= 2) {
+            for (const HostOp& h : out) {
+                fprintf(stderr, "   %s t=%d cmask=%llx cval=%llx m0=(%.3f,%.3f)\n", h.kind == OP_PHASE ? "PH" : (h.kind == OP_HAD ? "H " : (h.kind == OP_XSWAP ? "X " : "G ")),
+                    h.tq, (unsigned long long)h.cmask, (unsigned long long)h.cval, h.m[0], h.m[1]);
+            }
+        }
     }
 }
 
@@ -1026,12 +1041,21 @@ static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref, int NT = 256
 // Greedy, order-preserving selection with commutation-aware skipping.
 //   fits(op)   : can the op be executed under the current resource set (may grow the set)
 // Ops that are skipped block later ops that do not commute with them.
-template <typename FitFn>
-static void greedy_select(std::vector<HostOp>& pending, std::vector<HostOp>& taken, size_t maxTake, size_t lookahead, FitFn fits)
+// Lazy diagonals (r2): a diagonal op commutes with everything except a non-diagonal op on one of its qubits, so it may be
+// applied anywhere between its neighbours of that kind.  With `lazy`, a diagonal op is taken at once only when it costs
+// nothing here (isFree: none of its qubits is a tile qubit -> per-tile scalar); otherwise it is DEFERRED without blocking
+// anything, and pulled in right before the first taken non-diagonal op that acts on one of its qubits (so its phase joins
+// the stage of that butterfly instead of costing a phase application of its own), or left for a later pass / sweep where it
+// may be free.  When no non-diagonal op remains, the deferred ones are taken (progress, and no diagonal-only extra sweep).
+template <typename FitFn, typename FreeFn>
+static void greedy_select(std::vector<HostOp>& pending, std::vector<HostOp>& taken, size_t maxTake, size_t lookahead, FitFn fits, bool lazy,
+    FreeFn isFree)
 {
     uint64_t blockedT = 0, blockedD = 0;
-    std::vector<HostOp> rest;
-    rest.reserve(pending.size());
+    std::vector<char> gone(pending.size(), 0);
+    std::vector<size_t> deferred;
+    uint64_t deferredQ = 0;
+    bool nonDiagLeft = false;
     size_t i = 0;
     for (; i < pending.size(); ++i) {
         const HostOp& op = pending[i];
@@ -1041,19 +1065,63 @@ static void greedy_select(std::vector<HostOp>& pending, std::vector<HostOp>& tak
         const uint64_t usesT = op.tq >= 0 ? bitq(op.tq) : 0;
         const uint64_t usesD = op.cmask;
         bool conflict = (usesT & (blockedT | blockedD)) || (usesD & blockedT);
+        if (!conflict && lazy && op.kind == OP_PHASE && !isFree(op)) {
+            deferred.push_back(i);
+            deferredQ |= usesD;
+            continue;
+        }
         if (!conflict && !fits(op)) {
             conflict = true;
         }
         if (conflict) {
             blockedT |= usesT;
             blockedD |= usesD;
-            rest.push_back(op);
+            nonDiagLeft = nonDiagLeft || op.kind != OP_PHASE;
         } else {
+            if (usesT & deferredQ) {
+                // the deferred diagonals on the target come first (they were unblocked when they were deferred)
+                size_t w = 0;
+                deferredQ = 0;
+                for (size_t k = 0; k < deferred.size(); ++k) {
+                    const size_t j = deferred[k];
+                    if ((pending[j].cmask & usesT) && taken.size() + 1U < maxTake) {
+                        taken.push_back(pending[j]);
+                        gone[j] = 1;
+                    } else {
+                        deferred[w++] = j;
+                        deferredQ |= pending[j].cmask;
+                    }
+                }
+                deferred.resize(w);
+                if (usesT & deferredQ) { // no room for a diagonal it needs: the op cannot run in this selection either
+                    blockedT |= usesT;
+                    blockedD |= usesD;
+                    nonDiagLeft = true;
+                    continue;
+                }
+            }
             taken.push_back(op);
+            gone[i] = 1;
         }
     }
-    for (; i < pending.size(); ++i) {
-        rest.push_back(pending[i]);
+    for (size_t k = i; k < pending.size() && !nonDiagLeft; ++k) {
+        nonDiagLeft = pending[k].kind != OP_PHASE;
+    }
+    if (lazy && !nonDiagLeft) {
+        // only diagonal ops are left: take them now, in order
+        for (size_t k = 0; k < pending.size() && taken.size() < maxTake; ++k) {
+            if (!gone[k]) {
+                taken.push_back(pending[k]);
+                gone[k] = 1;
+            }
+        }
+    }
+    std::vector<HostOp> rest;
+    rest.reserve(pending.size());
+    for (size_t k = 0; k < pending.size(); ++k) {
+        if (!gone[k]) {
+            rest.push_back(pending[k]);
+        }
     }
     pending.swap(rest);
 }
@@ -1094,6 +1162,7 @@ static size_t greedy_count(const std::vector<HostOp>& pending, size_t maxTake, s
 }
 
 static int knob_plan_search();
+static int knob_lazy_diag();
 
 static void plan_sweep(std::vector<HostOp>& pending, const TileCfg& cfg, SweepPlan& sp)
 {
@@ -1156,17 +1225,21 @@ static void plan_sweep(std::vector<HostOp>& pending, const TileCfg& cfg, SweepPl
         inTile = cur;
         freeHigh = 0;
     }
-    greedy_select(pending, sel, (size_t)cfg.maxOps, 2048, [&](const HostOp& op) {
-        if (op.tq < 0 || (inTile & bitq(op.tq))) {
-            return true;
-        }
-        if (freeHigh > 0) {
-            inTile |= bitq(op.tq);
-            --freeHigh;
-            return true;
-        }
-        return false;
-    });
+    const bool lazy = knob_lazy_diag() != 0;
+    greedy_select(
+        pending, sel, (size_t)cfg.maxOps, 2048,
+        [&](const HostOp& op) {
+            if (op.tq < 0 || (inTile & bitq(op.tq))) {
+                return true;
+            }
+            if (freeHigh > 0) {
+                inTile |= bitq(op.tq);
+                --freeHigh;
+                return true;
+            }
+            return false;
+        },
+        lazy, [&](const HostOp& op) { return freeHigh == 0 && !(op.cmask & inTile); });
     sp.highQ.clear();
     for (int q = cfg.L; q < cfg.n; ++q) {
         if (inTile & bitq(q)) {
@@ -1235,18 +1308,21 @@ static void plan_sweep(std::vector<HostOp>& pending, const TileCfg& cfg, SweepPl
                 }
             }
         }
-        greedy_select(sel, pp.ops, (size_t)cfg.maxOps, 4096, [&](const HostOp& op) {
-            if (op.tq < 0 || (regSet & bitq(op.tq))) {
-                return true;
-            }
-            if (freeReg > 0) {
-                regSet |= bitq(op.tq);
-                --freeReg;
-                pp.regQ.push_back(op.tq);
-                return true;
-            }
-            return false;
-        });
+        greedy_select(
+            sel, pp.ops, (size_t)cfg.maxOps, 4096,
+            [&](const HostOp& op) {
+                if (op.tq < 0 || (regSet & bitq(op.tq))) {
+                    return true;
+                }
+                if (freeReg > 0) {
+                    regSet |= bitq(op.tq);
+                    --freeReg;
+                    pp.regQ.push_back(op.tq);
+                    return true;
+                }
+                return false;
+            },
+            lazy, [&](const HostOp& op) { return !(op.cmask & inTile); });
         sp.passes.push_back(pp);
     }
     if (!sel.empty()) {
@@ -1467,8 +1543,14 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                     slotMembers.push_back(st.slot[b]);
                 }
             }
+            uint32_t act = hm | sm;
+            for (int b = 0; b < 5; ++b) {
+                if ((cnts >> (5 * (b + 1))) & 31U) {
+                    act |= 1U << b;
+                }
+            }
             d.code = OPC_STAGE;
-            d.emask = hm | (sm << 5) | (cnts ? (1U << 10) : 0U);
+            d.emask = hm | (sm << 5) | (cnts ? (1U << 10) : 0U) | (act << 11);
             memcpy(d.m, &cnts, sizeof(cnts));
             dops.push_back(d);
             stage_reset();
@@ -1604,7 +1686,10 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                     code = (uncond ? K_GEN_U : K_GEN_P) * 5U + jr;
                 }
             }
-            d.code = code | (d.lmaskSb ? CODE_HAS_SB : 0U);
+            d.code = code | (d.lmaskSb ? CODE_HAS_SB : 0U) | (d.omask ? CODE_HAS_OUTER : 0U);
+            if (code < OPC_PHGEN) {
+                ds.needFull = 1;
+            }
             dops.push_back(d);
         }
         close_stage();
@@ -1820,10 +1905,10 @@ struct KernelCfg {
     int KC, RB, NT, MINB;
 };
 
-template <typename R, int KC, int RB, int NT, int MINB>
-static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes, uint32_t scratchBytes, uint64_t nTiles)
+template <typename R, int KC, int RB, int NT, int MINB, bool FULL>
+static int launch_sweep_v(State* s, const unsigned char* dprog, uint32_t progBytes, uint32_t scratchBytes, uint64_t nTiles)
 {
-    auto kern = k_fused_sweep<R, KC, RB, NT, MINB>;
+    auto kern = k_fused_sweep<R, KC, RB, NT, MINB, FULL>;
     const size_t shm = ((size_t)16 << KC) + progBytes + scratchBytes;
     static std::atomic<unsigned long long> attr_set_mask{ 0 }; // per device: the attribute is per-context
     if (!(attr_set_mask.load() & (1ULL << s->dev))) {
@@ -1843,10 +1928,11 @@ struct FusedKnobs {
     int RB = 4;   // measured on B200 (profiles/r1_tuning.md): RB=4/L=6 beats RB=3/L=7 by ~12% on the 30-qubit H/T/CNOT circuit
     int L32 = 6;
     int L64 = 6;
-    int RB64 = 3; // fp64: 8 double2 amplitudes per sub-block keep 3 CTAs/SM resident
+    int RB64 = 4; // fp64: measured r2 (QFT-30 fp64): RB=4 / 2 CTAs per SM 94.6 ms vs RB=3 / 3 CTAs 108.0 ms (the latter spills)
     int bundle = 7; // bit 0: merge Hadamards on distinct register bits into one LAYER op; bit 1: DIAG phase groups;
                     // bit 2: a LAYER stays open across ops that do not touch its qubits
     int pf = 0;     // 1: L2 prefetch of the CTA's next tile during the passes
+    int minb64 = 3; // fp64 with RB64 = 3: resident CTAs per SM the kernel is compiled for (3: 80 registers, spills; 2: 128 registers)
     int dlow = 1;   // first/last pass go straight HBM<->registers when at most this many of their register bits are chunk bits 0..2
 };
 static const FusedKnobs& knobs()
@@ -1857,6 +1943,9 @@ static const FusedKnobs& knobs()
         if (e) {
             int rb = 0, l32 = 0, l64 = 0, bn = 1, rb64 = 0, cp = 0, pf = 0, dlow = 1;
             const int got = sscanf(e, "%d,%d,%d,%d,%d,%d,%d,%d", &rb, &l32, &l64, &bn, &rb64, &cp, &pf, &dlow);
+            if (got >= 6 && (cp == 2 || cp == 3)) {
+                v.minb64 = cp; // 6th field (formerly the constant-bank variant switch): CTAs/SM of the fp64 RB=3 kernel
+            }
             if (got >= 8) {
                 v.dlow = dlow;
             }
@@ -1883,6 +1972,12 @@ static const FusedKnobs& knobs()
     }();
     return k;
 }
+template <typename R, int KC, int RB, int NT, int MINB>
+static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes, uint32_t scratchBytes, uint64_t nTiles, bool full)
+{
+    return full ? launch_sweep_v<R, KC, RB, NT, MINB, true>(s, dprog, progBytes, scratchBytes, nTiles)
+                : launch_sweep_v<R, KC, RB, NT, MINB, false>(s, dprog, progBytes, scratchBytes, nTiles);
+}
 static int knob_prefetch() { return knobs().pf; }
 static int knob_plan_search()
 {
@@ -1893,6 +1988,22 @@ static int knob_plan_search()
     return v;
 }
 static int knob_direct_low() { return knobs().dlow; }
+static int knob_force_full()
+{
+    static const int v = [] {
+        const char* e = getenv("B200SV_FORCE_FULL");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+static int knob_lazy_diag()
+{
+    static const int v = [] {
+        const char* e = getenv("B200SV_LAZY_DIAG");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
 static int knob_rewrite()
 {
     static const int v = [] {
@@ -1965,17 +2076,22 @@ int fused_flush(State* s)
     for (size_t i = 0; i < segs.size(); ++i) {
         const unsigned char* dp = ar->dev + segs[i].off;
         const uint32_t pb = (uint32_t)segs[i].bytes, sb = (uint32_t)segs[i].scratch;
+        const bool full = knob_force_full() || reinterpret_cast<const DevSweep*>(buf.data() + segs[i].off)->needFull != 0;
         if (s->prec == 32) {
             if (cfg.RB == 4) {
-                SV_TRY((launch_sweep<float, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles)));
+                SV_TRY((launch_sweep<float, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles, full)));
             } else {
-                SV_TRY((launch_sweep<float, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles)));
+                SV_TRY((launch_sweep<float, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles, full)));
             }
         } else {
             if (cfg.RB == 4) {
-                SV_TRY((launch_sweep<double, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles)));
+                SV_TRY((launch_sweep<double, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles, full)));
             } else {
-                SV_TRY((launch_sweep<double, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles)));
+                if (knobs().minb64 == 2) {
+                    SV_TRY((launch_sweep<double, FUSED_KC, 3, FUSED_NT, 2>(s, dp, pb, sb, nTiles, full)));
+                } else {
+                    SV_TRY((launch_sweep<double, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles, full)));
+                }
             }
         }
         s->stats.kernel_launches++;

@@ -14,8 +14,8 @@ echo "== reference ALU unittests on the drop-in's native QAlu kernels (--layer-q
 timeout 900 $U --layer-qengine --proc-cuda --disable-hardware-rng "$ALU" > gpurun_out/dropin_unittest_alu_full.log 2>&1; grep -B3 -A12 "FAILED" gpurun_out/dropin_unittest_alu_full.log | head -60; tail -4 gpurun_out/dropin_unittest_alu_full.log | tee gpurun_out/dropin_unittest_alu.log
 echo "== reference unittest with QUnit over the drop-in (--layer-qunit --proc-cuda): callers above the engine"
 timeout 900 $U --layer-qunit --proc-cuda --disable-hardware-rng "$LIST,$ALU" > gpurun_out/dropin_unittest_qunit_full.log 2>&1; grep -B12 "FAILED" gpurun_out/dropin_unittest_qunit_full.log | grep "^test_" | sort | uniq -c | head -20; tail -4 gpurun_out/dropin_unittest_qunit_full.log | tee gpurun_out/dropin_unittest_qunit.log
-echo "== reference unittest with QHybrid over the drop-in (--layer-qengine --proc-hybrid)"
-timeout 900 $U --layer-qengine --proc-hybrid --disable-hardware-rng "$LIST,$ALU" > gpurun_out/dropin_unittest_qhybrid_full.log 2>&1; grep -B12 "FAILED" gpurun_out/dropin_unittest_qhybrid_full.log | grep "^test_" | sort | uniq -c | head -20; tail -4 gpurun_out/dropin_unittest_qhybrid_full.log | tee gpurun_out/dropin_unittest_qhybrid.log
+echo "== reference unittest with QHybrid over the drop-in (--layer-qunit --proc-hybrid: test_main.cpp has no qengine-layer slot for QHybrid)"
+timeout 900 $U --layer-qunit --proc-hybrid --disable-hardware-rng "$LIST,$ALU" > gpurun_out/dropin_unittest_qhybrid_full.log 2>&1; grep -B12 "FAILED" gpurun_out/dropin_unittest_qhybrid_full.log | grep "^test_" | sort | uniq -c | head -20; tail -4 gpurun_out/dropin_unittest_qhybrid_full.log | tee gpurun_out/dropin_unittest_qhybrid.log
 echo "== reference unittest on QPager over the drop-in (--layer-qpager --proc-cuda)"
 timeout 900 $U --layer-qpager --proc-cuda --disable-hardware-rng "$LIST" > gpurun_out/dropin_unittest_qpager_full.log 2>&1; grep -A2 "^tests.cpp.*FAILED\|^\S.*tests.cpp:[0-9]*: FAILED" gpurun_out/dropin_unittest_qpager_full.log | grep -v "^--" | head -40; grep -B12 "FAILED" gpurun_out/dropin_unittest_qpager_full.log | grep "^test_" | sort | uniq -c | head -20; tail -4 gpurun_out/dropin_unittest_qpager_full.log | tee gpurun_out/dropin_unittest_qpager.log
 echo "== harness parity: drop-in vs compiled reference on the C1 circuit (20 q)"

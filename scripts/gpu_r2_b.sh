@@ -26,6 +26,22 @@ run qft64_rb3_2cta B200SV_FUSED=4,6,6,7,3,2 -- --steps 5 --warmup 3 --workload q
 run qft64_rb3_3cta B200SV_FUSED=4,6,6,7,3,3 -- --steps 5 --warmup 3 --workload qft --precision 64 --skip-check
 run qft32 X=1 -- --steps 5 --warmup 3 --workload qft --precision 32
 run grover30 X=1 -- --steps 3 --warmup 3 --workload grover --depth 3
+echo "== kernel to beat: the reference's own QEngineCUDA (oracle/_ref, sm_100) vs the drop-in, same harness, same script, same box"
+python - <<'PY'
+import sys; sys.path.insert(0,'.')
+from qrack_b200 import qscript
+open('/tmp/c2.qs','w').write(qscript.random_htcnot(30,40,seed=20250921,timed=True))
+open('/tmp/c2s.qs','w').write(qscript.random_htcnot(28,40,seed=20250921,timed=True))
+PY
+export LD_LIBRARY_PATH=$PWD/qrack_b200:${LD_LIBRARY_PATH:-}
+for sc in c2s c2; do
+  echo "-- $sc reference QEngineCUDA"; timeout 600 oracle/_ref/ref_harness_cuda_f32 /tmp/$sc.qs --engine cuda --time 2>&1 | tail -2 | tee -a gpurun_out/refcuda_harness.log
+  echo "-- $sc drop-in QEngineCUDA";   timeout 600 dropin/_build/harness_b200_f32 /tmp/$sc.qs --engine cuda --time 2>&1 | tail -2 | tee -a gpurun_out/refcuda_harness.log
+done
+for t in test_qft_permutation_init test_random_circuit_sampling; do
+  echo "-- benchmarks $t: reference CUDA engine"; timeout 900 oracle/_ref/benchmarks_refcuda --layer-qengine --proc-cuda --single -m 30 --samples 3 --disable-terminal-measurement --disable-hardware-rng $t 2>&1 | tail -12 | tee -a gpurun_out/refcuda_bench.log
+  echo "-- benchmarks $t: drop-in"; timeout 900 dropin/_build/f32/benchmarks_b200 --layer-qengine --proc-cuda --single -m 30 --samples 3 --disable-terminal-measurement --disable-hardware-rng $t 2>&1 | tail -12 | tee -a gpurun_out/refcuda_bench.log
+done
 echo "== ncu full (28 q)"
 NCU_OUT=prof_fused_r2b bash scripts/gpu_ncu_full.sh
 echo "== done"

@@ -245,6 +245,46 @@ def test_full_size_mirror_circuit_and_norm(n, prec):
         assert abs(a - b) < (1e-5 if prec == 32 else 1e-11)
 
 
+@pytest.mark.parametrize("n,prec,kind", [(30, 32, "htcnot"), (29, 64, "qft")])
+def test_full_size_parity_against_the_compiled_reference(n, prec, kind, tmp_path):
+    """Full-width states against the REFERENCE, not against ourselves: a 30-qubit fp32 depth-2 H/T/CNOT circuit (90 gates) and a
+    29-qubit fp64 QFT prefix (same bytes) are replayed on the compiled reference QEngineCPU (oracle/_ref, host cores) and on the
+    CUDA engine; every per-qubit Prob and 64 sampled amplitudes must agree (1e-6 fp32 / 1e-12 fp64 on amplitudes)."""
+    if util.ref_harness(prec) is None:
+        pytest.skip("oracle/_ref not built")
+    rng = random.Random(77)
+    if kind == "htcnot":
+        text = qscript.random_htcnot(n, 2, seed=31, timed=False)
+    else:
+        # H on a random half of the qubits, then the first 3 target qubits of QFT(0, n): 3 H + 84 controlled phases on all qubits
+        lines = ["qubits %d" % n] + ["H %d" % q for q in range(n) if rng.random() < 0.5]
+        for i in range(3):
+            hb = n - 1 - i
+            lines.append("H %d" % hb)
+            for j in range(hb):
+                lines.append("CPhaseRootN %d %d %d" % (hb - j + 1, j, hb))
+        text = "\n".join(lines) + "\n"
+    idx = sorted(rng.randrange(1 << n) for _ in range(64))
+    text += "".join("Prob %d\n" % q for q in range(n)) + "".join("GetAmplitude %d\n" % i for i in idx)
+    import subprocess
+    sp = tmp_path / "full.qs"
+    sp.write_text(text)
+    subprocess.run([util.ref_harness(prec), str(sp), "--results", str(tmp_path / "r.txt")], check=True, timeout=1500)
+    want = qscript.parse_results(open(str(tmp_path / "r.txt")).read())
+    _, got = qscript.run(text, util.make_factory(QEngineCUDA, prec))
+    assert len(got) == len(want) == n + 64
+    worst_p = worst_a = 0.0
+    for (gn, gv), (wn, wv) in zip(got, want):
+        assert gn == wn
+        if gn == "Prob":
+            worst_p = max(worst_p, abs(gv[0] - wv[0]))
+        else:
+            worst_a = max(worst_a, abs(complex(*gv) - complex(*wv)))
+    assert worst_a <= util.AMP_TOL[prec], "max |delta amp| over 64 samples = %.3e" % worst_a
+    # Prob is a 2^(n-1)-term reduction: the reference sums per thread in real1 (fp32: ~1e-5 of drift by itself)
+    assert worst_p <= (2e-5 if prec == 32 else 1e-10), "max |delta Prob| = %.3e" % worst_p
+
+
 def test_full_size_uniform_superposition_30q():
     n = 30
     q = QEngineCUDA(n, 0, random.Random(1), 1.0 + 0j, False, False)

@@ -179,6 +179,13 @@ int b200sv_hash(b200sv_t s, int start, int length, const unsigned char* values);
 /* flag_index < 0: PhaseFlipIfLess (:1703-1720); else CPhaseFlipIfLess (:1678-1701) */
 int b200sv_phase_flip_if_less(b200sv_t s, uint64_t greater_perm, int start, int length, int flag_index);
 
+/* Batched submission (what the reference does gate by gate in QCircuit::Run, include/qcircuit.hpp:121-324,
+ * src/qcircuit.cpp:173-281): n_gates single-target Apply2x2 calls in ONE ABI call.  Gate i is Apply2x2(off1[i], off2[i],
+ * mats8 + 8 i, powers = the bits of pmasks[i], nrm = 1, no norm output); off1[i] ^ off2[i] must be a single power.  Identical
+ * in effect to n_gates b200sv_apply2x2 calls (same queue, same fused planner), without the per-gate host round trip. */
+int b200sv_apply_gates(b200sv_t s, int n_gates, const uint64_t* off1, const uint64_t* off2, const uint64_t* pmasks,
+    const double* mats8);
+
 /* Scheduler diagnostic (no device needed): how many fused sweeps / in-tile passes a gate list would take.
  * kinds[i]: 0 real 2x2 (H-like), 1 diagonal (T/CZ-like), 2 X-like (CNOT), 3 complex general; cmasks = control qubits. */
 int b200sv_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks,

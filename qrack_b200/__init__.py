@@ -5,6 +5,7 @@ Layout: ``csrc/`` hand-written sm_100a CUDA kernels + the C ABI of ``include/b20
 circuit-script format shared with the oracle and the reference harness.
 """
 from .qengine import QEngineCUDA, QEngineHost  # noqa: F401
+from .qcircuit import QCircuit  # noqa: F401
 from . import qscript  # noqa: F401
 
-__all__ = ["QEngineCUDA", "QEngineHost", "qscript"]
+__all__ = ["QEngineCUDA", "QEngineHost", "QCircuit", "qscript"]

@@ -54,6 +54,7 @@ SIGNATURES = {
     "b200sv_set_amplitude": [H, c_uint64, c_double, c_double],
     "b200sv_apply2x2": [H, c_uint64, c_uint64, POINTER(c_double), c_int, POINTER(c_uint64), c_double, c_double,
                         POINTER(c_double)],
+    "b200sv_apply_gates": [H, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double)],
     "b200sv_xmask": [H, c_uint64],
     "b200sv_phase_parity": [H, c_double, c_uint64],
     "b200sv_phase_root_n_mask": [H, c_int, c_uint64],

@@ -1747,6 +1747,49 @@ int b200sv_apply2x2(b200sv_t s, uint64_t off1, uint64_t off2, const double* m8, 
     return B200SV_OK;
 }
 
+int b200sv_apply_gates(b200sv_t s, int n_gates, const uint64_t* off1, const uint64_t* off2, const uint64_t* pmasks, const double* mats8)
+{
+    SV_ENTER(s);
+    if (n_gates < 0 || (n_gates && (!off1 || !off2 || !pmasks || !mats8))) {
+        return einval("apply_gates: null argument");
+    }
+    const uint64_t dim = s->dim();
+    for (int i = 0; i < n_gates; ++i) {
+        const uint64_t diff = off1[i] ^ off2[i];
+        if (!diff || (diff & (diff - 1U)) || pmasks[i] >= dim || ((off1[i] | off2[i]) & ~pmasks[i])) {
+            return einval("apply_gates: every gate must be a single-target Apply2x2 form within the qubit bounds");
+        }
+    }
+    if (!s->amps) { // CHECK_ZERO_SKIP
+        return B200SV_OK;
+    }
+    for (int i = 0; i < n_gates; ++i) {
+        GateOp g;
+        make_gate_op(s->prec, off1[i], off2[i], pmasks[i], mats8 + 8 * (size_t)i, 1.0, g);
+        s->stats.gates_submitted++;
+        if (s->fusion && fused_accepts(s, g)) {
+            s->queue.push_back(g);
+            if (s->queue.size() >= 4096) {
+                SV_TRY(flush_queue(s));
+            }
+            continue;
+        }
+        // unfused engines (tiny registers, fusion switched off): the generic kernel, gate by gate
+        SV_TRY(flush_queue(s));
+        uint64_t pows[64];
+        int nb = 0;
+        for (uint64_t m = pmasks[i]; m; m &= m - 1U) {
+            pows[nb++] = m & (~m + 1U);
+        }
+        if (s->prec == 32) {
+            SV_TRY(launch_apply2x2<float>(s, off1[i], off2[i], mats8 + 8 * (size_t)i, nb, pows, 1.0, 0.0, nullptr));
+        } else {
+            SV_TRY(launch_apply2x2<double>(s, off1[i], off2[i], mats8 + 8 * (size_t)i, nb, pows, 1.0, 0.0, nullptr));
+        }
+    }
+    return B200SV_OK;
+}
+
 int b200sv_xmask(b200sv_t s, uint64_t mask)
 {
     SV_ENTER(s);
@@ -1756,7 +1799,30 @@ int b200sv_xmask(b200sv_t s, uint64_t mask)
     if (!s->amps || !mask) {
         return B200SV_OK;
     }
+    if (s->fusion && s->nq >= 5) {
+        // queued as X gates: the fused scheduler turns the XMask ... XMask wrappers of anti-controlled gates
+        // (QInterface::MACWrapper, include/qinterface.hpp:179-189) into control polarities, and hands a wide XMask that
+        // nothing absorbed back to launch_xmask at flush time
+        static const double xm[8] = { 0, 0, 1, 0, 1, 0, 0, 0 };
+        for (uint64_t m = mask; m; m &= m - 1U) {
+            GateOp g;
+            const uint64_t p = m & (~m + 1U);
+            make_gate_op(s->prec, 0, p, p, xm, 1.0, g);
+            s->queue.push_back(g);
+        }
+        s->stats.gates_submitted++;
+        if (s->queue.size() >= 4096) {
+            SV_TRY(flush_queue(s));
+        }
+        return B200SV_OK;
+    }
     SV_TRY(flush_queue(s));
+    return launch_xmask(s, mask);
+}
+} // extern "C"
+
+int b200sv::launch_xmask(State* s, uint64_t mask)
+{
     const uint64_t half = s->dim() >> 1;
     const uint64_t top = 1ULL << (63 - __builtin_clzll(mask));
     const unsigned grid = stream_grid(s->dev, half, 256);
@@ -1766,6 +1832,8 @@ int b200sv_xmask(b200sv_t s, uint64_t mask)
     s->stats.kernel_launches++;
     return B200SV_OK;
 }
+
+extern "C" {
 
 int b200sv_phase_parity(b200sv_t s, double radians, uint64_t mask)
 {

@@ -706,10 +706,12 @@ struct HostOp {
 
 static inline uint64_t bitq(int q) { return 1ULL << q; }
 
-static void rewrite_ops(std::vector<HostOp>& ops);
+static uint64_t rewrite_ops(std::vector<HostOp>& ops);
 static int knob_rewrite();
-static void lower_queue(const std::vector<GateOp>& q, std::vector<HostOp>& out)
+// returns the mask of a trailing XMask that is better served by the dedicated sweep (launch_xmask) after the fused sweeps
+static uint64_t lower_queue(const std::vector<GateOp>& q, std::vector<HostOp>& out)
 {
+    uint64_t xtail = 0;
     out.clear();
     out.reserve(q.size() * 2);
     for (const GateOp& g : q) {
@@ -773,7 +775,7 @@ static void lower_queue(const std::vector<GateOp>& q, std::vector<HostOp>& out)
         out.push_back(h);
     }
     if (knob_rewrite()) {
-        rewrite_ops(out);
+        xtail = rewrite_ops(out);
     }
     if (getenv("B200SV_FUSED_DEBUG")) {
         int cnt[4] = { 0, 0, 0, 0 };
@@ -789,6 +791,7 @@ static void lower_queue(const std::vector<GateOp>& q, std::vector<HostOp>& out)
             }
         }
     }
+    return xtail;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -833,7 +836,7 @@ static inline bool is_had_form(const double* m)
 }
 static int knob_rewrite();
 
-static void rewrite_ops(std::vector<HostOp>& ops)
+static uint64_t rewrite_ops(std::vector<HostOp>& ops)
 {
     std::vector<HostOp> out;
     std::vector<char> alive;
@@ -858,6 +861,17 @@ static void rewrite_ops(std::vector<HostOp>& ops)
     auto emit_phase1 = [&](int b, int val, double px, double py) {
         if (px == 1.0 && py == 0.0) {
             return;
+        }
+        const double pn = px * px + py * py;
+        if (val == 0 && pn > 0.0 && (hist[b].empty() || out[(size_t)hist[b].back()].kind != OP_GENERAL || out[(size_t)hist[b].back()].tq != b)) {
+            // phase on (b = 0)  =  global scalar p  x  phase 1/p on (b = 1): the kernel's register-bit predicates ask for value 1
+            const double nx = gx * px - gy * py;
+            gy = gx * py + gy * px;
+            gx = nx;
+            val = 1;
+            const double ix = px / pn, iy = -py / pn;
+            px = ix;
+            py = iy;
         }
         if (!hist[b].empty()) {
             HostOp& p = out[(size_t)hist[b].back()];
@@ -955,11 +969,42 @@ static void rewrite_ops(std::vector<HostOp>& ops)
     };
     static const double HS = 0.70710678118654752440;
     static const double HM[8] = { HS, 0, HS, 0, HS, 0, -HS, 0 };
-    for (const HostOp& op : ops) {
-        if (op.kind == OP_XSWAP && !op.cmask && (hist[op.tq].empty() || out[(size_t)hist[op.tq].back()].kind != OP_HAD ||
-                                                    out[(size_t)hist[op.tq].back()].tq != op.tq)) {
-            emit_u1(op.tq, op.m); // bare X next to a general gate (or to nothing): multiply / leave as a swap
-        } else if (op.kind == OP_XSWAP) { // R1
+    static const double XM[8] = { 0, 0, 1, 0, 1, 0, 0, 0 };
+    // R4: a bare X travels forward through everything that uses its qubit only as a control / phase predicate (the predicate's
+    // polarity flips), and two of them cancel.  QInterface::MACWrapper (include/qinterface.hpp:179-189) wraps every anti-controlled
+    // gate in XMask ... XMask: here that costs nothing instead of two sweeps.
+    uint64_t xpend = 0;
+    auto emit_bare_x = [&](int q) {
+        if (hist[q].empty() || out[(size_t)hist[q].back()].kind != OP_HAD || out[(size_t)hist[q].back()].tq != q) {
+            emit_u1(q, XM); // next to a general gate (or to nothing): multiply / leave as a swap
+        } else { // H X = Z-conjugate: H . (H Z H) -> Z H
+            emit_u1(q, HM);
+            emit_phase1(q, 1, -1.0, 0.0);
+            emit_u1(q, HM);
+        }
+    };
+    for (const HostOp& op0 : ops) {
+        HostOp op = op0;
+        op.cval ^= (op.cmask & xpend);
+        if (op.kind == OP_XSWAP && !op.cmask) {
+            xpend ^= bitq(op.tq);
+            continue;
+        }
+        if (op.tq >= 0 && (xpend & bitq(op.tq))) {
+            xpend &= ~bitq(op.tq);
+            if (is_u1(op) && op.kind == OP_HAD) {
+                emit_u1(op.tq, op.m); // X then H  =  H then Z
+                emit_phase1(op.tq, 1, -1.0, 0.0);
+                continue;
+            }
+            if (is_u1(op)) { // M . X: columns swapped
+                double mx[8] = { op.m[2], op.m[3], op.m[0], op.m[1], op.m[6], op.m[7], op.m[4], op.m[5] };
+                emit_u1(op.tq, mx);
+                continue;
+            }
+            emit_bare_x(op.tq); // a controlled op on that target: the X has to be applied first
+        }
+        if (op.kind == OP_XSWAP) { // R1 (controlled X)
             emit_u1(op.tq, HM);
             HostOp z;
             memset(&z, 0, sizeof(z));
@@ -968,11 +1013,7 @@ static void rewrite_ops(std::vector<HostOp>& ops)
             z.cmask = op.cmask | bitq(op.tq);
             z.cval = op.cval | bitq(op.tq);
             z.m[0] = -1.0;
-            if (!op.cmask) {
-                emit_phase1(op.tq, 1, -1.0, 0.0);
-            } else {
-                push(z);
-            }
+            push(z);
             emit_u1(op.tq, HM);
         } else if (is_u1(op)) {
             emit_u1(op.tq, op.m);
@@ -984,6 +1025,14 @@ static void rewrite_ops(std::vector<HostOp>& ops)
             gx = nx;
         } else {
             push(op);
+        }
+    }
+    uint64_t xtail = 0;
+    if (__builtin_popcountll(xpend) > 4) {
+        xtail = xpend; // a wide XMask that nothing absorbed: one dedicated permutation sweep beats that many fused swaps
+    } else {
+        for (uint64_t m = xpend; m; m &= m - 1U) {
+            emit_bare_x(__builtin_ctzll(m));
         }
     }
     std::vector<HostOp> res;
@@ -1003,6 +1052,7 @@ static void rewrite_ops(std::vector<HostOp>& ops)
         res.push_back(h);
     }
     ops.swap(res);
+    return xtail;
 }
 
 struct TileCfg {
@@ -2033,11 +2083,11 @@ int fused_flush(State* s)
         return B200SV_OK;
     }
     std::vector<HostOp> pending;
-    lower_queue(s->queue, pending);
+    const uint64_t xtail = lower_queue(s->queue, pending);
     const size_t nGates = s->queue.size();
     s->queue.clear();
     if (pending.empty()) {
-        return B200SV_OK;
+        return xtail ? launch_xmask(s, xtail) : B200SV_OK;
     }
     const TileCfg cfg = state_cfg(s->nq, s->prec);
     Arena* ar = get_arena(s);
@@ -2101,6 +2151,9 @@ int fused_flush(State* s)
     s->stats.fused_gates += nGates;
     SV_CUDA(cudaEventRecord(ar->done, s->stream));
     ar->pending = true;
+    if (xtail) {
+        SV_TRY(launch_xmask(s, xtail));
+    }
     return B200SV_OK;
 }
 
@@ -2372,7 +2425,7 @@ template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<
 int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state)
 {
     std::vector<HostOp> pending;
-    lower_queue(q, pending);
+    const uint64_t xtail = lower_queue(q, pending);
     const TileCfg cfg = state_cfg(n_qubits, precision);
     std::vector<unsigned char> buf;
     while (!pending.empty()) {
@@ -2384,6 +2437,20 @@ int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, voi
             emulate_sweep<float>(buf.data(), reinterpret_cast<EmuC<float>*>(host_state), n_qubits, cfg);
         } else {
             emulate_sweep<double>(buf.data(), reinterpret_cast<EmuC<double>*>(host_state), n_qubits, cfg);
+        }
+    }
+    if (xtail) { // the trailing XMask sweep (launch_xmask on the device)
+        const uint64_t dim = 1ULL << n_qubits;
+        const size_t ab = (precision == 32) ? 8 : 16;
+        unsigned char* st = reinterpret_cast<unsigned char*>(host_state);
+        unsigned char tmp[16];
+        for (uint64_t i = 0; i < dim; ++i) {
+            const uint64_t j = i ^ xtail;
+            if (i < j) {
+                memcpy(tmp, st + i * ab, ab);
+                memcpy(st + i * ab, st + j * ab, ab);
+                memcpy(st + j * ab, tmp, ab);
+            }
         }
     }
     return B200SV_OK;
@@ -2420,7 +2487,7 @@ int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targ
         }
     }
     std::vector<HostOp> pending;
-    lower_queue(q, pending);
+    (void)lower_queue(q, pending);
     const TileCfg cfg = state_cfg(n_qubits, precision);
     int sweeps = 0, passes = 0;
     std::vector<unsigned char> buf;

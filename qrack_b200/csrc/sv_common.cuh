@@ -126,6 +126,7 @@ int sm_count(int dev);
 
 // fused.cu
 int fused_flush(State* s);
+int launch_xmask(State* s, uint64_t mask); // the dedicated XMask permutation sweep (b200sv.cu); does not flush
 bool fused_accepts(const State* s, const GateOp& g);
 void fused_release(State* s);
 int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state);

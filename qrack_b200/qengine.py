@@ -1259,6 +1259,10 @@ class _CudaBackend:
         self._ck(self.lib.b200sv_apply2x2(self.h, off1, off2, m8, len(pows), pw, nrm, thresh, None))
         return None
 
+    def apply_gates(self, n, off1, off2, pmasks, mats8):
+        """b200sv_apply_gates: n single-target Apply2x2 forms (ctypes arrays) in one ABI call"""
+        self._ck(self.lib.b200sv_apply_gates(self.h, n, off1, off2, pmasks, mats8))
+
     def xmask(self, mask):
         self._ck(self.lib.b200sv_xmask(self.h, mask))
 
@@ -1403,6 +1407,20 @@ class QEngineCUDA(QEngineHost):
         q.qubitCount = n_qubits
         q.runningNorm = REAL1_DEFAULT_ARG
         return q
+
+    def RunCircuit(self, circuit):
+        """Whole-circuit submission: the recorded single-target gates of a ``qcircuit.QCircuit`` go through
+        ``b200sv_apply_gates`` in one ABI call.  Same effect as ``circuit.Run`` gate by gate (QCircuit::Run,
+        src/qcircuit.cpp:173-281); needs doNormalize off (QPager/QUnit create their engines that way)."""
+        if self.doNormalize:
+            raise ValueError("QEngineCUDA::RunCircuit: doNormalize engines take their gates one by one (running-norm bookkeeping)")
+        if circuit.GetQubitCount() != self.qubitCount or circuit.precision != self.precision:
+            raise ValueError("QEngineCUDA::RunCircuit: circuit width / precision differs from the engine's")
+        if self.be.is_zero():
+            return
+        n, o1, o2, pm, m8 = circuit.packed()
+        if n:
+            self.be.apply_gates(n, o1, o2, pm, m8)
 
     def SetDevice(self, dID: int):
         import ctypes

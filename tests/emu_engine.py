@@ -18,7 +18,7 @@ class _EmuBackend(_RestateBackend):
         self.queue = []
         self.flushes = 0
         for name in dir(_RestateBackend):
-            if name.startswith("_") or name in ("apply2x2", "fn", "finish"):
+            if name.startswith("_") or name in ("apply2x2", "fn", "finish", "xmask"):
                 continue
             attr = getattr(self, name)
             if callable(attr):
@@ -43,6 +43,17 @@ class _EmuBackend(_RestateBackend):
             pmask |= p
         self.queue.append((off1, off2, pmask, [complex(z) * nrm for z in mtrx]))
         return None
+
+    def xmask(self, mask):
+        # like b200sv_xmask with fusion on: queued as X gates (the rewrite turns XMask..XMask wrappers into control polarities)
+        if self.nq < 5 or self.amps is None:
+            self.flush()
+            return super().xmask(mask)
+        b = 0
+        while mask >> b:
+            if (mask >> b) & 1:
+                self.queue.append((0, 1 << b, 1 << b, [0j, 1 + 0j, 1 + 0j, 0j]))
+            b += 1
 
     def flush(self):
         if not self.queue:

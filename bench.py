@@ -394,6 +394,27 @@ def main():
         probs = [q.Prob(b) for b in range(n)]
         e2e_steps.append(time.perf_counter() - t0)
     barrier()
+    # the same end-to-end step with whole-circuit submission (QCircuit.Run -> b200sv_apply_gates: one ABI call per step)
+    e2e_batched = None
+    if not sharded:
+        try:
+            from qrack_b200 import QCircuit
+            circ = QCircuit(n, prec)
+            for name, a in calls:
+                getattr(circ, name)(*a)
+            circ.packed()
+            tb = []
+            for _ in range(args.steps):
+                t0 = time.perf_counter()
+                q.SetPermutation(0, 1.0 + 0j)
+                circ.Run(q)
+                probs_b = [q.Prob(b) for b in range(n)]
+                tb.append(time.perf_counter() - t0)
+            agree = max(abs(x - y) for x, y in zip(probs, probs_b))
+            e2e_batched = {"value": gates * args.steps / sum(tb), "unit": "gates/s", "abi_calls_per_step": 1,
+                           "recorded_apply2x2_forms": circ.GetGateCount(), "max_prob_diff_vs_per_gate_path": agree}
+        except NotImplementedError as e:
+            e2e_batched = {"unavailable": str(e)[:160]}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -473,6 +494,8 @@ def main():
                                 "sweeps_per_step": stats["fused_sweeps"] / max(1, args.steps)}
         if check is not None:
             line["check"] = check
+        if e2e_batched is not None:
+            line["e2e_batched"] = e2e_batched
         if world == 1 and stats["fused_sweeps"]:
             line["roofline"]["fused_single_qubit_sweep"] = fused_single_qubit_sweep_probe(q, n, amp_bytes, peak)
         if world == 1 and not args.skip_cpu_baseline:

@@ -133,6 +133,16 @@ class _RestateBackend:
                                 self.creal(nrm), self.creal(thresh), ctypes.byref(out) if calc_norm else None)
         return out.value if calc_norm else None
 
+    def apply_gates(self, n, off1, off2, pmasks, mats8):
+        """same call shape as the CUDA backend's batched submission (b200sv_apply_gates): here simply gate by gate"""
+        for i in range(n):
+            pm = int(pmasks[i])
+            pows = [1 << b for b in range(pm.bit_length()) if (pm >> b) & 1]
+            m = [complex(mats8[8 * i + 2 * k], mats8[8 * i + 2 * k + 1]) for k in range(4)]
+            if self.precision == 32:
+                m = [complex(np.float32(z.real), np.float32(z.imag)) for z in m]
+            self.apply2x2(int(off1[i]), int(off2[i]), m, pows, 1.0, 0.0, False)
+
     def xmask(self, mask):
         self.fn("orc_xmask")(self._p(), c_int(self.nq), c_uint64(mask))
 

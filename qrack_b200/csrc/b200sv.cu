@@ -413,6 +413,150 @@ __global__ void __launch_bounds__(256) k_prob_all_bits(const typename Cx<R>::typ
     }
 }
 
+
+// r2 version of the marginals sweep: coalesced 128-bit streaming loads and O(1) work per chunk.
+// The state is 2^cl 16-byte chunks (fp32: amplitudes 2c, 2c+1; fp64: amplitude c).  Thread gid of a power-of-two grid reads
+// chunk  it * T + gid  (T = total threads) for it = 0 .. 2^itBits - 1, so the chunk-index bits are, from the bottom: lane (5),
+// warp (3), block (gBits), iteration (itBits).  Only the iteration bits vary inside a thread: their marginals come from a
+// binary-counter (pairwise) summation — level b holds the sum of the last 2^b chunks with iteration bit b clear; when bit b
+// is set the running value joins A[b] and absorbs the carry — amortised two float adds per chunk, uniform control flow across
+// the whole grid (it depends on `it` only), and pairwise accuracy.  Lane / warp / block bits are resolved once at the end from
+// the per-thread totals.  HBM traffic = one read of the state.
+template <typename R, int MAXB>
+__global__ void __launch_bounds__(256) k_prob_all_bits2(const typename Cx<R>::type* __restrict__ psi, int itBits, int gBits, int nq,
+    double* __restrict__ out)
+{
+    constexpr int APCLOG = (sizeof(R) == 4) ? 1 : 0;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t gid = (uint64_t)blockIdx.x * 256U + tid;
+    const uint64_t T = (uint64_t)256U << gBits;
+    const uint4* base = reinterpret_cast<const uint4*>(psi);
+    float A[MAXB], carry[MAXB];
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+        A[b] = 0.f;
+        carry[b] = 0.f;
+    }
+    float a0 = 0.f, total = 0.f;
+    const uint32_t nIt = 1U << itBits;
+    for (uint32_t it0 = 0; it0 < nIt; it0 += 2) {
+        // two independent loads in flight per thread
+        const uint4 c0 = __ldcs(base + ((uint64_t)it0 * T + gid));
+        uint4 c1 = make_uint4(0, 0, 0, 0);
+        const bool two = (it0 + 1U) < nIt;
+        if (two) {
+            c1 = __ldcs(base + ((uint64_t)(it0 + 1U) * T + gid));
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) {
+                break;
+            }
+            const uint4 c = u ? c1 : c0;
+            float v;
+            if (APCLOG) {
+                const float x0 = __uint_as_float(c.x), y0 = __uint_as_float(c.y), x1 = __uint_as_float(c.z), y1 = __uint_as_float(c.w);
+                const float p1 = x1 * x1 + y1 * y1;
+                a0 += p1;
+                v = (x0 * x0 + y0 * y0) + p1;
+            } else {
+                const double x = __hiloint2double((int)c.y, (int)c.x), y = __hiloint2double((int)c.w, (int)c.z);
+                v = (float)(x * x + y * y);
+            }
+            const uint32_t it = it0 + (uint32_t)u;
+            bool done = false;
+#pragma unroll
+            for (int b = 0; b < MAXB; ++b) {
+                if (b < itBits && !done) {
+                    if ((it >> b) & 1U) {
+                        A[b] += v;
+                        v += carry[b];
+                    } else {
+                        carry[b] = v;
+                        done = true;
+                    }
+                }
+            }
+            if (!done) {
+                total = v; // it = 2^itBits - 1: every level has been folded in
+            }
+        }
+    }
+    // ---- per-thread results -> marginals.  Values reduced over the CTA: [0] total, [1] a0, [2 .. 2+itBits) A[b],
+    // [2+MAXB .. +5) lane-bit sums, then warp-bit sums are formed from the per-warp totals.
+    __shared__ double red[8][2 + MAXB + 5];
+    const int lane = tid & 31, warp = tid >> 5;
+    auto wsum = [](double v) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            v += __shfl_xor_sync(0xffffffffU, v, d);
+        }
+        return v;
+    };
+    {
+        const double t = wsum((double)total), z = wsum((double)a0);
+        if (lane == 0) {
+            red[warp][0] = t;
+            red[warp][1] = z;
+        }
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) {
+            if (b < itBits) {
+                const double v = wsum((double)A[b]);
+                if (lane == 0) {
+                    red[warp][2 + b] = v;
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            const double v = wsum(((lane >> d) & 1) ? (double)total : 0.0);
+            if (lane == 0) {
+                red[warp][2 + MAXB + d] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const int j = (int)tid;
+    if (j < 2 + MAXB + 5 + 3) {
+        double v = 0.0;
+        int qubit = -1; // -1: nothing, 64: total
+        if (j < 2 + MAXB + 5) {
+            for (int w = 0; w < 8; ++w) {
+                v += red[w][j];
+            }
+            if (j == 0) {
+                qubit = 64;
+            } else if (j == 1) {
+                qubit = APCLOG ? 0 : -1;
+            } else if (j < 2 + MAXB) {
+                qubit = (j - 2 < itBits) ? (APCLOG + 8 + gBits + (j - 2)) : -1;
+            } else {
+                qubit = APCLOG + (j - 2 - MAXB);
+            }
+        } else {
+            const int wb = j - (2 + MAXB + 5); // warp bit
+            for (int w = 0; w < 8; ++w) {
+                if ((w >> wb) & 1) {
+                    v += red[w][0];
+                }
+            }
+            qubit = APCLOG + 5 + wb;
+        }
+        if (qubit >= 0 && (qubit == 64 || qubit < nq)) {
+            atomicAdd(out + qubit, v);
+        }
+        if (j == 0) {
+            // block bits: this CTA's total counts for every block-index bit that is set
+            for (int g = 0; g < gBits; ++g) {
+                if ((blockIdx.x >> g) & 1U) {
+                    atomicAdd(out + (APCLOG + 8 + g), v);
+                }
+            }
+        }
+    }
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256) k_prob_mask(const typename Cx<R>::type* __restrict__ psi, uint64_t n, uint64_t mask,
     uint64_t perm, double* out)
@@ -2029,9 +2173,22 @@ int b200sv_prob_mask(b200sv_t s, uint64_t mask, uint64_t perm, double* out)
         // such as QUnit or a measurement loop ask for many qubits between two state changes)
         if (!s->margValid) {
             SV_CUDA(cudaMemsetAsync(s->d_scratch, 0, 65 * sizeof(double), s->stream));
-            const unsigned grid = std::min<unsigned>(stream_grid(s->dev, n >> 3, 256), (unsigned)sm_count(s->dev) * 8U);
-            DISPATCH_PREC(s, (k_prob_all_bits<float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, n, s->nq, s->d_scratch)),
-                (k_prob_all_bits<double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, n, s->nq, s->d_scratch)));
+            const int cl = s->nq - (s->prec == 32 ? 1 : 0); // log2 of the number of 16-byte chunks
+            if (cl >= 14) {
+                // coalesced version: power-of-two grid, at least 4 and at most 2^20 chunks per thread
+                int gBits = std::min(cl - 8 - 2, 11);
+                const int itBits = cl - 8 - gBits;
+                if (itBits > 20) {
+                    gBits += itBits - 20;
+                }
+                const int itB = cl - 8 - gBits;
+                DISPATCH_PREC(s, (k_prob_all_bits2<float, 20><<<1U << gBits, 256, 0, s->stream>>>((const float2*)s->amps, itB, gBits, s->nq, s->d_scratch)),
+                    (k_prob_all_bits2<double, 20><<<1U << gBits, 256, 0, s->stream>>>((const double2*)s->amps, itB, gBits, s->nq, s->d_scratch)));
+            } else {
+                const unsigned grid = std::min<unsigned>(stream_grid(s->dev, n >> 3, 256), (unsigned)sm_count(s->dev) * 8U);
+                DISPATCH_PREC(s, (k_prob_all_bits<float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, n, s->nq, s->d_scratch)),
+                    (k_prob_all_bits<double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, n, s->nq, s->d_scratch)));
+            }
             SV_CUDA(cudaGetLastError());
             s->stats.kernel_launches++;
             SV_TRY(read_scratch(s, 65));

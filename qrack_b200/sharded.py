@@ -228,6 +228,7 @@ class _ShardedBackend:
         self.exchanges = 0
         self.exchange_bytes = 0
         self.local_swaps = 0
+        self._batch = []  # local single-target gates waiting for ONE b200sv_apply_gates call
 
     # ---- helpers ------------------------------------------------------------------------------------------------
     @property
@@ -513,11 +514,42 @@ class _ShardedBackend:
                 deferred.append(g)
                 blocked_t |= uses_t
                 blocked_d |= uses_d
+            self._submit_batch()
             if not deferred:
                 break
             # the first deferred gate is blocked only by its rank-bit target: after the exchange it can run
             self._exchange(deferred, 0)
             ops = deferred
+
+    def _local_gate(self, ctrls, cperm, m, pt):
+        """UCMtrx(ctrls, m, pt, cperm) on the local engine; batched when its backend takes whole gate lists"""
+        be = getattr(self.loc, "be", None)
+        if be is None or not hasattr(be, "apply_gates"):
+            self.loc.UCMtrx(ctrls, m, pt, cperm)
+            return
+        off1, pmask = 0, 1 << pt
+        for j, c in enumerate(ctrls):
+            pmask |= 1 << c
+            if (cperm >> j) & 1:
+                off1 |= 1 << c
+        self._batch.append((off1, off1 | (1 << pt), pmask, m))
+
+    def _submit_batch(self):
+        g, self._batch = self._batch, []
+        if not g:
+            return
+        import ctypes
+        n = len(g)
+        m8 = (ctypes.c_double * (8 * n))()
+        k = 0
+        for x in g:
+            for z in x[3]:
+                z = complex(z)
+                m8[k] = z.real
+                m8[k + 1] = z.imag
+                k += 2
+        self.loc.be.apply_gates(n, (ctypes.c_uint64 * n)(*[x[0] for x in g]), (ctypes.c_uint64 * n)(*[x[1] for x in g]),
+                                (ctypes.c_uint64 * n)(*[x[2] for x in g]), m8)
 
     def _run_local(self, g: _Gate):
         nl = self.nl
@@ -534,7 +566,7 @@ class _ShardedBackend:
                 ctrls.append(pc)
         pt = self.perm[g.t]
         if pt < nl:
-            self.loc.UCMtrx(ctrls, g.m, pt, cperm)
+            self._local_gate(ctrls, cperm, g.m, pt)
             return
         # diagonal gate on a rank-bit qubit: this rank sees one diagonal entry
         d = g.m[3] if ((self.rank >> (pt - nl)) & 1) else g.m[0]
@@ -546,9 +578,9 @@ class _ShardedBackend:
             want_last = (cperm >> (len(ctrls) - 1)) & 1
             rest_perm = cperm & ((1 << (len(ctrls) - 1)) - 1)
             m = [1 + 0j, 0j, 0j, d] if want_last else [d, 0j, 0j, 1 + 0j]
-            self.loc.UCMtrx(ctrls[:-1], m, last, rest_perm)
+            self._local_gate(ctrls[:-1], rest_perm, m, last)
         else:
-            self.loc.Mtrx([d, 0j, 0j, d], 0)
+            self._local_gate([], 0, [d, 0j, 0j, d], 0)
 
     def _exchange(self, ops: List[_Gate], i: int):
         """make every rank-bit qubit local: all k rank bits <-> top k local bits, victims chosen by Belady's rule"""

@@ -8,6 +8,8 @@
 // the SM count, on-device final reductions with double atomics, no per-gate host synchronisation).
 #include "sv_common.cuh"
 
+#include <type_traits>
+
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -431,13 +433,14 @@ __global__ void __launch_bounds__(256) k_prob_all_bits2(const typename Cx<R>::ty
     const uint64_t gid = (uint64_t)blockIdx.x * 256U + tid;
     const uint64_t T = (uint64_t)256U << gBits;
     const uint4* base = reinterpret_cast<const uint4*>(psi);
-    float A[MAXB], carry[MAXB];
+    typedef typename std::conditional<sizeof(R) == 4, float, double>::type Acc; // fp64 states keep their 1e-12 parity bar
+    Acc A[MAXB], carry[MAXB];
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) {
-        A[b] = 0.f;
-        carry[b] = 0.f;
+        A[b] = 0;
+        carry[b] = 0;
     }
-    float a0 = 0.f, total = 0.f;
+    Acc a0 = 0, total = 0;
     const uint32_t nIt = 1U << itBits;
     for (uint32_t it0 = 0; it0 < nIt; it0 += 2) {
         // two independent loads in flight per thread
@@ -453,15 +456,15 @@ __global__ void __launch_bounds__(256) k_prob_all_bits2(const typename Cx<R>::ty
                 break;
             }
             const uint4 c = u ? c1 : c0;
-            float v;
+            Acc v;
             if (APCLOG) {
                 const float x0 = __uint_as_float(c.x), y0 = __uint_as_float(c.y), x1 = __uint_as_float(c.z), y1 = __uint_as_float(c.w);
                 const float p1 = x1 * x1 + y1 * y1;
-                a0 += p1;
-                v = (x0 * x0 + y0 * y0) + p1;
+                a0 += (Acc)p1;
+                v = (Acc)((x0 * x0 + y0 * y0) + p1);
             } else {
                 const double x = __hiloint2double((int)c.y, (int)c.x), y = __hiloint2double((int)c.w, (int)c.z);
-                v = (float)(x * x + y * y);
+                v = (Acc)(x * x + y * y);
             }
             const uint32_t it = it0 + (uint32_t)u;
             bool done = false;

@@ -65,3 +65,66 @@ def test_sharded_nccl_matches_oracle(prec, p2p, tmp_path):
     d = float(np.abs(z["state"].astype(np.complex128) - want[0].astype(np.complex128)).max())
     assert d <= util.AMP_TOL[prec], d
     assert int(z["exchanges"]) >= 1
+
+
+def _worker_queries(rank, world, port, text, prec, out_path):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from qrack_b200.sharded import QEngineSharded, cuda_engine_factory
+
+        def make(n, perm):
+            return QEngineSharded(n, perm, random.Random(1), 1.0 + 0j, precision=prec, dist=dist, world=world, rank=rank,
+                                  device=torch.device("cuda", rank), make_engine=cuda_engine_factory(rank, prec), p2p=True)
+        regs, results = qscript.run(text, make)
+        q = regs[0]
+        q.UpdateRunningNorm()
+        nrm = q.GetRunningNorm()
+        perm = q.MAll()                       # on-device sampling across the shards, then collapse
+        amp = q.GetAmplitude(perm)
+        if rank == 0:
+            np.savez(out_path, results=np.array([v for _, vals in results for v in vals], dtype=np.float64), norm=nrm, perm=perm,
+                     amp=abs(amp), exchanges=q.be.exchanges)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["htcnot", "qv", "grover"])
+def test_sharded_26q_against_the_compiled_reference(kind, tmp_path):
+    """BASELINE.md §3 'Parity': the sharded path at 26 qubits over every GPU of the box (8 ranks on the 8-GPU box) against the
+    compiled reference QEngineCPU: all per-qubit Prob, 48 sampled amplitudes (1e-6), the norm, and a sharded MAll."""
+    ng = _ngpu()
+    if ng < 2 or util.ref_harness(32) is None:
+        pytest.skip("needs >= 2 GPUs and oracle/_ref")
+    world = 8 if ng >= 8 else (4 if ng >= 4 else 2)
+    n = 26
+    rng = random.Random(5)
+    text = {"htcnot": lambda: qscript.random_htcnot(n, 6, seed=12, timed=False),
+            "qv": lambda: qscript.quantum_volume(n, depth=4, seed=13, timed=False),
+            "grover": lambda: "\n".join(l for l in qscript.grover(n, 1, target=3, timed=False).splitlines() if not l.startswith("ProbAll")) + "\n"}[kind]()
+    idx = sorted(rng.randrange(1 << n) for _ in range(48)) + [3]
+    text += "".join("Prob %d\n" % q for q in range(n)) + "".join("GetAmplitude %d\n" % i for i in idx)
+    import subprocess
+    sp = tmp_path / "s.qs"
+    sp.write_text(text)
+    subprocess.run([util.ref_harness(32), str(sp), "--results", str(tmp_path / "r.txt")], check=True, timeout=1200)
+    want = np.array([v for _, vals in qscript.parse_results(open(str(tmp_path / "r.txt")).read()) for v in vals], dtype=np.float64)
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "o.npz")
+    for attempt in range(3):
+        try:
+            mp.spawn(_worker_queries, args=(world, _free_port(), text, 32, out), nprocs=world, join=True)
+            break
+        except Exception as e:
+            if "EADDRINUSE" not in str(e) or attempt == 2:
+                raise
+    z = np.load(out)
+    got = z["results"]
+    assert got.shape == want.shape
+    assert np.abs(got[:n] - want[:n]).max() <= 2e-5          # Prob: fp32 reductions of 2^25 terms on both sides
+    assert np.abs(got[n:] - want[n:]).max() <= util.AMP_TOL[32]   # amplitudes (re, im pairs)
+    assert abs(float(z["norm"]) - 1.0) < 1e-4 and float(z["amp"]) > 0.999

@@ -103,6 +103,12 @@ public:
     real1_f ProbMask(const bitCapInt& mask, const bitCapInt& permutation) override;
     void ProbMaskAll(const bitCapInt& mask, real1* probsArray) override;
     void ProbRegAll(bitLenInt start, bitLenInt length, real1* probsArray) override;
+    // the QInterface default walks all 2^n basis states on the host (src/qinterface/qinterface.cpp:446-476)
+    void ProbBitsAll(const std::vector<bitLenInt>& bits, real1* probsArray) override;
+    // QEngine's versions (src/qengine/qengine.cpp:542-609) build the 2^k histogram first; with many measured qubits the
+    // shots are sampled as basis states on the device instead (b200sv_sample_many) — same distribution
+    std::map<bitCapInt, int> MultiShotMeasureMask(const std::vector<bitCapInt>& qPowers, unsigned shots) override;
+    void MultiShotMeasureMask(const std::vector<bitCapInt>& qPowers, unsigned shots, unsigned long long* shotsArray) override;
     real1_f ProbParity(const bitCapInt& mask) override;
     bool ForceMParity(const bitCapInt& mask, bool result, bool doForce = true) override;
     bitCapInt MAll() override;

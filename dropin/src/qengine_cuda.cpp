@@ -571,6 +571,115 @@ void QEngineCUDA::ProbRegAll(bitLenInt start, bitLenInt length, real1* probsArra
     ProbMaskAll(bitCapInt(bitRegMaskOcl(start, length)), probsArray);
 }
 
+void QEngineCUDA::ProbBitsAll(const std::vector<bitLenInt>& bits, real1* probsArray)
+{
+    ThrowIfQbIdArrayIsBad(bits, qubitCount, "QEngineCUDA::ProbBitsAll parameter bits array values must be within allocated qubit bounds!");
+    // one device sweep: histogram over the mask in ascending qubit order, then the host permutes its 2^k entries
+    bitCapIntOcl mask = 0U;
+    for (const bitLenInt& b : bits) {
+        mask |= pow2Ocl(b);
+    }
+    std::vector<bitLenInt> order(bits);
+    std::sort(order.begin(), order.end());
+    const bitCapIntOcl len = pow2Ocl(bits.size());
+    if (order == bits) {
+        ProbMaskAll(bitCapInt(mask), probsArray);
+        return;
+    }
+    std::vector<real1> asc((size_t)len);
+    ProbMaskAll(bitCapInt(mask), asc.data());
+    std::vector<bitLenInt> pos(bits.size());
+    for (size_t p = 0U; p < bits.size(); ++p) {
+        pos[p] = (bitLenInt)(std::find(order.begin(), order.end(), bits[p]) - order.begin());
+    }
+    for (bitCapIntOcl i = 0U; i < len; ++i) {
+        bitCapIntOcl src = 0U;
+        for (size_t p = 0U; p < bits.size(); ++p) {
+            if ((i >> p) & 1U) {
+                src |= pow2Ocl(pos[p]);
+            }
+        }
+        probsArray[i] = asc[(size_t)src];
+    }
+}
+
+static void SampleShots(QEngineCUDA* eng, b200sv_t sv, const std::vector<bitCapInt>& qPowers, unsigned shots, bitLenInt qubitCount,
+    std::vector<bitCapIntOcl>& keys)
+{
+    std::vector<bitLenInt> bitMap(qPowers.size());
+    std::transform(qPowers.begin(), qPowers.end(), bitMap.begin(), log2);
+    ThrowIfQbIdArrayIsBad(bitMap, qubitCount,
+        "QInterface::MultiShotMeasureMask parameter qPowers array values must be within allocated qubit bounds!");
+    keys.assign(shots, 0U);
+    std::vector<double> rnds(shots);
+    for (unsigned i = 0U; i < shots; ++i) {
+        rnds[i] = (double)eng->Rand();
+    }
+    if (bitMap.size() <= 16U) {
+        // few measured qubits: the 2^k histogram in one sweep, host draws (what QEngine::MultiShotMeasureMask does)
+        const bitCapIntOcl len = pow2Ocl(bitMap.size());
+        std::vector<real1> probs((size_t)len);
+        eng->ProbBitsAll(bitMap, probs.data());
+        std::vector<double> cum((size_t)len);
+        double tot = 0;
+        for (bitCapIntOcl i = 0U; i < len; ++i) {
+            tot += (double)probs[(size_t)i];
+            cum[(size_t)i] = tot;
+        }
+        for (unsigned i = 0U; i < shots; ++i) {
+            const double r = rnds[i] * tot;
+            bitCapIntOcl k = (bitCapIntOcl)(std::upper_bound(cum.begin(), cum.end(), r) - cum.begin());
+            keys[i] = (k < len) ? k : (len - 1U);
+        }
+        return;
+    }
+    std::vector<uint64_t> perms(shots);
+    if (b200sv_sample_many(sv, (int)shots, rnds.data(), perms.data()) != B200SV_OK) {
+        throw std::runtime_error(std::string("QEngineCUDA::MultiShotMeasureMask: ") + b200sv_last_error());
+    }
+    for (unsigned i = 0U; i < shots; ++i) {
+        bitCapIntOcl key = 0U;
+        for (size_t p = 0U; p < bitMap.size(); ++p) {
+            if ((perms[i] >> bitMap[p]) & 1U) {
+                key |= pow2Ocl(p);
+            }
+        }
+        keys[i] = key;
+    }
+}
+
+std::map<bitCapInt, int> QEngineCUDA::MultiShotMeasureMask(const std::vector<bitCapInt>& qPowers, unsigned shots)
+{
+    std::map<bitCapInt, int> results;
+    if (!shots) {
+        return results;
+    }
+    if (doNormalize) {
+        NormalizeState();
+    }
+    std::vector<bitCapIntOcl> keys;
+    SampleShots(this, sv, qPowers, shots, qubitCount, keys);
+    for (const bitCapIntOcl& k : keys) {
+        ++results[bitCapInt(k)];
+    }
+    return results;
+}
+
+void QEngineCUDA::MultiShotMeasureMask(const std::vector<bitCapInt>& qPowers, unsigned shots, unsigned long long* shotsArray)
+{
+    if (!shots) {
+        return;
+    }
+    if (doNormalize) {
+        NormalizeState();
+    }
+    std::vector<bitCapIntOcl> keys;
+    SampleShots(this, sv, qPowers, shots, qubitCount, keys);
+    for (unsigned i = 0U; i < shots; ++i) {
+        shotsArray[i] = (unsigned long long)keys[i];
+    }
+}
+
 real1_f QEngineCUDA::ProbParity(const bitCapInt& mask)
 {
     if (mask >= maxQPower) {

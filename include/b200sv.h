@@ -126,6 +126,10 @@ int b200sv_expectation(b200sv_t s, int start, int length, double* out);
 int b200sv_highest_prob(b200sv_t s, uint64_t* perm);
 /* smallest index i with cumulative sum_{j<=i} |psi[j]|^2 > rnd, or the last index with |psi|^2>0 (MAll :2026-2050) */
 int b200sv_sample(b200sv_t s, double rnd, uint64_t* perm);
+/* n_shots samples of the whole register WITHOUT collapse in one call (MultiShotMeasureMask, src/qengine/qengine.cpp:542-609:
+ * the k measured bits are read off each sampled basis state — same distribution as drawing from the 2^k histogram);
+ * rnds[i] in [0,1) -> perms[i] = first index whose cumulative probability exceeds rnds[i] (MAll's search). */
+int b200sv_sample_many(b200sv_t s, int n_shots, const double* rnds, uint64_t* perms);
 
 /* ---- structure (state.cpp:1271-1748; utility.cpp:54-68) ---- */
 /* a <- a (x) b with b's qubits inserted at `start` (Compose :1368-1459; start==n_a is the append form :1271-1362) */

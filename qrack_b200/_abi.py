@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200sv_expectation": [H, c_int, c_int, POINTER(c_double)],
     "b200sv_highest_prob": [H, POINTER(c_uint64)],
     "b200sv_sample": [H, c_double, POINTER(c_uint64)],
+    "b200sv_sample_many": [H, c_int, POINTER(c_double), POINTER(c_uint64)],
     "b200sv_compose": [H, H, c_int],
     "b200sv_decompose": [H, c_int, c_int, H],
     "b200sv_dispose_perm": [H, c_int, c_int, c_uint64],

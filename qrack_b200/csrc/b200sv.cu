@@ -1036,12 +1036,46 @@ static int read_scratch(State* s, int count)
     return B200SV_OK;
 }
 
+template <typename R>
+static int launch_apply2x2(State* s, uint64_t off1, uint64_t off2, const double* m8, int nb, const uint64_t* pows, double nrm, double thresh,
+    double* normOutDev);
+
+// A queued gate back in its (offset1, offset2, powers) form on the generic kernel
+static int run_gate_unfused(State* s, const GateOp& g)
+{
+    uint64_t pows[64];
+    int nb = 0;
+    const uint64_t pmask = g.cmask | (1ULL << g.target);
+    for (uint64_t m = pmask; m; m &= m - 1U) {
+        pows[nb++] = m & (~m + 1U);
+    }
+    const uint64_t off1 = g.cval, off2 = g.cval | (1ULL << g.target);
+    return (s->prec == 32) ? launch_apply2x2<float>(s, off1, off2, g.m, nb, pows, 1.0, 0.0, nullptr)
+                           : launch_apply2x2<double>(s, off1, off2, g.m, nb, pows, 1.0, 0.0, nullptr);
+}
+
 static int flush_queue(State* s)
 {
     if (s->queue.empty()) {
         return B200SV_OK;
     }
-    return fused_flush(s);
+    // fused_flush consumes the queue.  If its planner / encoder gives up (ESTATE: "no progress", "does not fit") nothing has been
+    // launched yet, so the gates are replayed one by one on the generic kernel instead of being dropped; a CUDA failure
+    // (launch, allocation) leaves the state undefined and is reported.
+    std::vector<GateOp> saved;
+    const bool keep = s->queue.size() <= 8192;
+    if (keep) {
+        saved = s->queue;
+    }
+    const int rc = fused_flush(s);
+    if (rc == B200SV_ESTATE && keep) {
+        s->queue.clear();
+        for (const GateOp& g : saved) {
+            SV_TRY(run_gate_unfused(s, g));
+        }
+        return B200SV_OK;
+    }
+    return rc;
 }
 
 } // namespace b200sv
@@ -2520,6 +2554,91 @@ int b200sv_sample(b200sv_t s, double rnd, uint64_t* perm)
     return B200SV_OK;
 }
 
+
+// Multi-shot sampling of the whole register without collapse (QEngine::MultiShotMeasureMask,
+// src/qengine/qengine.cpp:542-609, draws from the 2^k histogram of the measured bits — here the k-bit outcome is read off a
+// sampled basis state, which has the same distribution and needs neither the histogram nor a 2^n device->host copy).
+// rnds[i] in [0, 1): shot i returns the first index whose cumulative probability exceeds rnds[i] (the search of MAll,
+// state.cpp:2026-2050).  ONE chunk-sum sweep serves every shot; each distinct chunk that holds a shot is copied once.
+int b200sv_sample_many(b200sv_t s, int n_shots, const double* rnds, uint64_t* perms)
+{
+    SV_ENTER_RO(s);
+    if (n_shots < 0 || (n_shots && (!rnds || !perms))) {
+        return einval("sample_many: null argument");
+    }
+    SV_TRY(flush_queue(s));
+    const uint64_t n = s->dim();
+    for (int i = 0; i < n_shots; ++i) {
+        perms[i] = n - 1U;
+    }
+    if (!s->amps || !n_shots) {
+        return B200SV_OK;
+    }
+    const uint64_t chunk = std::min<uint64_t>(n, 1ULL << 14);
+    const uint64_t nchunks = n / chunk;
+    SV_TRY(ensure_scratch(s, nchunks));
+    const double eps = (s->prec == 32) ? 1.7763568394002505e-15 : 6.310887241768095e-30;
+    DISPATCH_PREC(s, (k_chunk_sums<float><<<(unsigned)nchunks, 256, 0, s->stream>>>((const float2*)s->amps, chunk, (float)eps, s->d_scratch)),
+        (k_chunk_sums<double><<<(unsigned)nchunks, 256, 0, s->stream>>>((const double2*)s->amps, chunk, eps, s->d_scratch)));
+    SV_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    SV_TRY(read_scratch(s, (int)nchunks));
+    // shots in ascending order of rnd walk the chunk prefix sums once
+    std::vector<int> order((size_t)n_shots);
+    for (int i = 0; i < n_shots; ++i) {
+        order[(size_t)i] = i;
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return rnds[a] < rnds[b]; });
+    std::vector<double> prefix(nchunks + 1, 0.0);
+    uint64_t lastNonzeroChunk = nchunks;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        prefix[c + 1] = prefix[c] + s->h_scratch[c];
+        if (s->h_scratch[c] > 0) {
+            lastNonzeroChunk = c;
+        }
+    }
+    if (lastNonzeroChunk == nchunks) {
+        return B200SV_OK; // all-zero state
+    }
+    const size_t ab = s->amp_bytes();
+    std::vector<char> host(chunk * ab);
+    uint64_t loaded = nchunks, c = 0;
+    for (int k = 0; k < n_shots; ++k) {
+        const int i = order[(size_t)k];
+        const double r = rnds[i];
+        while (c < lastNonzeroChunk && !(prefix[c + 1] > r)) {
+            ++c;
+        }
+        if (loaded != c) {
+            SV_CUDA(cudaMemcpyAsync(host.data(), (char*)s->amps + c * chunk * ab, chunk * ab, cudaMemcpyDeviceToHost, s->stream));
+            SV_CUDA(cudaStreamSynchronize(s->stream));
+            loaded = c;
+        }
+        double tot = prefix[c];
+        uint64_t lastNz = c * chunk, pick = n;
+        for (uint64_t j = 0; j < chunk; ++j) {
+            double p;
+            if (s->prec == 32) {
+                const float2 v = ((float2*)host.data())[j];
+                p = (double)(v.x * v.x + v.y * v.y);
+            } else {
+                const double2 v = ((double2*)host.data())[j];
+                p = v.x * v.x + v.y * v.y;
+            }
+            if (p > eps) {
+                tot += p;
+                lastNz = c * chunk + j;
+                if (tot > r) {
+                    pick = lastNz;
+                    break;
+                }
+            }
+        }
+        perms[i] = (pick == n) ? lastNz : pick;
+    }
+    return B200SV_OK;
+}
+
 // ---- structure ---------------------------------------------------------------------------------------------------------
 
 int b200sv_compose(b200sv_t a, b200sv_t b, int start)
@@ -2563,7 +2682,13 @@ int b200sv_compose(b200sv_t a, b200sv_t b, int start)
     if (e != cudaSuccess) {
         return cuda_fail(e, "cudaMalloc(compose)");
     }
-    SV_TRY(cross_wait(a, b));
+    {
+        const int rcw = cross_wait(a, b);
+        if (rcw != B200SV_OK) {
+            cudaFree(out);
+            return rcw;
+        }
+    }
     const uint64_t startMask = (1ULL << start) - 1U;
     const uint64_t midMask = ((1ULL << b->nq) - 1U) << start;
     const uint64_t endMask = (n - 1U) & ~(startMask | midMask);

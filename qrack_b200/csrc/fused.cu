@@ -661,9 +661,13 @@ __global__ void __launch_bounds__(NT, MINB)
                 }
                 const uint32_t xsb = sbc * APC;
                 // linear walk over the pass's ops; only ops with a predicate on outer qubits look at the per-tile ballot
+                // (the next op's header is fetched while the current body runs: the read past the last op lands in the
+                // program / scratch area behind the op array and is never used)
+                uint4 hdNext = *reinterpret_cast<const uint4*>(&ops[opBegin].code);
 #pragma unroll 1
                 for (int o = opBegin; o < opEnd; ++o) {
-                    const uint4 hd = *reinterpret_cast<const uint4*>(&ops[o].code);
+                    const uint4 hd = hdNext;
+                    hdNext = *reinterpret_cast<const uint4*>(&ops[o + 1].code);
                     if ((hd.x & CODE_HAS_OUTER) && !((ballots[par][o >> 5] >> (o & 31)) & 1U)) {
                         continue;
                     }

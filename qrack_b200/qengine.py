@@ -918,6 +918,69 @@ class QEngineHost:
             self.NormalizeState()
         return self.be.prob_mask_all(mask)
 
+    def ProbBitsAll(self, bits: Sequence[int]) -> np.ndarray:
+        """QInterface::ProbBitsAll (src/qinterface/qinterface.cpp:446-476): histogram over the listed qubits, bits[p] -> output
+        bit p.  The reference loops over all 2^n basis states on the host; here ONE device sweep builds the histogram
+        (prob_mask_all, ascending qubit order) and the host only permutes its 2^k entries into the requested bit order."""
+        bits = [int(b) for b in bits]
+        for b in bits:
+            self._check_qubit(b, "ProbBitsAll")
+        if len(set(bits)) != len(bits):
+            raise ValueError("ProbBitsAll: duplicate qubit")
+        if self.doNormalize:
+            self.NormalizeState()
+        mask = 0
+        for b in bits:
+            mask |= 1 << b
+        asc = self.be.prob_mask_all(mask)          # index bit j <-> j-th lowest qubit of the mask
+        order = sorted(bits)
+        if order == bits:
+            return asc
+        k = len(bits)
+        idx = np.arange(1 << k, dtype=np.int64)
+        src = np.zeros(1 << k, dtype=np.int64)     # ascending-order index of every requested-order index
+        for p, b in enumerate(bits):
+            src |= ((idx >> p) & 1) << order.index(b)
+        return asc[src]
+
+    def MultiShotMeasureMask(self, qPowers: Sequence[int], shots: int) -> dict:
+        """QEngine::MultiShotMeasureMask (src/qengine/qengine.cpp:542-576): `shots` samples of the listed qubits without
+        collapse, as {outcome: count} with qPowers[p] -> outcome bit p.  Few measured qubits: one histogram sweep
+        (ProbBitsAll) and host draws, like the reference.  Many measured qubits (where the reference builds a 2^k histogram by
+        reading the whole state): basis states are sampled on the device (one chunk-sum sweep for all shots) and the measured
+        bits are read off them — the same distribution.  Draws come from this engine's generator (the reference seeds
+        std::mt19937 from std::random_device: outcomes are not reproducible there either)."""
+        if not shots:
+            return {}
+        bits = []
+        for p in qPowers:
+            p = int(p)
+            if p <= 0 or (p & (p - 1)) or p >= self.maxQPower:
+                raise ValueError("QInterface::MultiShotMeasureMask parameter qPowers array values must be within allocated qubit bounds!")
+            bits.append(p.bit_length() - 1)
+        if len(set(bits)) != len(bits):
+            raise ValueError("QInterface::MultiShotMeasureMask parameter qPowers array values must not repeat!")
+        out = {}
+        if len(bits) <= 16 or not hasattr(self.be, "sample_many"):
+            probs = np.asarray(self.ProbBitsAll(bits), dtype=np.float64)
+            tot = float(probs.sum())
+            if tot <= 0:
+                return {0: int(shots)}
+            cum = np.cumsum(probs / tot)
+            draws = np.searchsorted(cum, [self.Rand() for _ in range(shots)], side="right")
+            for d in np.minimum(draws, probs.size - 1):
+                out[int(d)] = out.get(int(d), 0) + 1
+            return out
+        if self.doNormalize:
+            self.NormalizeState()
+        perms = self.be.sample_many([self.Rand() for _ in range(shots)])
+        for perm in perms:
+            key = 0
+            for p, b in enumerate(bits):
+                key |= ((int(perm) >> b) & 1) << p
+            out[key] = out.get(key, 0) + 1
+        return out
+
     def CtrlOrAntiProb(self, controlState: bool, control: int, target: int) -> float:  # state.cpp:1814-1869
         if self.be.is_zero():
             return 0.0
@@ -1327,6 +1390,14 @@ class _CudaBackend:
         p = ctypes.c_uint64()
         self._ck(self.lib.b200sv_sample(self.h, float(rnd), ctypes.byref(p)))
         return p.value
+
+    def sample_many(self, rnds) -> list:
+        import ctypes
+        n = len(rnds)
+        r = (ctypes.c_double * max(n, 1))(*[float(x) for x in rnds])
+        out = (ctypes.c_uint64 * max(n, 1))()
+        self._ck(self.lib.b200sv_sample_many(self.h, n, r, out))
+        return [int(out[i]) for i in range(n)]
 
     def compose(self, other: "_CudaBackend", start: int):
         self._ck(self.lib.b200sv_compose(self.h, other.h, start))

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 U=dropin/_build/f32/unittest_b200
 H=dropin/_build/harness_b200_f32
 R=oracle/_ref/ref_harness_f32
-LIST="test_cnot,test_apply_single_bit,test_global_phase,test_qft_h,test_compose,test_decompose,test_dispose,test_dispose_perm,test_allocate,test_trydecompose,test_prob*,test_cprob,test_forcem,test_getamplitude,test_getquantumstate,test_getprobs,test_normalize,test_grover,test_h_cnot_rand,test_m,test_mreg,test_swap,test_t,test_ccnot,test_ucmtrx,test_mirror_circuit*"
+LIST="test_cnot,test_apply_single_bit,test_global_phase,test_qft_h,test_compose,test_decompose,test_dispose,test_dispose_perm,test_allocate,test_trydecompose,test_prob*,test_cprob,test_forcem,test_getamplitude,test_getquantumstate,test_getprobs,test_normalize,test_grover,test_h_cnot_rand,test_m,test_mreg,test_swap,test_t,test_ccnot,test_ucmtrx,test_multishotmeasuremask,test_bell_m,test_mirror_circuit*"
 echo "== reference unittest on QEngineCUDA drop-in (--layer-qengine --proc-cuda)"
 timeout 900 $U --layer-qengine --proc-cuda --disable-hardware-rng "$LIST" > gpurun_out/dropin_unittest_qengine_full.log 2>&1; grep -B3 -A12 "FAILED" gpurun_out/dropin_unittest_qengine_full.log | head -60; tail -4 gpurun_out/dropin_unittest_qengine_full.log | tee gpurun_out/dropin_unittest_qengine.log
 ALU="test_rol,test_ror,test_inc,test_incs,test_incc,test_incsc,test_cinc,test_dec,test_decs,test_decc,test_decsc,test_cdec,test_mul,test_div,test_mulmodnout,test_imulmodnout,test_powmodnout,test_cmul,test_cdiv,test_cmulmodnout,test_cimulmodnout,test_cpowmodnout,test_c_phase_flip_if_less,test_superposition_reg,test_adc_superposition_reg,test_sbc_superposition_reg,test_superposition_reg_long,test_adc_superposition_reg_long_index,test_sbc_superposition_reg_long_index,test_hash,test_fulladd,test_ifulladd,test_adc,test_iadc,test_cfulladd,test_cifulladd,test_cadc,test_ciadc,test_set_reg,test_amplitude_amplification,test_basis_change"

@@ -27,7 +27,7 @@ HARN = os.path.join(B, "harness_b200_f32")
 
 HOT = ("test_cnot,test_apply_single_bit,test_global_phase,test_qft_h,test_compose,test_decompose,test_dispose,test_dispose_perm,"
        "test_allocate,test_trydecompose,test_prob*,test_cprob,test_forcem,test_getamplitude,test_getquantumstate,test_getprobs,"
-       "test_normalize,test_grover,test_h_cnot_rand,test_m,test_mreg,test_swap,test_t,test_ccnot,test_ucmtrx,test_mirror_circuit*")
+       "test_normalize,test_grover,test_h_cnot_rand,test_m,test_mreg,test_swap,test_t,test_ccnot,test_ucmtrx,test_multishotmeasuremask,test_bell_m,test_mirror_circuit*")
 ALU = ("test_rol,test_ror,test_inc,test_incs,test_incc,test_incsc,test_cinc,test_dec,test_decs,test_decc,test_decsc,test_cdec,test_mul,"
        "test_div,test_mulmodnout,test_imulmodnout,test_powmodnout,test_cmul,test_cdiv,test_cmulmodnout,test_cimulmodnout,"
        "test_cpowmodnout,test_c_phase_flip_if_less,test_superposition_reg,test_adc_superposition_reg,test_sbc_superposition_reg,"

@@ -170,3 +170,31 @@ def test_qalu_argument_errors_and_unsupported_backends():
     q.ZeroAmplitudes()
     q.INC(3, 0, 4)                                       # CHECK_ZERO_SKIP
     assert q.IsZeroAmplitude()
+
+
+def test_prob_bits_all_order_and_multishot_histogram_path():
+    """QInterface::ProbBitsAll (qinterface.cpp:446-476) indexes its output by the ORDER of the listed qubits; the small-mask path
+    of MultiShotMeasureMask (qengine.cpp:542-576) draws from that histogram."""
+    import numpy as np
+    from oracle.restate_engine import QEngineRestate
+    n = 7
+    q = QEngineRestate(n, 0, random.Random(3), 1.0 + 0j, False, False, precision=64)
+    for b in range(n):
+        q.U(b, 0.3 + 0.4 * b, 0.1 * b, 0.2)
+    q.CNOT(0, 5)
+    q.CNOT(6, 2)
+    st = q.GetQuantumState()
+    pr = (st.real ** 2 + st.imag ** 2)
+    bits = [5, 0, 6]
+    want = np.zeros(8)
+    for i in range(1 << n):
+        k = sum(((i >> b) & 1) << p for p, b in enumerate(bits))
+        want[k] += pr[i]
+    got = q.ProbBitsAll(bits)
+    assert np.abs(np.asarray(got, dtype=np.float64) - want).max() < 1e-12
+    res = q.MultiShotMeasureMask([1 << b for b in bits], 4000)
+    assert sum(res.values()) == 4000 and set(res) <= set(range(8))
+    emp = np.array([res.get(k, 0) for k in range(8)]) / 4000.0
+    assert np.abs(emp - want).max() < 0.04          # ~5 sigma of a 4000-shot binomial
+    with pytest.raises(ValueError):
+        q.MultiShotMeasureMask([3], 10)

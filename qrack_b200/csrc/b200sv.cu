@@ -212,6 +212,61 @@ static int launch_apply2x2(State* s, uint64_t off1, uint64_t off2, const double*
     return B200SV_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// 128-bit streaming helpers for the elementwise sweeps and reductions: every global access is one 16-byte chunk
+// (fp32: amplitudes 2j and 2j+1 as a float4, fp64: one double2), grid-stride, so a warp touches 512 contiguous bytes per
+// instruction.  f(i, amp) is called once per amplitude; map_amps writes the returned amplitude back.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, typename F>
+__device__ __forceinline__ void for_amps(const typename Cx<R>::type* __restrict__ psi, uint64_t n, F f)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sizeof(R) == 4 && n >= 2) {
+        const float4* p = reinterpret_cast<const float4*>(psi);
+        const uint64_t m = n >> 1;
+        for (uint64_t j = gid; j < m; j += stride) {
+            const float4 v = p[j];
+            typename Cx<R>::type a0, a1;
+            a0.x = (R)v.x;
+            a0.y = (R)v.y;
+            a1.x = (R)v.z;
+            a1.y = (R)v.w;
+            f(2U * j, a0);
+            f(2U * j + 1U, a1);
+        }
+    } else {
+        for (uint64_t i = gid; i < n; i += stride) {
+            f(i, psi[i]);
+        }
+    }
+}
+template <typename R, typename F> __device__ __forceinline__ void map_amps(typename Cx<R>::type* psi, uint64_t n, F f)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sizeof(R) == 4 && n >= 2) {
+        float4* p = reinterpret_cast<float4*>(psi);
+        const uint64_t m = n >> 1;
+        for (uint64_t j = gid; j < m; j += stride) {
+            const float4 v = p[j];
+            typename Cx<R>::type a0, a1;
+            a0.x = (R)v.x;
+            a0.y = (R)v.y;
+            a1.x = (R)v.z;
+            a1.y = (R)v.w;
+            a0 = f(2U * j, a0);
+            a1 = f(2U * j + 1U, a1);
+            p[j] = make_float4((float)a0.x, (float)a0.y, (float)a1.x, (float)a1.y);
+        }
+    } else {
+        for (uint64_t i = gid; i < n; i += stride) {
+            psi[i] = f(i, psi[i]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // elementwise sweeps
 // ---------------------------------------------------------------------------------------------------------
@@ -220,14 +275,7 @@ __global__ void __launch_bounds__(256) k_apply_m(typename Cx<R>::type* psi, uint
     typename Cx<R>::type nrm)
 {
     typedef typename Cx<R>::type C;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        if ((i & mask) == result) {
-            psi[i] = cmul<C>(nrm, psi[i]);
-        } else {
-            psi[i] = mk<R>(0, 0);
-        }
-    }
+    map_amps<R>(psi, n, [&](uint64_t i, C a) { return ((i & mask) == result) ? cmul<C>(nrm, a) : mk<R>(0, 0); });
 }
 
 template <typename R>
@@ -266,14 +314,13 @@ __global__ void __launch_bounds__(256) k_phase_parity(typename Cx<R>::type* psi,
     typename Cx<R>::type odd, typename Cx<R>::type even)
 {
     typedef typename Cx<R>::type C;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    map_amps<R>(psi, n, [&](uint64_t i, C a) {
         if ((i & cmask) != cmask) {
-            continue;
+            return a;
         }
         const bool p = __popcll(i & mask) & 1;
-        psi[i] = cmul<C>(p ? odd : even, psi[i]);
-    }
+        return cmul<C>(p ? odd : even, a);
+    });
 }
 
 template <typename R>
@@ -281,29 +328,27 @@ __global__ void __launch_bounds__(256) k_phase_root_n(typename Cx<R>::type* psi,
     R radians)
 {
     typedef typename Cx<R>::type C;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    map_amps<R>(psi, n, [&](uint64_t i, C a) {
         const uint64_t steps = (uint64_t)__popcll(i & mask) % nPhases;
-        if (steps) {
-            R sn, cs;
-            sincos(radians * (R)steps, &sn, &cs);
-            psi[i] = cmul<C>(mk<R>(cs, sn), psi[i]);
+        if (!steps) {
+            return a;
         }
-    }
+        R sn, cs;
+        sincos(radians * (R)steps, &sn, &cs);
+        return cmul<C>(mk<R>(cs, sn), a);
+    });
 }
 
 template <typename R>
 __global__ void __launch_bounds__(256) k_normalize(typename Cx<R>::type* psi, uint64_t n, typename Cx<R>::type f, R thresh)
 {
     typedef typename Cx<R>::type C;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        C a = psi[i];
+    map_amps<R>(psi, n, [&](uint64_t, C a) {
         if (cnorm(a) < thresh) {
             a = mk<R>(0, 0);
         }
-        psi[i] = cmul<C>(f, a);
-    }
+        return cmul<C>(f, a);
+    });
 }
 
 // UniformlyControlledSingleBit (reference state.cpp:1094-1198)
@@ -441,48 +486,48 @@ __global__ void __launch_bounds__(256) k_prob_all_bits2(const typename Cx<R>::ty
         carry[b] = 0;
     }
     Acc a0 = 0, total = 0;
-    const uint32_t nIt = 1U << itBits;
-    for (uint32_t it0 = 0; it0 < nIt; it0 += 2) {
-        // two independent loads in flight per thread
-        const uint4 c0 = __ldcs(base + ((uint64_t)it0 * T + gid));
-        uint4 c1 = make_uint4(0, 0, 0, 0);
-        const bool two = (it0 + 1U) < nIt;
-        if (two) {
-            c1 = __ldcs(base + ((uint64_t)(it0 + 1U) * T + gid));
-        }
+    // four independent 16-byte loads in flight per thread; the four chunk values are combined pairwise in registers (levels 0
+    // and 1 of the counter), so the counter proper runs once per four chunks, starting at level 2
+    const uint32_t nIt = 1U << itBits; // >= 4
+    for (uint32_t it0 = 0; it0 < nIt; it0 += 4) {
+        uint4 c[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !two) {
-                break;
-            }
-            const uint4 c = u ? c1 : c0;
-            Acc v;
+        for (int u = 0; u < 4; ++u) {
+            c[u] = __ldcs(base + ((uint64_t)(it0 + (uint32_t)u) * T + gid));
+        }
+        Acc w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
             if (APCLOG) {
-                const float x0 = __uint_as_float(c.x), y0 = __uint_as_float(c.y), x1 = __uint_as_float(c.z), y1 = __uint_as_float(c.w);
+                const float x0 = __uint_as_float(c[u].x), y0 = __uint_as_float(c[u].y), x1 = __uint_as_float(c[u].z), y1 = __uint_as_float(c[u].w);
                 const float p1 = x1 * x1 + y1 * y1;
                 a0 += (Acc)p1;
-                v = (Acc)((x0 * x0 + y0 * y0) + p1);
+                w[u] = (Acc)((x0 * x0 + y0 * y0) + p1);
             } else {
-                const double x = __hiloint2double((int)c.y, (int)c.x), y = __hiloint2double((int)c.w, (int)c.z);
-                v = (Acc)(x * x + y * y);
+                const double x = __hiloint2double((int)c[u].y, (int)c[u].x), y = __hiloint2double((int)c[u].w, (int)c[u].z);
+                w[u] = (Acc)(x * x + y * y);
             }
-            const uint32_t it = it0 + (uint32_t)u;
-            bool done = false;
+        }
+        A[0] += w[1] + w[3];
+        const Acc w23 = w[2] + w[3];
+        A[1] += w23;
+        Acc v = (w[0] + w[1]) + w23;
+        const uint32_t it = it0 >> 2;
+        bool done = false;
 #pragma unroll
-            for (int b = 0; b < MAXB; ++b) {
-                if (b < itBits && !done) {
-                    if ((it >> b) & 1U) {
-                        A[b] += v;
-                        v += carry[b];
-                    } else {
-                        carry[b] = v;
-                        done = true;
-                    }
+        for (int b = 2; b < MAXB; ++b) {
+            if (b < itBits && !done) {
+                if ((it >> (b - 2)) & 1U) {
+                    A[b] += v;
+                    v += carry[b];
+                } else {
+                    carry[b] = v;
+                    done = true;
                 }
             }
-            if (!done) {
-                total = v; // it = 2^itBits - 1: every level has been folded in
-            }
+        }
+        if (!done) {
+            total = v; // the last group: every level has been folded in
         }
     }
     // ---- per-thread results -> marginals.  Values reduced over the CTA: [0] total, [1] a0, [2 .. 2+itBits) A[b],
@@ -564,20 +609,20 @@ template <typename R>
 __global__ void __launch_bounds__(256) k_prob_mask(const typename Cx<R>::type* __restrict__ psi, uint64_t n, uint64_t mask,
     uint64_t perm, double* out)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    typedef typename Cx<R>::type C;
     double acc = 0;
     R part = 0;
     int cnt = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for_amps<R>(psi, n, [&](uint64_t i, C a) {
         if ((i & mask) == perm) {
-            part += cnorm(psi[i]);
+            part += cnorm(a);
         }
         if (++cnt == 64) {
             acc += (double)part;
             part = 0;
             cnt = 0;
         }
-    }
+    });
     acc += (double)part;
     block_atomic_add(acc, out);
 }
@@ -607,25 +652,33 @@ template <typename R>
 __global__ void __launch_bounds__(256) k_prob_parity(const typename Cx<R>::type* __restrict__ psi, uint64_t n, uint64_t mask,
     double* out)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    typedef typename Cx<R>::type C;
     double acc = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    R part = 0;
+    int cnt = 0;
+    for_amps<R>(psi, n, [&](uint64_t i, C a) {
         if (__popcll(i & mask) & 1) {
-            acc += (double)cnorm(psi[i]);
+            part += cnorm(a);
         }
-    }
+        if (++cnt == 64) {
+            acc += (double)part;
+            part = 0;
+            cnt = 0;
+        }
+    });
+    acc += (double)part;
     block_atomic_add(acc, out);
 }
 
 template <typename R>
 __global__ void __launch_bounds__(256) k_norm(const typename Cx<R>::type* __restrict__ psi, uint64_t n, R thresh, double* out)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    typedef typename Cx<R>::type C;
     double acc = 0;
     R part = 0;
     int cnt = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const R v = cnorm(psi[i]);
+    for_amps<R>(psi, n, [&](uint64_t, C a) {
+        const R v = cnorm(a);
         if (v >= thresh) {
             part += v;
         }
@@ -634,7 +687,7 @@ __global__ void __launch_bounds__(256) k_norm(const typename Cx<R>::type* __rest
             part = 0;
             cnt = 0;
         }
-    }
+    });
     acc += (double)part;
     block_atomic_add(acc, out);
 }
@@ -660,11 +713,9 @@ template <typename R>
 __global__ void __launch_bounds__(256) k_expectation(const typename Cx<R>::type* __restrict__ psi, uint64_t n, int start,
     uint64_t lenMask, double* out)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    typedef typename Cx<R>::type C;
     double acc = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        acc += (double)cnorm(psi[i]) * (double)((i >> start) & lenMask);
-    }
+    for_amps<R>(psi, n, [&](uint64_t i, C a) { acc += (double)cnorm(a) * (double)((i >> start) & lenMask); });
     block_atomic_add(acc, out);
 }
 
@@ -732,10 +783,19 @@ __global__ void __launch_bounds__(256) k_chunk_sums(const typename Cx<R>::type* 
 {
     const uint64_t base = (uint64_t)blockIdx.x * chunk;
     double acc = 0;
-    for (uint64_t i = threadIdx.x; i < chunk; i += blockDim.x) {
-        const R v = cnorm(psi[base + i]);
-        if (v > eps) {
-            acc += (double)v;
+    if (sizeof(R) == 4 && chunk >= 2) { // 128-bit loads: two amplitudes per access
+        const float4* p = reinterpret_cast<const float4*>(psi + base);
+        for (uint64_t j = threadIdx.x; j < (chunk >> 1); j += blockDim.x) {
+            const float4 q = p[j];
+            const float v0 = q.x * q.x + q.y * q.y, v1 = q.z * q.z + q.w * q.w;
+            acc += (double)((v0 > (float)eps ? v0 : 0.f) + (v1 > (float)eps ? v1 : 0.f));
+        }
+    } else {
+        for (uint64_t i = threadIdx.x; i < chunk; i += blockDim.x) {
+            const R v = cnorm(psi[base + i]);
+            if (v > eps) {
+                acc += (double)v;
+            }
         }
     }
     sums[blockIdx.x] = 0;
@@ -750,16 +810,16 @@ __global__ void __launch_bounds__(256) k_argmax(const typename Cx<R>::type* __re
 {
     __shared__ double sv[256];
     __shared__ unsigned long long si[256];
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    typedef typename Cx<R>::type C;
     double bv = -1;
     unsigned long long bi = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double v = (double)cnorm(psi[i]);
-        if (v > bv) {
+    for_amps<R>(psi, n, [&](uint64_t i, C a) {
+        const double v = (double)cnorm(a);
+        if (v > bv || (v == bv && i < bi)) {
             bv = v;
             bi = i;
         }
-    }
+    });
     sv[threadIdx.x] = bv;
     si[threadIdx.x] = bi;
     __syncthreads();
@@ -790,6 +850,18 @@ __global__ void __launch_bounds__(256) k_compose(typename Cx<R>::type* __restric
 {
     typedef typename Cx<R>::type C;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    if (sizeof(R) == 4 && start >= 1) {
+        // fp32, inserted register above qubit 0: amplitudes 2j and 2j+1 share the b factor and are adjacent in a: 128-bit accesses
+        float4* o4 = reinterpret_cast<float4*>(out);
+        for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < (n >> 1); j += stride) {
+            const uint64_t l = j << 1;
+            const float4 x = *reinterpret_cast<const float4*>(a + ((l & startMask) | ((l & endMask) >> nb)));
+            const C y = b[(l & midMask) >> start];
+            o4[j] = make_float4(x.x * (float)y.x - x.y * (float)y.y, x.x * (float)y.y + x.y * (float)y.x, x.z * (float)y.x - x.w * (float)y.y,
+                x.z * (float)y.y + x.w * (float)y.x);
+        }
+        return;
+    }
     for (uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += stride) {
         const C x = a[(l & startMask) | ((l & endMask) >> nb)];
         const C y = b[(l & midMask) >> start];
@@ -802,6 +874,15 @@ __global__ void __launch_bounds__(256) k_dispose_perm(typename Cx<R>::type* __re
     const typename Cx<R>::type* __restrict__ in, uint64_t n, uint64_t skipMask, int length, uint64_t disposedRes)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    if (sizeof(R) == 4 && (skipMask & 1U) && n >= 2) {
+        // fp32, disposed register above qubit 0: kept amplitudes 2j, 2j+1 are adjacent in the source too
+        float4* o4 = reinterpret_cast<float4*>(out);
+        for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < (n >> 1); j += stride) {
+            const uint64_t h = j << 1, lo = h & skipMask;
+            o4[j] = *reinterpret_cast<const float4*>(in + (lo | ((h ^ lo) << length) | disposedRes));
+        }
+        return;
+    }
     for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += stride) {
         const uint64_t lo = h & skipMask;
         out[h] = in[lo | ((h ^ lo) << length) | disposedRes];
@@ -860,6 +941,85 @@ __global__ void __launch_bounds__(256) k_decompose_marginals(const typename Cx<R
             }
             if (sh[partPower + b] != 0.0) {
                 atomicAdd(&partAngle[b], sh[partPower + b]);
+            }
+        }
+    }
+}
+
+
+// r2 single-pass form of the marginals for the usual case that ONE side of the split is small (<= 2^11 entries; QUnit
+// decomposes a few qubits out of a big register, or keeps a few).  The thread owns one index `o` of the LARGE side and walks
+// the small side `j`: its row sums never leave registers and the rebuilt amplitude sqrt(P) e^{i theta} (state.cpp:1677-1695)
+// is written straight to the new state — no 2^n doubles of accumulators, no per-amplitude global atomics.  The small side is
+// summed per warp with shuffles (all lanes are at the same j), then per CTA in shared-memory bins, then one atomic per bin
+// and CTA.  HBM traffic = one read of the state + one write of the large side.
+//   smallIsPart = 1: o = remainder index, j = part index;  0: o = part index, j = remainder index.
+template <typename R>
+__global__ void __launch_bounds__(256) k_decompose_onepass(const typename Cx<R>::type* __restrict__ psi, int start, int length, int nq,
+    int smallIsPart, R floorv, typename Cx<R>::type* __restrict__ outLarge, double* smallProb, double* smallAngle, int needSmall)
+{
+    extern __shared__ double sh[];
+    const uint64_t partPower = 1ULL << length, remPower = 1ULL << (nq - length);
+    const uint64_t smallN = smallIsPart ? partPower : remPower, largeN = smallIsPart ? remPower : partPower;
+    if (needSmall) {
+        for (uint64_t b = threadIdx.x; b < 2 * smallN; b += blockDim.x) {
+            sh[b] = 0;
+        }
+        __syncthreads();
+    }
+    const uint64_t startMask = (1ULL << start) - 1U;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    // every lane of a warp runs the same number of iterations (largeN is a power of two >= 32 or the tail lanes idle with zeros)
+    const uint64_t rounds = (largeN + stride - 1U) / stride;
+    for (uint64_t it = 0; it < rounds; ++it) {
+        const uint64_t o = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool live = o < largeN;
+        double P = 0, A = 0;
+        for (uint64_t j = 0; j < smallN; ++j) {
+            const uint64_t r = smallIsPart ? o : j, k = smallIsPart ? j : o;
+            double dn = 0, ang = 0;
+            if (live) {
+                const uint64_t i = (r & startMask) | (k << start) | ((r >> start) << (start + length));
+                const auto amp = psi[i];
+                const R nrm = cnorm(amp);
+                dn = (double)nrm;
+                if (nrm > floorv) {
+                    ang = (double)atan2(amp.y, amp.x) * dn;
+                }
+                P += dn;
+                A += ang;
+            }
+            if (needSmall) {
+                const double wp = warp_sum(dn), wa = warp_sum(ang);
+                if (lane == 0 && wp != 0.0) {
+                    atomicAdd(&sh[j], wp);
+                    if (wa != 0.0) {
+                        atomicAdd(&sh[smallN + j], wa);
+                    }
+                }
+            }
+        }
+        if (live) {
+            const R p = (R)P;
+            R th = (R)A;
+            if (p > floorv) {
+                th = (R)(A / P);
+            }
+            const R mag = (R)sqrt((double)p);
+            R sn, cs;
+            sincos(th, &sn, &cs);
+            outLarge[o] = mk<R>(mag * cs, mag * sn);
+        }
+    }
+    if (needSmall) {
+        __syncthreads();
+        for (uint64_t b = threadIdx.x; b < smallN; b += blockDim.x) {
+            if (sh[b] != 0.0) {
+                atomicAdd(&smallProb[b], sh[b]);
+            }
+            if (sh[smallN + b] != 0.0) {
+                atomicAdd(&smallAngle[b], sh[smallN + b]);
             }
         }
     }
@@ -981,6 +1141,85 @@ static int ensure_scratch(State* s, size_t doubles)
     return B200SV_OK;
 }
 
+
+// ---- state-buffer cache --------------------------------------------------------------------------------------------------
+// Compose / Decompose / Dispose replace the state buffer by one of another size, and QUnit-style callers do that all the time.
+// cudaMalloc + cudaFree of GiB-sized buffers cost milliseconds each and synchronise the device (measured r2: Compose 29+1 at
+// 15.8 ms for a 2 ms kernel), so released state buffers are kept per device and handed out again on an exact size match.
+struct BufCache {
+    std::mutex m;
+    struct Ent {
+        void* p;
+        size_t bytes;
+    };
+    std::vector<Ent> ent[64];
+    size_t held[64] = { 0 };
+};
+static BufCache& buf_cache()
+{
+    static BufCache c;
+    return c;
+}
+static void buf_cache_flush(int dev)
+{
+    BufCache& c = buf_cache();
+    std::vector<BufCache::Ent> drop;
+    {
+        std::lock_guard<std::mutex> lk(c.m);
+        drop.swap(c.ent[dev & 63]);
+        c.held[dev & 63] = 0;
+    }
+    for (const BufCache::Ent& e : drop) {
+        cudaFree(e.p);
+    }
+}
+// current device must be `dev`
+static cudaError_t state_buf_alloc(int dev, size_t bytes, void** out)
+{
+    BufCache& c = buf_cache();
+    {
+        std::lock_guard<std::mutex> lk(c.m);
+        std::vector<BufCache::Ent>& v = c.ent[dev & 63];
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (v[i].bytes == bytes) {
+                *out = v[i].p;
+                c.held[dev & 63] -= bytes;
+                v.erase(v.begin() + (long)i);
+                return cudaSuccess;
+            }
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        buf_cache_flush(dev);
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+// the caller has synchronised every stream that used the buffer
+static void state_buf_free(int dev, void* p, size_t bytes)
+{
+    if (!p) {
+        return;
+    }
+    BufCache& c = buf_cache();
+    static const size_t cap = [] {
+        const char* e = getenv("B200SV_BUF_CACHE_MB");
+        return (size_t)(e ? atoll(e) : 49152) << 20; // default: at most 48 GiB of released buffers per device
+    }();
+    {
+        std::lock_guard<std::mutex> lk(c.m);
+        std::vector<BufCache::Ent>& v = c.ent[dev & 63];
+        if (bytes >= ((size_t)1 << 16) && v.size() < 8 && c.held[dev & 63] + bytes <= cap) {
+            v.push_back({ p, bytes });
+            c.held[dev & 63] += bytes;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+
 static int alloc_amps(State* s, bool clear)
 {
     if (s->amps) {
@@ -990,11 +1229,12 @@ static int alloc_amps(State* s, bool clear)
         return einval("external buffer was released; cannot re-allocate");
     }
     const size_t bytes = (size_t)s->dim() * s->amp_bytes();
-    cudaError_t e = cudaMalloc(&s->amps, bytes);
+    cudaError_t e = state_buf_alloc(s->dev, bytes, &s->amps);
     if (e != cudaSuccess) {
         s->amps = nullptr;
         return cuda_fail(e, "cudaMalloc(state)");
     }
+    s->amps_bytes = bytes;
     if (clear) {
         SV_CUDA(cudaMemsetAsync(s->amps, 0, bytes, s->stream));
     }
@@ -1007,8 +1247,13 @@ static void free_amps(State* s)
         cudaStreamSynchronize(s->stream);
     }
     if (s->amps && !s->external) {
-        cudaFree(s->amps);
+        if (s->amps_bytes) {
+            state_buf_free(s->dev, s->amps, s->amps_bytes);
+        } else {
+            cudaFree(s->amps);
+        }
     }
+    s->amps_bytes = 0;
     if (s->spare) {
         cudaFree(s->spare); // the ping-pong buffer goes with the state it was sized for
         s->spare = nullptr;
@@ -1495,6 +1740,7 @@ int b200sv_set_device(b200sv_t s, int device)
     // swap guts
     free_amps(s);
     std::swap(s->amps, n->amps);
+    std::swap(s->amps_bytes, n->amps_bytes);
     std::swap(s->stream, n->stream);
     std::swap(s->ownStream, n->ownStream);
     std::swap(s->d_scratch, n->d_scratch);
@@ -2213,7 +2459,7 @@ int b200sv_prob_mask(b200sv_t s, uint64_t mask, uint64_t perm, double* out)
             const int cl = s->nq - (s->prec == 32 ? 1 : 0); // log2 of the number of 16-byte chunks
             if (cl >= 14) {
                 // coalesced version: power-of-two grid, at least 4 and at most 2^20 chunks per thread
-                int gBits = std::min(cl - 8 - 2, 11);
+                int gBits = std::min(cl - 8 - 2, 11); // at least 4 chunks per thread
                 const int itBits = cl - 8 - gBits;
                 if (itBits > 20) {
                     gBits += itBits - 20;
@@ -2678,7 +2924,7 @@ int b200sv_compose(b200sv_t a, b200sv_t b, int start)
     }
     const uint64_t n = 1ULL << nq;
     void* out = nullptr;
-    cudaError_t e = cudaMalloc(&out, n * a->amp_bytes());
+    cudaError_t e = state_buf_alloc(a->dev, n * a->amp_bytes(), &out);
     if (e != cudaSuccess) {
         return cuda_fail(e, "cudaMalloc(compose)");
     }
@@ -2704,6 +2950,7 @@ int b200sv_compose(b200sv_t a, b200sv_t b, int start)
     SV_TRY(cross_wait(b, a));
     free_amps(a); // synchronises a's stream first
     a->amps = out;
+    a->amps_bytes = n * a->amp_bytes();
     a->nq = nq;
     return B200SV_OK;
 }
@@ -2728,7 +2975,7 @@ int b200sv_dispose_perm(b200sv_t s, int start, int length, uint64_t perm)
     }
     const uint64_t rem = 1ULL << nl;
     void* out = nullptr;
-    cudaError_t e = cudaMalloc(&out, rem * s->amp_bytes());
+    cudaError_t e = state_buf_alloc(s->dev, rem * s->amp_bytes(), &out);
     if (e != cudaSuccess) {
         return cuda_fail(e, "cudaMalloc(dispose)");
     }
@@ -2744,6 +2991,7 @@ int b200sv_dispose_perm(b200sv_t s, int start, int length, uint64_t perm)
     }
     free_amps(s);
     s->amps = out;
+    s->amps_bytes = rem * s->amp_bytes();
     s->nq = nl; // (the reference sets qubitCount 1 when nl==0, state.cpp:1741-1745; the adapter handles that)
     return B200SV_OK;
 }
@@ -2789,7 +3037,9 @@ int b200sv_decompose(b200sv_t s, int start, int length, b200sv_t dest)
                 SV_CUDA(cudaStreamSynchronize(s->stream));
                 free_amps(dest);
                 dest->amps = s->amps;
+                dest->amps_bytes = s->amps_bytes;
                 s->amps = nullptr;
+                s->amps_bytes = 0;
             }
         } else {
             free_amps(s);
@@ -2800,76 +3050,149 @@ int b200sv_decompose(b200sv_t s, int start, int length, b200sv_t dest)
     const uint64_t n = s->dim();
     const uint64_t partPower = 1ULL << length, remPower = 1ULL << nl;
     const double floorv = (s->prec == 32) ? 1.7763568394002505e-15 : 6.310887241768095e-30; // amplitudeFloor = REAL1_EPSILON (qrack_types.hpp:206,209)
+    const size_t ab = s->amp_bytes();
+    const bool onePass = (partPower <= 2048 || remPower <= 2048);
+    const bool smallIsPart = partPower <= remPower;
+    void* nout = nullptr; // the remainder state
+    void* pout = nullptr; // the part state (only if dest)
     double* acc = nullptr;
-    const size_t accN = 2 * remPower + 2 * partPower;
-    cudaError_t e = cudaMalloc(&acc, accN * sizeof(double));
+    cudaError_t e = state_buf_alloc(s->dev, remPower * ab, &nout);
     if (e != cudaSuccess) {
-        return cuda_fail(e, "cudaMalloc(decompose marginals)");
-    }
-    cudaMemsetAsync(acc, 0, accN * sizeof(double), s->stream);
-    double* remProb = acc;
-    double* remAngle = acc + remPower;
-    double* partProb = dest ? acc + 2 * remPower : nullptr;
-    double* partAngle = dest ? acc + 2 * remPower + partPower : nullptr;
-    const int partShared = dest && partPower <= 2048;
-    const size_t shm = partShared ? 2 * partPower * sizeof(double) : 0;
-    const unsigned grid = std::min<unsigned>(stream_grid(s->dev, n, 256), (unsigned)sm_count(s->dev) * 8U);
-    DISPATCH_PREC(s, (k_decompose_marginals<float><<<grid, 256, shm, s->stream>>>((const float2*)s->amps, n, start, length, (float)floorv, remProb, remAngle, partProb, partAngle, partShared)),
-        (k_decompose_marginals<double><<<grid, 256, shm, s->stream>>>((const double2*)s->amps, n, start, length, floorv, remProb, remAngle, partProb, partAngle, partShared)));
-    s->stats.kernel_launches++;
-    void* nout = nullptr;
-    e = cudaMalloc(&nout, remPower * s->amp_bytes());
-    if (e != cudaSuccess) {
-        cudaStreamSynchronize(s->stream);
-        cudaFree(acc);
         return cuda_fail(e, "cudaMalloc(decompose remainder)");
     }
-    {
-        const unsigned g2 = stream_grid(s->dev, remPower, 256);
-        DISPATCH_PREC(s, (k_polar_rebuild<float><<<g2, 256, 0, s->stream>>>((float2*)nout, remPower, remProb, remAngle, (float)floorv)),
-            (k_polar_rebuild<double><<<g2, 256, 0, s->stream>>>((double2*)nout, remPower, remProb, remAngle, floorv)));
-        s->stats.kernel_launches++;
-    }
-    int rc = B200SV_OK;
     if (dest) {
-        // build the part state on s's device, then move it if dest lives elsewhere
-        void* pout = nullptr;
-        e = cudaMalloc(&pout, partPower * s->amp_bytes());
+        e = state_buf_alloc(s->dev, partPower * ab, &pout);
         if (e != cudaSuccess) {
-            rc = cuda_fail(e, "cudaMalloc(decompose part)");
+            state_buf_free(s->dev, nout, remPower * ab);
+            return cuda_fail(e, "cudaMalloc(decompose part)");
+        }
+    }
+    auto fail = [&](cudaError_t err, const char* what) {
+        cudaStreamSynchronize(s->stream);
+        if (acc) {
+            cudaFree(acc);
+        }
+        state_buf_free(s->dev, nout, remPower * ab);
+        if (pout) {
+            state_buf_free(s->dev, pout, partPower * ab);
+        }
+        return cuda_fail(err, what);
+    };
+    if (onePass) {
+        // one read of the state: the large side is rebuilt in the kernel, the small side from its bins afterwards
+        const uint64_t smallN = smallIsPart ? partPower : remPower, largeN = smallIsPart ? remPower : partPower;
+        const bool needSmall = smallIsPart ? (dest != nullptr) : true;
+        const bool needLarge = smallIsPart ? true : (dest != nullptr);
+        void* outLarge = smallIsPart ? nout : pout;
+        void* scratchLarge = nullptr;
+        if (!needLarge) {
+            // Dispose of a LARGE part: nothing of it is kept, but the kernel writes its rows; give it a throw-away buffer
+            e = state_buf_alloc(s->dev, largeN * ab, &scratchLarge);
+            if (e != cudaSuccess) {
+                return fail(e, "cudaMalloc(decompose scratch)");
+            }
+            outLarge = scratchLarge;
+        }
+        e = cudaMalloc(&acc, 2 * smallN * sizeof(double));
+        if (e != cudaSuccess) {
+            if (scratchLarge) {
+                state_buf_free(s->dev, scratchLarge, largeN * ab);
+            }
+            return fail(e, "cudaMalloc(decompose bins)");
+        }
+        cudaMemsetAsync(acc, 0, 2 * smallN * sizeof(double), s->stream);
+        const unsigned grid = (unsigned)std::min<uint64_t>((largeN + 255U) / 256U, (uint64_t)sm_count(s->dev) * 8U);
+        const size_t shm = needSmall ? 2 * smallN * sizeof(double) : 0;
+        if (s->prec == 32) {
+            if (shm > 48 * 1024) {
+                cudaFuncSetAttribute(k_decompose_onepass<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+            }
+            k_decompose_onepass<float><<<grid, 256, shm, s->stream>>>((const float2*)s->amps, start, length, s->nq, smallIsPart ? 1 : 0, (float)floorv,
+                (float2*)outLarge, acc, acc + smallN, needSmall ? 1 : 0);
         } else {
+            if (shm > 48 * 1024) {
+                cudaFuncSetAttribute(k_decompose_onepass<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+            }
+            k_decompose_onepass<double><<<grid, 256, shm, s->stream>>>((const double2*)s->amps, start, length, s->nq, smallIsPart ? 1 : 0, floorv,
+                (double2*)outLarge, acc, acc + smallN, needSmall ? 1 : 0);
+        }
+        s->stats.kernel_launches++;
+        void* outSmall = smallIsPart ? pout : nout;
+        if (outSmall) {
+            const unsigned g2 = stream_grid(s->dev, smallN, 256);
+            DISPATCH_PREC(s, (k_polar_rebuild<float><<<g2, 256, 0, s->stream>>>((float2*)outSmall, smallN, acc, acc + smallN, (float)floorv)),
+                (k_polar_rebuild<double><<<g2, 256, 0, s->stream>>>((double2*)outSmall, smallN, acc, acc + smallN, floorv)));
+            s->stats.kernel_launches++;
+        }
+        e = cudaStreamSynchronize(s->stream);
+        if (scratchLarge) {
+            state_buf_free(s->dev, scratchLarge, largeN * ab);
+        }
+        if (e != cudaSuccess) {
+            return fail(e, "decompose");
+        }
+    } else {
+        // both sides large: global accumulators (double atomics), then two rebuild sweeps
+        const size_t accN = 2 * remPower + 2 * partPower;
+        e = cudaMalloc(&acc, accN * sizeof(double));
+        if (e != cudaSuccess) {
+            return fail(e, "cudaMalloc(decompose marginals)");
+        }
+        cudaMemsetAsync(acc, 0, accN * sizeof(double), s->stream);
+        double* remProb = acc;
+        double* remAngle = acc + remPower;
+        double* partProb = dest ? acc + 2 * remPower : nullptr;
+        double* partAngle = dest ? acc + 2 * remPower + partPower : nullptr;
+        const unsigned grid = std::min<unsigned>(stream_grid(s->dev, n, 256), (unsigned)sm_count(s->dev) * 8U);
+        DISPATCH_PREC(s, (k_decompose_marginals<float><<<grid, 256, 0, s->stream>>>((const float2*)s->amps, n, start, length, (float)floorv, remProb, remAngle, partProb, partAngle, 0)),
+            (k_decompose_marginals<double><<<grid, 256, 0, s->stream>>>((const double2*)s->amps, n, start, length, floorv, remProb, remAngle, partProb, partAngle, 0)));
+        s->stats.kernel_launches++;
+        {
+            const unsigned g2 = stream_grid(s->dev, remPower, 256);
+            DISPATCH_PREC(s, (k_polar_rebuild<float><<<g2, 256, 0, s->stream>>>((float2*)nout, remPower, remProb, remAngle, (float)floorv)),
+                (k_polar_rebuild<double><<<g2, 256, 0, s->stream>>>((double2*)nout, remPower, remProb, remAngle, floorv)));
+            s->stats.kernel_launches++;
+        }
+        if (dest) {
             const unsigned g3 = stream_grid(s->dev, partPower, 256);
             DISPATCH_PREC(s, (k_polar_rebuild<float><<<g3, 256, 0, s->stream>>>((float2*)pout, partPower, partProb, partAngle, (float)floorv)),
                 (k_polar_rebuild<double><<<g3, 256, 0, s->stream>>>((double2*)pout, partPower, partProb, partAngle, floorv)));
             s->stats.kernel_launches++;
-            cudaStreamSynchronize(s->stream);
-            if (dest->dev == s->dev) {
-                free_amps(dest);
-                dest->amps = pout;
-            } else {
-                DevGuard g4(dest->dev);
-                rc = alloc_amps(dest, false);
-                if (rc == B200SV_OK) {
-                    e = cudaMemcpyPeer(dest->amps, dest->dev, pout, s->dev, partPower * s->amp_bytes());
-                    if (e != cudaSuccess) {
-                        rc = cuda_fail(e, "decompose peer copy");
-                    }
-                }
-                cudaFree(pout);
-            }
+        }
+        e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) {
+            return fail(e, "decompose");
         }
     }
-    e = cudaStreamSynchronize(s->stream);
     cudaFree(acc);
-    if (e != cudaSuccess && rc == B200SV_OK) {
-        rc = cuda_fail(e, "decompose");
+    acc = nullptr;
+    int rc = B200SV_OK;
+    if (dest) {
+        // the part state was built on s's device: adopt it, or move it if dest lives elsewhere
+        if (dest->dev == s->dev) {
+            free_amps(dest);
+            dest->amps = pout;
+            dest->amps_bytes = partPower * ab;
+        } else {
+            DevGuard g4(dest->dev);
+            rc = alloc_amps(dest, false);
+            if (rc == B200SV_OK) {
+                e = cudaMemcpyPeer(dest->amps, dest->dev, pout, s->dev, partPower * ab);
+                if (e != cudaSuccess) {
+                    rc = cuda_fail(e, "decompose peer copy");
+                }
+            }
+            state_buf_free(s->dev, pout, partPower * ab);
+        }
+        pout = nullptr;
     }
     if (rc != B200SV_OK) {
-        cudaFree(nout);
+        state_buf_free(s->dev, nout, remPower * ab);
         return rc;
     }
     free_amps(s);
     s->amps = nout;
+    s->amps_bytes = remPower * ab;
     s->nq = nl;
     return B200SV_OK;
 }

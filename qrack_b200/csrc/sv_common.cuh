@@ -82,6 +82,7 @@ struct State {
     int nq = 0;
     int prec = 32;
     void* amps = nullptr; // device buffer (nullptr == the zero state)
+    size_t amps_bytes = 0; // size it was allocated with through the state-buffer cache (0: plain cudaMalloc / external)
     bool external = false;
     void* spare = nullptr; // second state-sized buffer kept by the out-of-place QAlu sweeps (ping-pong with amps)
     size_t spare_bytes = 0;

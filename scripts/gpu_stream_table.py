@@ -60,8 +60,9 @@ for prec in [int(p) for p in os.environ.get("PRECS", "32").split(",")]:
     row(tag + "XMask 5 qubits (dedicated sweep)", timed(q, lambda: (q.be.set_fusion(0), q.XMask(0b1000100010001000100000), q.be.set_fusion(1))), 2 * N * S)
     row(tag + "PhaseParity 4 qubits", timed(q, lambda: q.PhaseParity(0.7, 0b10001000100010000)), 2 * N * S)
     row(tag + "PhaseRootNMask 4 qubits", timed(q, lambda: q.PhaseRootNMask(3, 0b10001000100010000)), 2 * N * S)
-    row(tag + "Prob(q=20)", timed(q, lambda: q.be.prob_mask(1 << 20, 1 << 20)), N * S // 2, "reads the matching half")
-    row(tag + "Prob(q=2)", timed(q, lambda: q.be.prob_mask(1 << 2, 1 << 2)), N * S, "low qubit: every sector is touched")
+    # (Prob of ONE qubit is served by the memoised all-marginals sweep below)
+    row(tag + "ProbReg 2 high qubits", timed(q, lambda: q.be.prob_mask((1 << 20) | (1 << 21), 1 << 20)), N * S // 4, "reads the matching quarter")
+    row(tag + "ProbMask 2 low qubits", timed(q, lambda: q.be.prob_mask(0b110, 0b010)), N * S, "low qubits: every sector is touched")
     row(tag + "ProbMask 3 qubits", timed(q, lambda: q.be.prob_mask((1 << 20) | (1 << 11) | (1 << 25), 1 << 20)), N * S // 8)
     row(tag + "ProbParity 4 qubits", timed(q, lambda: q.be.prob_parity(0b10001000100010000)), N * S)
     row(tag + "all single-qubit marginals", timed(q, lambda: q.Prob(5), setup=lambda: q.be.set_amplitude(0, q.be.get_amplitude(0))), N * S,

@@ -229,6 +229,11 @@ class _ShardedBackend:
         self.exchange_bytes = 0
         self.local_swaps = 0
         self._batch = []  # local single-target gates waiting for ONE b200sv_apply_gates call
+        # X gates are never executed: |psi_logical> = X^{xinv} |psi_stored>.  An X (XMask) toggles bits of `xinv`; every later
+        # gate is conjugated (control polarities flip, a target's matrix becomes X m X), every index that goes to or comes
+        # from the stored state is XORed.  QInterface::MACWrapper (include/qinterface.hpp:179-189) wraps each anti-controlled
+        # gate of INC/DEC/ZeroPhaseFlip in XMask ... XMask: on rank-bit qubits those would each cost a page exchange.
+        self.xinv = 0
 
     # ---- helpers ------------------------------------------------------------------------------------------------
     @property
@@ -246,6 +251,10 @@ class _ShardedBackend:
         for q in _bits(idx):
             out |= 1 << self.perm[q]
         return out
+
+    def _stored(self, idx: int, mask: Optional[int] = None) -> int:
+        """logical basis index -> the logical-qubit-ordered index of the STORED vector (pending X inversions applied)"""
+        return idx ^ (self.xinv if mask is None else (self.xinv & mask))
 
     def _split(self, pmask: int):
         lm = pmask & ((1 << self.nl) - 1)
@@ -277,6 +286,7 @@ class _ShardedBackend:
 
     def set_permutation(self, perm: int, phase: complex):
         self.pending.clear()
+        self.xinv = 0
         self.perm = list(range(self.n))
         self.loc.Finish()
         self.shard.zero_live()
@@ -297,24 +307,35 @@ class _ShardedBackend:
             m = list(mtrx)
             if off1 & diff:  # off1 holds the |1> branch
                 m = [m[3], m[2], m[1], m[0]]
-            self.pending.append(_Gate(t, pmask & ~diff, off1 & ~diff, m))
+            cmask = pmask & ~diff
+            if not cmask and m[0] == 0 and m[3] == 0 and m[1] == 1 and m[2] == 1:
+                self.xinv ^= 1 << t                             # a bare X: one more inversion, nothing to execute
+                return None
+            cval = (off1 & ~diff) ^ (self.xinv & cmask)      # control polarities see the stored bits
+            if (self.xinv >> t) & 1:
+                m = [m[3], m[2], m[1], m[0]]                    # X m X
+            self.pending.append(_Gate(t, cmask, cval, m))
             return None
         if bin(diff).count("1") == 2 and pmask == diff and mtrx[0] == 0 and mtrx[3] == 0 and mtrx[1] == 1 and mtrx[2] == 1:
             # uncontrolled Swap: relabel, no data motion (QPager::Swap does the same for meta qubits)
             self.flush()
             a, b = [q for q in _bits(diff)]
             self.perm[a], self.perm[b] = self.perm[b], self.perm[a]
+            xa, xb = (self.xinv >> a) & 1, (self.xinv >> b) & 1
+            if xa != xb:                                        # the pending inversions travel with the qubits
+                self.xinv ^= (1 << a) | (1 << b)
             return None
         raise NotImplementedError("two-target Apply2x2 forms (ISwap/SqrtSwap/CSwap) are not sharded; decompose them")
 
     def xmask(self, mask):
-        for q in _bits(mask):
-            self.pending.append(_Gate(q, 0, 0, [0j, 1 + 0j, 1 + 0j, 0j]))
+        self.xinv ^= mask   # never executed: see __init__
 
     def phase_parity(self, radians, mask):
         self.flush()
         lm, gm = self._split(self._pmask(mask))
         sign = -1.0 if (bin(self.rank & gm).count("1") & 1) else 1.0
+        if bin(self.xinv & mask).count("1") & 1:
+            sign = -sign                                         # parity of the logical bits = stored parity ^ parity of the inversions
         if lm:
             self.loc.PhaseParity(sign * radians, lm)
         else:  # all qubits are rank bits: a per-rank scalar, e^{+i r/2} for odd parity, e^{-i r/2} for even (state.cpp:1035-1051)
@@ -323,6 +344,14 @@ class _ShardedBackend:
             self.loc.Mtrx([ph, 0j, 0j, ph], 0)
 
     def phase_root_n_mask(self, n, mask):
+        if self.xinv & mask:
+            # popcount of the LOGICAL bits is not a function of the stored popcount: the mask phase is the product of the
+            # single-qubit PhaseRootN gates, which the gate path conjugates correctly
+            rad = -math.pi / (1 << (n - 1))
+            ph = complex(math.cos(rad), math.sin(rad))
+            for q in _bits(mask):
+                self.apply2x2(0, 1 << q, [1 + 0j, 0j, 0j, ph], [1 << q], 1.0, 0.0, False)
+            return
         self.flush()
         lm, gm = self._split(self._pmask(mask))
         steps = bin(self.rank & gm).count("1")
@@ -336,7 +365,7 @@ class _ShardedBackend:
     def apply_m(self, mask, result, nrm: complex):
         self.flush()
         lm, gm = self._split(self._pmask(mask))
-        lr, gr = self._split(self._pindex(result))
+        lr, gr = self._split(self._pindex(self._stored(result, mask)))
         if (self.rank & gm) != gr:
             self.loc.Finish()
             self.shard.zero_live()
@@ -349,7 +378,7 @@ class _ShardedBackend:
     def prob_mask(self, mask, perm) -> float:
         self.flush()
         lm, gm = self._split(self._pmask(mask))
-        lr, gr = self._split(self._pindex(perm))
+        lr, gr = self._split(self._pindex(self._stored(perm, mask)))
         v = 0.0
         if (self.rank & gm) == gr:
             v = self.loc.be.prob_mask(lm, lr) if lm else self.loc.be.norm(0.0)
@@ -361,6 +390,8 @@ class _ShardedBackend:
         odd_rank = bin(self.rank & gm).count("1") & 1
         tot = self.loc.be.norm(0.0)
         podd = self.loc.be.prob_parity(lm) if lm else 0.0
+        if bin(self.xinv & mask).count("1") & 1:
+            odd_rank ^= 1                                        # odd logical parity = even stored parity
         return self._allreduce([(tot - podd) if odd_rank else podd])[0]
 
     def norm(self, thresh) -> float:
@@ -373,7 +404,7 @@ class _ShardedBackend:
 
     def get_amplitude(self, perm: int) -> complex:
         self.flush()
-        p = self._pindex(perm)
+        p = self._pindex(self._stored(perm))
         a = 0j
         if (p >> self.nl) == self.rank:
             a = self.loc.GetAmplitude(p & ((1 << self.nl) - 1))
@@ -382,7 +413,7 @@ class _ShardedBackend:
 
     def set_amplitude(self, perm: int, amp: complex):
         self.flush()
-        p = self._pindex(perm)
+        p = self._pindex(self._stored(perm))
         if (p >> self.nl) == self.rank:
             self.loc.SetAmplitude(p & ((1 << self.nl) - 1), amp)
 
@@ -402,7 +433,10 @@ class _ShardedBackend:
         # phys index bit perm[q] holds logical qubit q: transpose the 2^n tensor accordingly
         t = phys.reshape([2] * self.n)  # axis 0 = most significant physical bit (n-1)
         axes = [self.n - 1 - self.perm[q] for q in range(self.n - 1, -1, -1)]
-        return np.ascontiguousarray(t.transpose(axes)).reshape(-1)
+        v = np.ascontiguousarray(t.transpose(axes)).reshape(-1)
+        if self.xinv:
+            v = v[np.arange(v.size, dtype=np.int64) ^ self.xinv]   # logical[i] = stored[i ^ xinv]
+        return v
 
     def get_probs(self):
         s = self.get_state()
@@ -446,7 +480,7 @@ class _ShardedBackend:
         if self.rank == pick:
             idx = float((pick << self.nl) | self.loc.be.sample(rnd - cum))
         phys = int(round(self._allreduce([idx])[0]))
-        return self._logical_index(phys)
+        return self._logical_index(phys) ^ self.xinv
 
     def highest_prob(self) -> int:
         self.flush()
@@ -454,7 +488,7 @@ class _ShardedBackend:
         a = self.loc.GetAmplitude(li)
         rows = self._gather_scalars([a.real * a.real + a.imag * a.imag, float((self.rank << self.nl) | li)])
         best = max(range(self.world), key=lambda r: (rows[r][0], -r))
-        return self._logical_index(int(round(rows[best][1])))
+        return self._logical_index(int(round(rows[best][1]))) ^ self.xinv
 
     def prob_mask_all(self, mask: int) -> np.ndarray:
         self.flush()
@@ -474,7 +508,14 @@ class _ShardedBackend:
                 if (j >> i) & 1:
                     o |= 1 << where[b]
             out[o] += float(loc[j])
-        return np.asarray(self._allreduce(out.tolist()), dtype=self.real)
+        res = np.asarray(self._allreduce(out.tolist()), dtype=self.real)
+        flip = 0
+        for j, q in enumerate(qs):
+            if (self.xinv >> q) & 1:
+                flip |= 1 << j
+        if flip:
+            res = res[np.arange(res.size, dtype=np.int64) ^ flip]   # logical outcome = stored outcome ^ inversions on the mask
+        return res
 
     _UNSUPPORTED = ("collapse_parity", "uniform_parity_rz", "uniformly_controlled", "inner", "expectation", "compose", "decompose",
                     "dispose_perm", "get_page", "set_page", "copy_page", "shuffle", "copy_state", "clone")

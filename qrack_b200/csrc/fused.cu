@@ -31,8 +31,9 @@ constexpr int MAX_PASS = 8;
 constexpr int MAX_OPS = 96;
 constexpr int MAX_HOST_OPS = 384; // gates per sweep before merging (LAYER / DIAG groups shrink them to <= MAX_OPS device ops)
 constexpr int MAX_SLOTS = 128; // per-tile phase table (1 + register-bit phases of the DIAG ops); filled by warps 4..7
-constexpr int MAX_NCH = 16; // register chunks per sub-block (RB <= 4)
-constexpr int MAX_NA = 32;  // register amplitudes per sub-block
+constexpr int MAX_NCH = 32; // register chunks per sub-block (RB <= 5)
+constexpr int MAX_NA = 64;  // register amplitudes per sub-block
+constexpr int MAX_JR = 6;   // register-bit indices (fp32 RB = 5: qubit 0 + 5 chunk bits)
 
 // device op codes.  Single-gate ops: kind * 5 + jr (jr = register-bit index of the target; dense so that the dispatch is a
 // shallow branch tree).  OPC_STAGE = per-bit phases + Hadamard butterflies; OPC_SCALE = per-tile scalar.
@@ -44,12 +45,15 @@ constexpr uint32_t OPC_SCALE = 16U; // multiply every amplitude by the per-tile 
 //   The phase of bit J is the product of (a) one per-tile table slot (members whose predicate is outer qubits AND bit J) and
 //   (b) thread-level members (predicate: outer qubits AND thread bits AND bit J), tested per thread against the per-tile
 //   "effective" (mask, val) table.  Group 0 = members without a register bit (thread-uniform phase on the whole sub-block).
-//   header: emask = hmask | slotMask << 5 | anyMembers << 10; lmaskSb = first table slot; lvalSb = first member;
-//   m[0] (as uint32) = six 5-bit member counts (group 0, then bits 0..4).
+//   header: emask = hmask | slotMask << 6 | anyMembers << 12 | activeBits << 13; lmaskSb = first table slot; lvalSb = first
+//   member; m[0] (as uint32) = seven 4-bit member counts (group 0, then register bits 0..5).
 constexpr uint32_t OPC_STAGE = 17U;
 // OPC_PH2 + pair: phase on the 2^(J-2)... register amplitudes that have BOTH register bits of the pair set (CZ / CPhase whose
 // two qubits are register-resident); pair index = k * (k - 1) / 2 + j for bits j < k.
-constexpr uint32_t OPC_PH2 = 18U; // .. 27
+constexpr uint32_t OPC_PH2 = 18U; // .. 32 (15 pairs of 6 register bits)
+// STAGE header fields (DevOp.emask) and member-count packing (first word of DevOp.m): 6-bit masks, 7 groups x 4 bits
+constexpr int ST_SM_SHIFT = 6, ST_ANY_BIT = 12, ST_ACT_SHIFT = 13, ST_CNT_BITS = 4;
+constexpr uint32_t ST_MASK = 63U, ST_CNT_MASK = 15U;
 constexpr uint32_t CODE_HAS_SB = 0x100U;
 constexpr uint32_t CODE_HAS_OUTER = 0x200U; // the op has a predicate on qubits outside the tile: consult the per-tile ballot
 constexpr int MAX_MEMBERS = 320; // thread-level phase members per sweep (8 bytes each in the double-buffered per-tile table)
@@ -310,13 +314,13 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
 #define SV_J(J) (((1 << (J)) < NA) ? (J) : 0)
 #define SV_CASES(J)                                                                                                    \
     case K_XSWAP * 5 + J:                                                                                              \
-        app_xswap<R, SV_J(J), NA>(a, em);                                                                              \
+        app_xswap<R, SV_J(J), NA>(a, (uint32_t)em);                                                                           \
         break;                                                                                                         \
     case K_GEN_U * 5 + J:                                                                                              \
-        app_general<R, SV_J(J), NA, false>(a, m, em);                                                                  \
+        app_general<R, SV_J(J), NA, false>(a, m, (uint32_t)em);                                                                \
         break;                                                                                                         \
     case K_GEN_P * 5 + J:                                                                                              \
-        app_general<R, SV_J(J), NA, true>(a, m, em);                                                                   \
+        app_general<R, SV_J(J), NA, true>(a, m, (uint32_t)em);                                                                \
         break;
 #define SV_PAIR(K, J)                                                                                                  \
     case OPC_PH2 + (K) * ((K)-1) / 2 + (J):                                                                            \
@@ -325,9 +329,9 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         }                                                                                                              \
         break;
     if ((hd.x & 0xffU) == OPC_STAGE) {
-        const uint32_t hm = hd.y & 31U, sm = (hd.y >> 5) & 31U, act = hd.y >> 11;
+        const uint32_t hm = hd.y & ST_MASK, sm = (hd.y >> ST_SM_SHIFT) & ST_MASK, act = hd.y >> ST_ACT_SHIFT;
         uint32_t slot = hd.z, mk = hd.w;
-        if (!FULL && !(hd.y & (1U << 10))) {
+        if (!FULL && !(hd.y & (1U << ST_ANY_BIT))) {
             // the common shape: per-tile slot phases and butterflies only (no thread-level members)
 #define SV_STAGE_FAST(J)                                                                                               \
     if (((1 << (J)) < NA) && ((act >> (J)) & 1U)) {                                                                    \
@@ -347,10 +351,11 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
             SV_STAGE_FAST(2)
             SV_STAGE_FAST(3)
             SV_STAGE_FAST(4)
+            SV_STAGE_FAST(5)
 #undef SV_STAGE_FAST
             return;
         }
-        const uint32_t cnts = (hd.y & (1U << 10)) ? *reinterpret_cast<const uint32_t*>(op.m) : 0U;
+        const uint32_t cnts = (hd.y & (1U << ST_ANY_BIT)) ? *reinterpret_cast<const uint32_t*>(op.m) : 0U;
         // product of the thread-level members [mk, mk + c) that fire for this thread, times (px, py)
 #define SV_MEMBERS(c)                                                                                                  \
     _Pragma("unroll 1") for (uint32_t k = 0; k < (c); ++k, ++mk) {                                                                         \
@@ -363,7 +368,7 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         }                                                                                                              \
     }
         {
-            const uint32_t c = cnts & 31U;
+            const uint32_t c = cnts & ST_CNT_MASK;
             if (c) {
                 R px = (R)1, py = (R)0;
                 SV_MEMBERS(c)
@@ -378,7 +383,7 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         }
 #define SV_STAGE_BIT(J)                                                                                                \
     if (((1 << (J)) < NA) && ((act >> (J)) & 1U)) {                                                                    \
-        const uint32_t c = (cnts >> (5 * ((J) + 1))) & 31U;                                                            \
+        const uint32_t c = (cnts >> (ST_CNT_BITS * ((J) + 1))) & ST_CNT_MASK;                                          \
         if (((sm >> (J)) & 1U) | c) {                                                                                  \
             R px = (R)1, py = (R)0;                                                                                    \
             if ((sm >> (J)) & 1U) {                                                                                    \
@@ -400,6 +405,7 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         SV_STAGE_BIT(2)
         SV_STAGE_BIT(3)
         SV_STAGE_BIT(4)
+        SV_STAGE_BIT(5)
 #undef SV_STAGE_BIT
 #undef SV_MEMBERS
         return;
@@ -408,7 +414,8 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
     if (hd.x & CODE_HAS_SB) {
         tp = (xsb & hd.z) == hd.w;
     }
-    const uint32_t em = tp ? hd.y : 0U;
+    // register-amplitude predicate mask (64 bits when the sub-block holds 64 amplitudes: high word = third word of op.m)
+    const uint64_t em = tp ? ((uint64_t)hd.y | ((NA > 32) ? ((uint64_t)reinterpret_cast<const uint32_t*>(op.m)[2] << 32) : 0ULL)) : 0ULL;
     if (FULL && (hd.x & 0xffU) < OPC_PHGEN) {
         switch (hd.x & 0xffU) {
             SV_CASES(0)
@@ -439,12 +446,17 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         SV_PAIR(4, 1)
         SV_PAIR(4, 2)
         SV_PAIR(4, 3)
+        SV_PAIR(5, 0)
+        SV_PAIR(5, 1)
+        SV_PAIR(5, 2)
+        SV_PAIR(5, 3)
+        SV_PAIR(5, 4)
     case OPC_PHGEN: {
         const typename O::Ph ph = O::mkph(m[0], m[1]);
 #pragma unroll
         for (int e = 0; e < NA; ++e) {
             const A v = O::mulc(a[e], ph);
-            a[e] = ((em >> e) & 1U) ? v : a[e];
+            a[e] = ((em >> e) & 1ULL) ? v : a[e];
         }
     } break;
     default:
@@ -517,7 +529,7 @@ __global__ void __launch_bounds__(NT, MINB)
     constexpr int NCH = 1 << RB;
     constexpr int NA = NCH * APC;
     static_assert(NA <= MAX_NA && NCH <= MAX_NCH, "register sub-block too large");
-    static_assert(NT >= 128 + MAX_SLOTS, "the per-tile preamble uses warps 0..3 and one thread per table slot");
+    static_assert(NT >= 128, "the per-tile preamble uses warps 0..3 for the ballots and the tile scalar");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* tileB = smem;
     unsigned char* sprog = smem + ((size_t)16 << KC);
@@ -602,9 +614,10 @@ __global__ void __launch_bounds__(NT, MINB)
                 tileScale[0] = fx * (R)sw.scale;
                 tileScale[1] = fy * (R)sw.scale;
             }
-        } else if (tid - 127 < sw.nSlots) {
-            // product (in double) of the member phases that fire for this tile
-            const int sl = tid - 127;
+        }
+        // table slots 1..: product (in double) of the member phases that fire for this tile; one thread per slot, the threads
+        // beyond the four role warps first (NT = 256), everybody when the CTA has only those four (NT = 128)
+        for (int sl = 1 + ((NT > 128) ? (tid >= 128 ? tid - 128 : tid + NT - 128) : tid); sl < sw.nSlots; sl += NT) {
             double fx = 1.0, fy = 0.0;
             for (int i = sw.slotBeg[sl], e = sw.slotBeg[sl + 1]; i < e; ++i) {
                 const DevOuterPhase<R>& op = outer[i];
@@ -1544,7 +1557,7 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                 roffA[e * APC + w] = (off << cfg.apcLog) | (uint32_t)w;
             }
         }
-        const uint32_t fullE = (NA >= 32) ? 0xffffffffU : ((1U << NA) - 1U);
+        const uint64_t fullE = (NA >= 64) ? ~0ULL : ((1ULL << NA) - 1ULL);
         auto reg_index = [&](int tb) {
             int jr = 0;
             for (int b = 0; b < tb; ++b) {
@@ -1571,17 +1584,17 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
         // diagonal except the butterflies, so a phase on bit J may join until the stage holds a butterfly on J; the stage is
         // emitted (closed) before the first single op that does not commute with its contents, or at the end of the pass.
         struct Stage {
-            bool h[5];
-            std::vector<DevOuterPhase<R>> slot[5]; // outer-only members of bit J's phase (per-tile product -> one table slot)
-            std::vector<DevMember<R>> thr[6];      // group 0 = thread-uniform, 1 + J = bit J
+            bool h[MAX_JR];
+            std::vector<DevOuterPhase<R>> slot[MAX_JR]; // outer-only members of bit J's phase (per-tile product -> one table slot)
+            std::vector<DevMember<R>> thr[MAX_JR + 1];  // group 0 = thread-uniform, 1 + J = bit J
             bool any;
         } st;
         auto stage_reset = [&]() {
-            for (int b = 0; b < 5; ++b) {
+            for (int b = 0; b < MAX_JR; ++b) {
                 st.h[b] = false;
                 st.slot[b].clear();
             }
-            for (int g = 0; g < 6; ++g) {
+            for (int g = 0; g < MAX_JR + 1; ++g) {
                 st.thr[g].clear();
             }
             st.any = false;
@@ -1589,14 +1602,14 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
         stage_reset();
         auto stage_slots = [&]() {
             int n = 0;
-            for (int b = 0; b < 5; ++b) {
+            for (int b = 0; b < MAX_JR; ++b) {
                 n += st.slot[b].empty() ? 0 : 1;
             }
             return n;
         };
         auto stage_members = [&]() {
             size_t n = 0;
-            for (int g = 0; g < 6; ++g) {
+            for (int g = 0; g < MAX_JR + 1; ++g) {
                 n += st.thr[g].size();
             }
             return n;
@@ -1610,8 +1623,8 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
             uint32_t hm = 0, sm = 0, cnts = 0;
             d.lmaskSb = (uint32_t)slotMembers.size() + 1U; // first table slot of this stage
             d.lvalSb = (uint32_t)memberList.size();        // first thread-level member
-            for (int g = 0; g < 6; ++g) {
-                cnts |= (uint32_t)st.thr[g].size() << (5 * g);
+            for (int g = 0; g < MAX_JR + 1; ++g) {
+                cnts |= (uint32_t)st.thr[g].size() << (ST_CNT_BITS * g);
                 memberList.insert(memberList.end(), st.thr[g].begin(), st.thr[g].end());
             }
             for (int b = 0; b < JRN; ++b) {
@@ -1624,13 +1637,13 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                 }
             }
             uint32_t act = hm | sm;
-            for (int b = 0; b < 5; ++b) {
-                if ((cnts >> (5 * (b + 1))) & 31U) {
+            for (int b = 0; b < MAX_JR; ++b) {
+                if ((cnts >> (ST_CNT_BITS * (b + 1))) & ST_CNT_MASK) {
                     act |= 1U << b;
                 }
             }
             d.code = OPC_STAGE;
-            d.emask = hm | (sm << 5) | (cnts ? (1U << 10) : 0U) | (act << 11);
+            d.emask = hm | (sm << ST_SM_SHIFT) | (cnts ? (1U << ST_ANY_BIT) : 0U) | (act << ST_ACT_SHIFT);
             memcpy(d.m, &cnts, sizeof(cnts));
             dops.push_back(d);
             stage_reset();
@@ -1663,7 +1676,7 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                     }
                     auto fits = [&]() {
                         return asSlot ? (slotMembers.size() + (size_t)stage_slots() + (st.slot[jr].empty() ? 1U : 0U) + 2U < (size_t)MAX_SLOTS)
-                                      : (st.thr[jr + 1].size() < 31U && memberList.size() + stage_members() + 1U < (size_t)MAX_MEMBERS);
+                                      : (st.thr[jr + 1].size() < (size_t)ST_CNT_MASK && memberList.size() + stage_members() + 1U < (size_t)MAX_MEMBERS);
                     };
                     if (!fits()) {
                         close_stage();
@@ -1731,16 +1744,20 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
             d.oval = hop.cval & ~tileMask;
             d.lmaskSb = lmask & ~regAmpMask;
             d.lvalSb = lval & ~regAmpMask;
-            uint32_t em = 0;
+            uint64_t em = 0;
             for (int e = 0; e < NA; ++e) {
                 if ((roffA[e] & lmr) == lvr) {
-                    em |= 1U << e;
+                    em |= 1ULL << e;
                 }
             }
-            d.emask = em;
+            d.emask = (uint32_t)em;
             const bool uncond = (em == fullE && d.lmaskSb == 0);
             for (int k = 0; k < 8; ++k) {
                 d.m[k] = (R)hop.m[k];
+            }
+            if (NA > 32) { // 64 register amplitudes (fp32, RB = 5; phase ops only): the high half of the mask rides in the third word of m
+                const uint32_t hi = (uint32_t)(em >> 32);
+                memcpy(reinterpret_cast<unsigned char*>(d.m) + 8, &hi, sizeof(hi));
             }
             uint32_t code = 0;
             if (hop.kind == OP_PHASE) {
@@ -1809,15 +1826,15 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                     uint32_t cnts = 0;
                     memcpy(&cnts, dops[o].m, sizeof(cnts));
                     int nm = 0, nsl = 0;
-                    for (int g = 0; g < 6; ++g) {
-                        nm += (int)((cnts >> (5 * g)) & 31U);
+                    for (int g = 0; g < MAX_JR + 1; ++g) {
+                        nm += (int)((cnts >> (ST_CNT_BITS * g)) & ST_CNT_MASK);
                     }
-                    for (int b = 0, sl = (int)dops[o].lmaskSb - 1; b < 5; ++b) {
-                        if ((dops[o].emask >> 5) & (1U << b)) {
+                    for (int b = 0, sl = (int)dops[o].lmaskSb - 1; b < MAX_JR; ++b) {
+                        if ((dops[o].emask >> ST_SM_SHIFT) & (1U << b)) {
                             nsl += (int)slotMembers[sl++].size();
                         }
                     }
-                    fprintf(stderr, " STAGE(h%x,s%x:%d,t%d)", dops[o].emask & 31U, (dops[o].emask >> 5) & 31U, nsl, nm);
+                    fprintf(stderr, " STAGE(h%x,s%x:%d,t%d)", dops[o].emask & ST_MASK, (dops[o].emask >> ST_SM_SHIFT) & ST_MASK, nsl, nm);
                 } else if (c == OPC_SCALE) {
                     fprintf(stderr, " SCALE");
                 } else if (c == OPC_PHGEN) {
@@ -2092,15 +2109,41 @@ static int knob_rewrite()
     }();
     return v;
 }
+
 constexpr int FUSED_KC = 12;
 constexpr int FUSED_NT = 256;
 
-static TileCfg state_cfg(int nq, int prec)
+static int knob_rb5()
+{
+    static const int v = [] {
+        const char* e = getenv("B200SV_RB5");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+// light = the flush holds no swap / general-matrix op: its sweeps run on the light kernel variant, which has the registers for
+// 2^5-chunk sub-blocks (fp32: 64 amplitudes, 6 register qubits per pass) on 128-thread CTAs — half the decode work per
+// amplitude and fewer passes per sweep.  Needs full-size tiles.
+static TileCfg state_cfg(int nq, int prec, bool light = false)
 {
     const FusedKnobs& k = knobs();
-    TileCfg c = make_cfg(nq, prec, FUSED_KC, prec == 32 ? k.RB : k.RB64, prec == 32 ? k.L32 : k.L64, FUSED_NT);
+    int rb = prec == 32 ? k.RB : k.RB64, nt = FUSED_NT;
+    if (light && knob_rb5() && rb == 4 && nq >= FUSED_KC + 2) {
+        rb = 5;
+        nt = 128;
+    }
+    TileCfg c = make_cfg(nq, prec, FUSED_KC, rb, prec == 32 ? k.L32 : k.L64, nt);
     c.bundle = k.bundle;
     return c;
+}
+static bool flush_is_light(const std::vector<HostOp>& ops)
+{
+    for (const HostOp& h : ops) {
+        if (h.kind == OP_GENERAL || h.kind == OP_XSWAP) {
+            return false;
+        }
+    }
+    return true;
 }
 
 int fused_flush(State* s)
@@ -2119,7 +2162,7 @@ int fused_flush(State* s)
     if (pending.empty()) {
         return xtail ? launch_xmask(s, xtail) : B200SV_OK;
     }
-    const TileCfg cfg = state_cfg(s->nq, s->prec);
+    const TileCfg cfg = state_cfg(s->nq, s->prec, flush_is_light(pending));
     Arena* ar = get_arena(s);
     if (!ar->done) {
         SV_CUDA(cudaEventCreateWithFlags(&ar->done, cudaEventDisableTiming));
@@ -2157,7 +2200,17 @@ int fused_flush(State* s)
         const unsigned char* dp = ar->dev + segs[i].off;
         const uint32_t pb = (uint32_t)segs[i].bytes, sb = (uint32_t)segs[i].scratch;
         const bool full = knob_force_full() || reinterpret_cast<const DevSweep*>(buf.data() + segs[i].off)->needFull != 0;
-        if (s->prec == 32) {
+        if (cfg.RB == 5) {
+            if (full) {
+                set_error("fused sweep: a full op in a light flush");
+                return B200SV_ESTATE;
+            }
+            if (s->prec == 32) {
+                SV_TRY((launch_sweep_v<float, FUSED_KC, 5, 128, 2, false>(s, dp, pb, sb, nTiles)));
+            } else {
+                SV_TRY((launch_sweep_v<double, FUSED_KC, 5, 128, 2, false>(s, dp, pb, sb, nTiles)));
+            }
+        } else if (s->prec == 32) {
             if (cfg.RB == 4) {
                 SV_TRY((launch_sweep<float, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles, full)));
             } else {
@@ -2209,7 +2262,12 @@ static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xs
     if (code & CODE_HAS_SB) {
         tp = (xsb & lmaskSb) == lvalSb;
     }
-    const uint32_t em = tp ? emask : 0U;
+    uint64_t em = tp ? (uint64_t)emask : 0ULL;
+    if (tp && NA > 32) {
+        uint32_t hi = 0;
+        memcpy(&hi, reinterpret_cast<const unsigned char*>(op.m) + 8, sizeof(hi));
+        em |= (uint64_t)hi << 32;
+    }
     const uint32_t c = code & 0xffU;
     auto had = [&](int J) {
         for (int e = 0; e < NA; ++e) {
@@ -2228,9 +2286,9 @@ static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xs
         }
     };
     if (c == OPC_STAGE) {
-        const uint32_t hm = emask & 31U, sm = (emask >> 5) & 31U;
+        const uint32_t hm = emask & ST_MASK, sm = (emask >> ST_SM_SHIFT) & ST_MASK;
         uint32_t slot = lmaskSb, mk = lvalSb, cnts = 0;
-        if (emask & (1U << 10)) {
+        if (emask & (1U << ST_ANY_BIT)) {
             memcpy(&cnts, op.m, sizeof(cnts));
         }
         auto run_members = [&](uint32_t cN, R& px, R& py) {
@@ -2245,7 +2303,7 @@ static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xs
         };
         {
             R px = (R)1, py = (R)0;
-            run_members(cnts & 31U, px, py);
+            run_members(cnts & ST_CNT_MASK, px, py);
             if (px != (R)1 || py != (R)0) {
                 for (int e = 0; e < NA; ++e) {
                     a[e] = emu_mul(a[e], px, py);
@@ -2253,7 +2311,7 @@ static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xs
             }
         }
         for (int J = 0; (1 << J) < NA; ++J) {
-            const uint32_t cN = (cnts >> (5 * (J + 1))) & 31U;
+            const uint32_t cN = (cnts >> (ST_CNT_BITS * (J + 1))) & ST_CNT_MASK;
             R px = (R)1, py = (R)0;
             if ((sm >> J) & 1U) {
                 px = tileScale[2 * slot];
@@ -2456,7 +2514,7 @@ int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, voi
 {
     std::vector<HostOp> pending;
     const uint64_t xtail = lower_queue(q, pending);
-    const TileCfg cfg = state_cfg(n_qubits, precision);
+    const TileCfg cfg = state_cfg(n_qubits, precision, flush_is_light(pending));
     std::vector<unsigned char> buf;
     while (!pending.empty()) {
         size_t bytes = 0, scratch = 0, nops = 0;
@@ -2518,7 +2576,7 @@ int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targ
     }
     std::vector<HostOp> pending;
     (void)lower_queue(q, pending);
-    const TileCfg cfg = state_cfg(n_qubits, precision);
+    const TileCfg cfg = state_cfg(n_qubits, precision, flush_is_light(pending));
     int sweeps = 0, passes = 0;
     std::vector<unsigned char> buf;
     while (!pending.empty()) {

@@ -2002,14 +2002,25 @@ int b200sv_shuffle(b200sv_t a, b200sv_t b)
         SV_CUDA(cudaGetLastError());
         a->stats.kernel_launches++;
     } else {
+        // no peer access between the two devices: staged through a buffer on a's device (from the state-buffer cache: a
+        // QPager meta gate calls this twice per gate), every copy checked
         void* tmp = nullptr;
-        SV_CUDA(cudaMalloc(&tmp, half * ab));
-        cudaMemcpyAsync(tmp, pa, half * ab, cudaMemcpyDeviceToDevice, a->stream);
-        cudaMemcpyPeerAsync(pa, a->dev, pb, b->dev, half * ab, a->stream);
-        cudaMemcpyPeerAsync(pb, b->dev, tmp, a->dev, half * ab, a->stream);
-        cudaStreamSynchronize(a->stream);
-        cudaFree(tmp);
-        SV_CUDA(cudaGetLastError());
+        cudaError_t e = state_buf_alloc(a->dev, half * ab, &tmp);
+        if (e != cudaSuccess) {
+            return cuda_fail(e, "cudaMalloc(shuffle staging)");
+        }
+        e = cudaMemcpyAsync(tmp, pa, half * ab, cudaMemcpyDeviceToDevice, a->stream);
+        if (e == cudaSuccess) {
+            e = cudaMemcpyPeerAsync(pa, a->dev, pb, b->dev, half * ab, a->stream);
+        }
+        if (e == cudaSuccess) {
+            e = cudaMemcpyPeerAsync(pb, b->dev, tmp, a->dev, half * ab, a->stream);
+        }
+        const cudaError_t es = cudaStreamSynchronize(a->stream);
+        state_buf_free(a->dev, tmp, half * ab);
+        if (e != cudaSuccess || es != cudaSuccess) {
+            return cuda_fail(e != cudaSuccess ? e : es, "shuffle (staged)");
+        }
     }
     SV_TRY(cross_wait(b, a));
     return B200SV_OK;

@@ -45,20 +45,21 @@ constexpr uint32_t OPC_SCALE = 16U; // multiply every amplitude by the per-tile 
 //   The phase of bit J is the product of (a) one per-tile table slot (members whose predicate is outer qubits AND bit J) and
 //   (b) thread-level members (predicate: outer qubits AND thread bits AND bit J), tested per thread against the per-tile
 //   "effective" (mask, val) table.  Group 0 = members without a register bit (thread-uniform phase on the whole sub-block).
-//   header: emask = hmask | slotMask << 6 | anyMembers << 12 | activeBits << 13; lmaskSb = first table slot; lvalSb = first
-//   member; m[0] (as uint32) = seven 4-bit member counts (group 0, then register bits 0..5).
+//   header: emask = hmask | slotMask << 6 | anyMembers << 12 | activeBits << 13 | rotMask << 19 (bit J: the butterfly of bit J is a
+//   real rotation [[c,-s],[s,c]] with (c, s) from the rotation table instead of a Hadamard); lmaskSb = first table slot;
+//   lvalSb = first member | first rotation << 16; m[0] (as uint32) = seven 4-bit member counts (group 0, then register bits 0..5).
 constexpr uint32_t OPC_STAGE = 17U;
 // OPC_PH2 + pair: phase on the 2^(J-2)... register amplitudes that have BOTH register bits of the pair set (CZ / CPhase whose
 // two qubits are register-resident); pair index = k * (k - 1) / 2 + j for bits j < k.
 constexpr uint32_t OPC_PH2 = 18U; // .. 32 (15 pairs of 6 register bits)
 // STAGE header fields (DevOp.emask) and member-count packing (first word of DevOp.m): 6-bit masks, 7 groups x 4 bits
-constexpr int ST_SM_SHIFT = 6, ST_ANY_BIT = 12, ST_ACT_SHIFT = 13, ST_CNT_BITS = 4;
+constexpr int ST_SM_SHIFT = 6, ST_ANY_BIT = 12, ST_ACT_SHIFT = 13, ST_RM_SHIFT = 19, ST_CNT_BITS = 4;
 constexpr uint32_t ST_MASK = 63U, ST_CNT_MASK = 15U;
 constexpr uint32_t CODE_HAS_SB = 0x100U;
 constexpr uint32_t CODE_HAS_OUTER = 0x200U; // the op has a predicate on qubits outside the tile: consult the per-tile ballot
 constexpr int MAX_MEMBERS = 320; // thread-level phase members per sweep (8 bytes each in the double-buffered per-tile table)
 // host (scheduler) op kinds
-enum { OP_GENERAL = 0, OP_HAD = 1, OP_XSWAP = 2, OP_PHASE = 3 };
+enum { OP_GENERAL = 0, OP_HAD = 1, OP_XSWAP = 2, OP_PHASE = 3, OP_ROT = 4 }; // OP_ROT: real rotation [[c,-s],[s,c]], m[0] = c, m[1] = s
 
 template <typename R> struct alignas(16) DevOp {
     uint64_t omask, oval; // predicate on the tile's global base index (qubits outside the tile)
@@ -99,8 +100,9 @@ struct alignas(16) DevSweep {
     int directOut; // 1: the last pass writes straight to HBM; 0: through the smem tile
     int nMem;      // thread-level phase members (DevMember records at memOff)
     int memOff;
+    int nRot;      // real rotations of the STAGE ops ((c, s) pairs at rotOff)
+    int rotOff;
     int needFull;  // 1: the program holds XSWAP / general-matrix ops (launch the FULL kernel variant); 0: STAGE / phase ops only
-    int pad0;
     unsigned short slotBeg[MAX_SLOTS + 1]; // slot s multiplies the outer records [slotBeg[s], slotBeg[s+1])
     uint64_t highLow[MAX_HIGH]; // (2^q - 1) for push_apart of the tile base, ascending
     uint64_t highPow[MAX_HIGH]; // 2^q
@@ -177,6 +179,13 @@ template <> struct AmpOps<float> {
         x = f2add(x, y);
         y = f2fma(y, pk(-2.0f, -2.0f), x);
     }
+    static __device__ __forceinline__ void rot(A& x, A& y, float c, float s)
+    {
+        const ull cc = pk(c, c), ss = pk(s, s), ns = pk(-s, -s);
+        const A nx = f2fma(x, cc, f2mul(y, ns));
+        y = f2fma(y, cc, f2mul(x, ss));
+        x = nx;
+    }
     static __device__ __forceinline__ A scale(A a, float s) { return f2mul(a, pk(s, s)); }
     static __device__ __forceinline__ A unit() { return pk(1.0f, 0.0f); }
     static __device__ __forceinline__ Ph toph(A a)
@@ -218,6 +227,12 @@ template <> struct AmpOps<double> {
         y.x = fma(y.x, -2.0, x.x);
         y.y = fma(y.y, -2.0, x.y);
     }
+    static __device__ __forceinline__ void rot(A& x, A& y, double c, double s)
+    {
+        const A nx = make_double2(fma(c, x.x, -s * y.x), fma(c, x.y, -s * y.y));
+        y = make_double2(fma(c, y.x, s * x.x), fma(c, y.y, s * x.y));
+        x = nx;
+    }
     static __device__ __forceinline__ A scale(A a, double s) { return make_double2(a.x * s, a.y * s); }
     static __device__ __forceinline__ A unit() { return make_double2(1.0, 0.0); }
     static __device__ __forceinline__ Ph toph(A a) { return Ph{ a.x, a.y }; }
@@ -236,6 +251,17 @@ template <typename R, int JR, int NA> __device__ __forceinline__ void app_had(ty
     for (int e = 0; e < NA; ++e) {
         if (!(e & (1 << JR))) {
             AmpOps<R>::had(a[e], a[e | (1 << JR)]);
+        }
+    }
+}
+// real rotation [[c, -s], [s, c]] on register bit JR: 4 packed instructions per amplitude pair (a general 2x2 takes 8)
+template <typename R, int JR, int NA> __device__ __forceinline__ void app_rot(typename AmpOps<R>::A (&a)[NA], R c, R s)
+{
+    typedef AmpOps<R> O;
+#pragma unroll
+    for (int e = 0; e < NA; ++e) {
+        if (!(e & (1 << JR))) {
+            O::rot(a[e], a[e | (1 << JR)], c, s);
         }
     }
 }
@@ -306,7 +332,7 @@ template <typename R> struct alignas(16) DevMember {
 
 template <typename R, int NA, bool FULL>
 __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const DevOp<R>& op, const uint4 hd, uint32_t xsb,
-    const R* __restrict__ tileScale, const DevMember<R>* __restrict__ members, const uint2* __restrict__ eff)
+    const R* __restrict__ tileScale, const DevMember<R>* __restrict__ members, const uint2* __restrict__ eff, const R* __restrict__ rotTab)
 {
     typedef AmpOps<R> O;
     typedef typename O::A A;
@@ -329,8 +355,9 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         }                                                                                                              \
         break;
     if ((hd.x & 0xffU) == OPC_STAGE) {
-        const uint32_t hm = hd.y & ST_MASK, sm = (hd.y >> ST_SM_SHIFT) & ST_MASK, act = hd.y >> ST_ACT_SHIFT;
-        uint32_t slot = hd.z, mk = hd.w;
+        const uint32_t hm = hd.y & ST_MASK, sm = (hd.y >> ST_SM_SHIFT) & ST_MASK, act = (hd.y >> ST_ACT_SHIFT) & ST_MASK,
+                       rm = (hd.y >> ST_RM_SHIFT) & ST_MASK;
+        uint32_t slot = hd.z, mk = hd.w & 0xffffU, ri = hd.w >> 16;
         if (!FULL && !(hd.y & (1U << ST_ANY_BIT))) {
             // the common shape: per-tile slot phases and butterflies only (no thread-level members)
 #define SV_STAGE_FAST(J)                                                                                               \
@@ -343,7 +370,12 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
             }                                                                                                          \
         }                                                                                                              \
         if ((hm >> (J)) & 1U) {                                                                                        \
-            app_had<R, SV_J(J), NA>(a);                                                                                \
+            if ((rm >> (J)) & 1U) {                                                                                    \
+                app_rot<R, SV_J(J), NA>(a, rotTab[2U * ri], rotTab[2U * ri + 1U]);                                     \
+                ++ri;                                                                                                  \
+            } else {                                                                                                   \
+                app_had<R, SV_J(J), NA>(a);                                                                            \
+            }                                                                                                          \
         }                                                                                                              \
     }
             SV_STAGE_FAST(0)
@@ -397,7 +429,12 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
             }                                                                                                          \
         }                                                                                                              \
         if ((hm >> (J)) & 1U) {                                                                                        \
-            app_had<R, SV_J(J), NA>(a);                                                                                \
+            if ((rm >> (J)) & 1U) {                                                                                    \
+                app_rot<R, SV_J(J), NA>(a, rotTab[2U * ri], rotTab[2U * ri + 1U]);                                     \
+                ++ri;                                                                                                  \
+            } else {                                                                                                   \
+                app_had<R, SV_J(J), NA>(a);                                                                            \
+            }                                                                                                          \
         }                                                                                                              \
     }
         SV_STAGE_BIT(0)
@@ -571,6 +608,7 @@ __global__ void __launch_bounds__(NT, MINB)
     const int nMem = sw.nMem;
     const DevMember<R>* members = reinterpret_cast<const DevMember<R>*>(sprog + sw.memOff);
     uint2* const effTab = reinterpret_cast<uint2*>(tileTab + 2U * tabStride);
+    const R* const rotTab = reinterpret_cast<const R*>(sprog + sw.rotOff); // (c, s) of the stages' real rotations
     __syncthreads();
 
     uint32_t par = 0;
@@ -710,7 +748,7 @@ __global__ void __launch_bounds__(NT, MINB)
                     if ((hd.x & CODE_HAS_OUTER) && !((ballots[par][o >> 5] >> (o & 31)) & 1U)) {
                         continue;
                     }
-                    exec_op<R, NA, FULL>(a, ops[o], hd, xsb, tileScale, members, effCur);
+                    exec_op<R, NA, FULL>(a, ops[o], hd, xsb, tileScale, members, effCur, rotTab);
                 }
                 if (toGlobal) {
 #pragma unroll
@@ -821,15 +859,15 @@ static uint64_t lower_queue(const std::vector<GateOp>& q, std::vector<HostOp>& o
         xtail = rewrite_ops(out);
     }
     if (getenv("B200SV_FUSED_DEBUG")) {
-        int cnt[4] = { 0, 0, 0, 0 };
+        int cnt[5] = { 0, 0, 0, 0, 0 };
         for (const HostOp& h : out) {
             cnt[h.kind]++;
         }
-        fprintf(stderr, "lowered: %zu gates -> %zu ops (general %d, hadamard %d, xswap %d, phase %d)\n", q.size(), out.size(), cnt[0], cnt[1],
-            cnt[2], cnt[3]);
+        fprintf(stderr, "lowered: %zu gates -> %zu ops (general %d, hadamard %d, xswap %d, phase %d, rotation %d)\n", q.size(), out.size(), cnt[0],
+            cnt[1], cnt[2], cnt[3], cnt[4]);
         if (atoi(getenv("B200SV_FUSED_DEBUG")) >= 2) {
             for (const HostOp& h : out) {
-                fprintf(stderr, "   %s t=%d cmask=%llx cval=%llx m0=(%.3f,%.3f)\n", h.kind == OP_PHASE ? "PH" : (h.kind == OP_HAD ? "H " : (h.kind == OP_XSWAP ? "X " : "G ")),
+                fprintf(stderr, "   %s t=%d cmask=%llx cval=%llx m0=(%.3f,%.3f)\n", h.kind == OP_PHASE ? "PH" : (h.kind == OP_HAD ? "H " : (h.kind == OP_XSWAP ? "X " : (h.kind == OP_ROT ? "R " : "G "))),
                     h.tq, (unsigned long long)h.cmask, (unsigned long long)h.cval, h.m[0], h.m[1]);
             }
         }
@@ -878,6 +916,7 @@ static inline bool is_had_form(const double* m)
     return m[1] == 0.0 && m[3] == 0.0 && m[5] == 0.0 && m[7] == 0.0 && m[0] > 0.0 && m[0] == m[2] && m[0] == m[4] && m[6] == -m[0];
 }
 static int knob_rewrite();
+static int knob_rot();
 
 static uint64_t rewrite_ops(std::vector<HostOp>& ops)
 {
@@ -1078,12 +1117,67 @@ static uint64_t rewrite_ops(std::vector<HostOp>& ops)
             emit_bare_x(__builtin_ctzll(m));
         }
     }
+    // R5: an uncontrolled UNITARY general gate is  g . diag(1, p_post) . [[c, -s], [s, c]] . diag(1, p_pre)  with real c, s >= 0.
+    // The real rotation costs 4 packed instructions per amplitude pair instead of 8 for a general 2x2, runs inside a STAGE
+    // (no dispatch of its own), and the two phases are ordinary diagonal ops: they merge with the CZ / T phases around them
+    // and are applied lazily.  Quantum-volume layers (AI gates + CNOTs) become rotations + phases only: the flush is "light".
     std::vector<HostOp> res;
     res.reserve(out.size() + 1);
+    const bool rot = knob_rot() != 0;
     for (size_t i = 0; i < out.size(); ++i) {
-        if (alive[i]) {
-            res.push_back(out[i]);
+        if (!alive[i]) {
+            continue;
         }
+        const HostOp& h = out[i];
+        if (rot && h.kind == OP_GENERAL && !h.cmask) {
+            const double* m = h.m;
+            const double n00 = m[0] * m[0] + m[1] * m[1], n10 = m[4] * m[4] + m[5] * m[5];
+            const double n01 = m[2] * m[2] + m[3] * m[3], n11 = m[6] * m[6] + m[7] * m[7];
+            // unitary within rounding of the (possibly float-rounded) entries: unit columns, orthogonal
+            const double ox = m[0] * m[2] + m[1] * m[3] + m[4] * m[6] + m[5] * m[7], oy = m[0] * m[3] - m[1] * m[2] + m[4] * m[7] - m[5] * m[6];
+            if (fabs(n00 + n10 - 1.0) < 1e-5 && fabs(n01 + n11 - 1.0) < 1e-5 && fabs(ox) < 1e-5 && fabs(oy) < 1e-5 && n10 > 1e-24 && n01 > 1e-24) {
+                const double c = sqrt(n00), sn = sqrt(n10);
+                double g0x = 1.0, g0y = 0.0; // g = u00 / |u00| (1 when u00 = 0)
+                if (c > 1e-12) {
+                    g0x = m[0] / c;
+                    g0y = m[1] / c;
+                }
+                // p_post = (u10 / g) / s,  p_pre = -(u01 / g) / s'   (s' = |u01|, equal to s for a unitary)
+                const double s01 = sqrt(n01);
+                const double ax = (m[4] * g0x + m[5] * g0y) / sn, ay = (m[5] * g0x - m[4] * g0y) / sn;
+                const double bx = -(m[2] * g0x + m[3] * g0y) / s01, by = -(m[3] * g0x - m[2] * g0y) / s01;
+                // fold |u01| != |u10| (rounding) into the rotation's sine: use their mean
+                const double sm = 0.5 * (sn + s01);
+                const double nx = gx * g0x - gy * g0y;
+                gy = gx * g0y + gy * g0x;
+                gx = nx;
+                HostOp ph;
+                memset(&ph, 0, sizeof(ph));
+                ph.kind = OP_PHASE;
+                ph.tq = -1;
+                ph.cmask = bitq(h.tq);
+                ph.cval = bitq(h.tq);
+                if (bx != 1.0 || by != 0.0) {
+                    ph.m[0] = bx;
+                    ph.m[1] = by;
+                    res.push_back(ph);
+                }
+                HostOp r;
+                memset(&r, 0, sizeof(r));
+                r.kind = OP_ROT;
+                r.tq = h.tq;
+                r.m[0] = c;
+                r.m[1] = sm;
+                res.push_back(r);
+                if (ax != 1.0 || ay != 0.0) {
+                    ph.m[0] = ax;
+                    ph.m[1] = ay;
+                    res.push_back(ph);
+                }
+                continue;
+            }
+        }
+        res.push_back(h);
     }
     if (gx != 1.0 || gy != 0.0) {
         HostOp h;
@@ -1464,6 +1558,7 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
     std::vector<DevOuterPhase<R>> outerList;
     std::vector<std::vector<DevOuterPhase<R>>> slotMembers; // table slots 1.. (register-bit phases of the STAGE ops)
     std::vector<DevMember<R>> memberList;                   // thread-level members of the STAGE ops
+    std::vector<R> rotList;                                 // (c, s) of the STAGE ops' real rotations
     ds.nHigh = (int)sp.highQ.size();
     ds.lowAmpBits = cfg.L;
     ds.kc = kc;
@@ -1585,6 +1680,8 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
         // emitted (closed) before the first single op that does not commute with its contents, or at the end of the pass.
         struct Stage {
             bool h[MAX_JR];
+            bool isRot[MAX_JR];
+            double rc[MAX_JR], rs[MAX_JR];
             std::vector<DevOuterPhase<R>> slot[MAX_JR]; // outer-only members of bit J's phase (per-tile product -> one table slot)
             std::vector<DevMember<R>> thr[MAX_JR + 1];  // group 0 = thread-uniform, 1 + J = bit J
             bool any;
@@ -1592,6 +1689,7 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
         auto stage_reset = [&]() {
             for (int b = 0; b < MAX_JR; ++b) {
                 st.h[b] = false;
+                st.isRot[b] = false;
                 st.slot[b].clear();
             }
             for (int g = 0; g < MAX_JR + 1; ++g) {
@@ -1620,9 +1718,9 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
             }
             DevOp<R> d;
             memset(&d, 0, sizeof(d));
-            uint32_t hm = 0, sm = 0, cnts = 0;
+            uint32_t hm = 0, sm = 0, rm = 0, cnts = 0;
             d.lmaskSb = (uint32_t)slotMembers.size() + 1U; // first table slot of this stage
-            d.lvalSb = (uint32_t)memberList.size();        // first thread-level member
+            d.lvalSb = (uint32_t)memberList.size() | ((uint32_t)(rotList.size() / 2U) << 16); // first member | first rotation
             for (int g = 0; g < MAX_JR + 1; ++g) {
                 cnts |= (uint32_t)st.thr[g].size() << (ST_CNT_BITS * g);
                 memberList.insert(memberList.end(), st.thr[g].begin(), st.thr[g].end());
@@ -1630,6 +1728,11 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
             for (int b = 0; b < JRN; ++b) {
                 if (st.h[b]) {
                     hm |= 1U << b;
+                    if (st.isRot[b]) {
+                        rm |= 1U << b;
+                        rotList.push_back((R)st.rc[b]);
+                        rotList.push_back((R)st.rs[b]);
+                    }
                 }
                 if (!st.slot[b].empty()) {
                     sm |= 1U << b;
@@ -1643,7 +1746,7 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                 }
             }
             d.code = OPC_STAGE;
-            d.emask = hm | (sm << ST_SM_SHIFT) | (cnts ? (1U << ST_ANY_BIT) : 0U) | (act << ST_ACT_SHIFT);
+            d.emask = hm | (sm << ST_SM_SHIFT) | (cnts ? (1U << ST_ANY_BIT) : 0U) | (act << ST_ACT_SHIFT) | (rm << ST_RM_SHIFT);
             memcpy(d.m, &cnts, sizeof(cnts));
             dops.push_back(d);
             stage_reset();
@@ -1709,15 +1812,21 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                     }
                     // tables full: falls through to a single op
                 }
-            } else if ((cfg.bundle & 1) && !hop.cmask && hop.kind == OP_HAD) {
-                // uncontrolled Hadamard: butterfly of the stage (after the stage's phase on that bit)
+            } else if ((cfg.bundle & 1) && !hop.cmask && (hop.kind == OP_HAD || hop.kind == OP_ROT)) {
+                // uncontrolled Hadamard / real rotation: butterfly of the stage (after the stage's phase on that bit)
                 const int jr = reg_index(tile_bit(cfg, sp.highQ, hop.tq));
-                if (st.h[jr]) {
+                if (st.h[jr] || rotList.size() / 2U + 8U >= 65535U) {
                     close_stage();
                 }
                 st.h[jr] = true;
                 st.any = true;
-                scale *= hop.m[0];
+                if (hop.kind == OP_ROT) {
+                    st.isRot[jr] = true;
+                    st.rc[jr] = hop.m[0];
+                    st.rs[jr] = hop.m[1];
+                } else {
+                    scale *= hop.m[0];
+                }
                 if (!(cfg.bundle & 4)) {
                     close_stage();
                 }
@@ -1769,12 +1878,18 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
                 }
             } else {
                 const uint32_t jr = (uint32_t)reg_index(tile_bit(cfg, sp.highQ, hop.tq));
-                if (hop.kind == OP_HAD) {
+                if (hop.kind == OP_HAD || hop.kind == OP_ROT) {
                     // only with stage bundling switched off for butterflies: a stage of its own
                     close_stage();
                     st.h[jr] = true;
                     st.any = true;
-                    scale *= hop.m[0];
+                    if (hop.kind == OP_ROT) {
+                        st.isRot[jr] = true;
+                        st.rc[jr] = hop.m[0];
+                        st.rs[jr] = hop.m[1];
+                    } else {
+                        scale *= hop.m[0];
+                    }
                     close_stage();
                     continue;
                 } else if (hop.kind == OP_XSWAP) {
@@ -1874,8 +1989,11 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
     const size_t memBytes = memberList.size() * sizeof(DevMember<R>); // multiple of 16
     ds.outerOff = (int)(sizeof(DevSweep) + opsBytes);
     ds.memOff = (int)(sizeof(DevSweep) + opsBytes + outerBytes);
+    const size_t rotBytes = (rotList.size() * sizeof(R) + 15U) & ~(size_t)15U;
+    ds.rotOff = (int)(sizeof(DevSweep) + opsBytes + outerBytes + memBytes);
+    ds.nRot = (int)(rotList.size() / 2U);
     const size_t start = buf.size();
-    size_t bytes = ((sizeof(DevSweep) + opsBytes + outerBytes + memBytes) + 15U) & ~(size_t)15U;
+    size_t bytes = ((sizeof(DevSweep) + opsBytes + outerBytes + memBytes + rotBytes) + 15U) & ~(size_t)15U;
     if (scratchOut) {
         *scratchOut = (size_t)ds.scratchBytes;
     }
@@ -1893,6 +2011,9 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
     }
     if (!memberList.empty()) {
         memcpy(buf.data() + start + ds.memOff, memberList.data(), memBytes);
+    }
+    if (!rotList.empty()) {
+        memcpy(buf.data() + start + ds.rotOff, rotList.data(), rotList.size() * sizeof(R));
     }
     return bytes;
 }
@@ -2113,6 +2234,14 @@ static int knob_rewrite()
 constexpr int FUSED_KC = 12;
 constexpr int FUSED_NT = 256;
 
+static int knob_rot()
+{
+    static const int v = [] {
+        const char* e = getenv("B200SV_ROT");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
 static int knob_rb5()
 {
     static const int v = [] {
@@ -2255,7 +2384,7 @@ template <typename R> static inline EmuC<R> emu_mul(EmuC<R> a, R px, R py) { ret
 
 template <typename R>
 static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xsb, const R* tileScale, int NA,
-    const DevMember<R>* members, const uint2* eff)
+    const DevMember<R>* members, const uint2* eff, const R* rotTab)
 {
     const uint32_t code = op.code, emask = op.emask, lmaskSb = op.lmaskSb, lvalSb = op.lvalSb;
     bool tp = true;
@@ -2286,8 +2415,8 @@ static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xs
         }
     };
     if (c == OPC_STAGE) {
-        const uint32_t hm = emask & ST_MASK, sm = (emask >> ST_SM_SHIFT) & ST_MASK;
-        uint32_t slot = lmaskSb, mk = lvalSb, cnts = 0;
+        const uint32_t hm = emask & ST_MASK, sm = (emask >> ST_SM_SHIFT) & ST_MASK, rm = (emask >> ST_RM_SHIFT) & ST_MASK;
+        uint32_t slot = lmaskSb, mk = lvalSb & 0xffffU, ri = lvalSb >> 16, cnts = 0;
         if (emask & (1U << ST_ANY_BIT)) {
             memcpy(&cnts, op.m, sizeof(cnts));
         }
@@ -2323,7 +2452,19 @@ static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xs
                 phase_reg(J, px, py);
             }
             if ((hm >> J) & 1U) {
-                had(J);
+                if ((rm >> J) & 1U) {
+                    const R c = rotTab[2 * ri], sn = rotTab[2 * ri + 1];
+                    ++ri;
+                    for (int e = 0; e < NA; ++e) {
+                        if (!(e & (1 << J))) {
+                            const EmuC<R> x = a[e], y = a[e | (1 << J)];
+                            a[e] = EmuC<R>{ c * x.x - sn * y.x, c * x.y - sn * y.y };
+                            a[e | (1 << J)] = EmuC<R>{ sn * x.x + c * y.x, sn * x.y + c * y.y };
+                        }
+                    }
+                } else {
+                    had(J);
+                }
             }
         }
         return;
@@ -2412,6 +2553,7 @@ template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<
     std::vector<R> tab((size_t)2 * std::max(1, sw.nSlots));
     std::vector<EmuC<R>> a((size_t)NA);
     const DevMember<R>* members = reinterpret_cast<const DevMember<R>*>(prog + sw.memOff);
+    const R* rotTab = reinterpret_cast<const R*>(prog + sw.rotOff);
     std::vector<uint2> eff((size_t)std::max(1, sw.nMem));
     for (uint64_t t = 0; t < nTiles; ++t) {
         uint64_t base = t << sw.lowAmpBits;
@@ -2485,7 +2627,7 @@ template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<
                     const uint32_t xsb = sbc * (uint32_t)APC;
                     for (int o = ps.opBegin; o < ps.opEnd; ++o) {
                         if (act[o]) {
-                            emu_exec_op<R>(a, ops[o], xsb, tab.data(), NA, members, eff.data());
+                            emu_exec_op<R>(a, ops[o], xsb, tab.data(), NA, members, eff.data(), rotTab);
                         }
                     }
                     for (int e = 0; e < NCH; ++e) {
@@ -2567,7 +2709,17 @@ int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targ
             g.m[2] = 0.8;
             g.m[4] = 0.8;
             g.m[6] = -0.6;
-            g.m[1] = (kinds[i] == 3) ? 0.1 : 0.0; // kind 3: complex general
+            if (kinds[i] == 3) { // complex general, unitary: [[c, -e^{il} s], [e^{ip} s, e^{i(p+l)} c]], c = 0.8, s = 0.6, p = 0.3, l = 0.5
+                const double c = 0.8, sn = 0.6, ph = 0.3, la = 0.5;
+                g.m[0] = c;
+                g.m[1] = 0.0;
+                g.m[2] = -cos(la) * sn;
+                g.m[3] = -sin(la) * sn;
+                g.m[4] = cos(ph) * sn;
+                g.m[5] = sin(ph) * sn;
+                g.m[6] = cos(ph + la) * c;
+                g.m[7] = sin(ph + la) * c;
+            }
             if (kinds[i] == 4) { // exact Hadamard
                 g.m[0] = g.m[2] = g.m[4] = 0.70710678118654752440;
                 g.m[6] = -g.m[0];

@@ -24,6 +24,18 @@ for l in sys.stdin:
   tail -3 gpurun_out/bench_${name}_$N.err
 }
 echo "== bench htcnot (headline circuit, 30+$K qubits)"; bench htcnot --steps ${STEPS:-3} --warmup 3
+echo "== NVLink counter check: Tx bytes of GPU 0 over a run of 7 circuit replays (3 warm-up + 2 timed + 2 e2e, no mirror check)"
+nvl() { nvidia-smi nvlink -gt d -i 0 2>/dev/null | awk '/Data Tx/ {s += $5} END {printf "%.0f\n", s * 1024}'; }
+T0=$(nvl)
+timeout 900 $TR --master-port $((29500 + RANDOM % 400)) bench.py --gpus $N --steps 2 --warmup 3 --skip-check 2>/dev/null > gpurun_out/bench_nvl_$N.json
+T1=$(nvl)
+python - <<PY | tee gpurun_out/nvlink_check_$N.txt
+import json
+j = json.loads(open('gpurun_out/bench_nvl_$N.json').read().strip().splitlines()[-1])
+model = j['sharding']['nvlink_bytes_out_per_gpu_per_step'] * 7
+meas = $T1 - $T0
+print('NVLink Tx of GPU 0 over 7 replays: counter delta %.2f GB, model (exchanges x page x (N-1)/N) %.2f GB, ratio %.3f' % (meas / 1e9, model / 1e9, meas / max(model, 1)))
+PY
 echo "== bench qv (configs[3]: 30+$K qubits, depth = qubits)"; bench qv --steps ${STEPS:-2} --warmup 3 --workload qv
 echo "== bench grover (configs[4]: 31+$K qubits)"; bench grover --steps ${STEPS:-2} --warmup 3 --workload grover --qubits 31 --depth 3
 echo "== the unchanged reference QPager over the drop-in, one page per GPU (QRACK_QPAGER_DEVICES)"

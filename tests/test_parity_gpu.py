@@ -4,6 +4,7 @@
  (3) the compiled reference itself (oracle/_ref/ref_harness_*) when it travelled to the box,
  (4) size-independent properties at BASELINE.json's full sizes (28-30 qubits).
 Tolerances (north_star): max |delta amp| <= 1e-6 (fp32) / 1e-12 (fp64)."""
+import os
 import random
 
 import numpy as np
@@ -517,3 +518,30 @@ def test_memoised_marginals_follow_every_state_change(prec):
     o2.CopyStateVec(o)
     for q, w in enumerate(marginals(o2)[0]):
         assert abs(g2.Prob(q) - w) <= tol
+
+
+@pytest.mark.parametrize("env", [{"B200SV_RB5": "0"}, {"B200SV_ROT": "0"}, {"B200SV_LAZY_DIAG": "0"}, {"B200SV_REWRITE": "0"},
+                                 {"B200SV_FORCE_FULL": "1"}, {"B200SV_FUSED": "3,6,6,7,3"}],
+                         ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
+def test_scheduler_knobs_keep_parity_on_the_device(env):
+    """Every scheduler / kernel-variant switch (sub-block size, rotation stages, lazy diagonals, the rewrite itself, the full kernel
+    variant, the RB=3 tile shape) must reproduce the oracle on the DEVICE kernels too (the library reads its knobs once per process,
+    hence the subprocess).  17-18 qubits: several tiles, high tile qubits, outer controls, thread-level members, several passes."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, random; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from oracle.restate_engine import QEngineRestate\n"
+        "from qrack_b200 import QEngineCUDA, qscript\n"
+        "import util\n"
+        "for prec, n in ((32, 18), (64, 17)):\n"
+        "    text = (qscript.random_htcnot(n, 10, seed=3, timed=False) + qscript.quantum_volume(n, depth=4, seed=9, timed=False).split('\\n', 1)[1]\n"
+        "            + 'QFT 2 9\\nCCNOT 1 14 7\\nAntiCNOT 3 16\\nMCPhase 2 3 13 8 0.6 0.8 1 0\\nINC 5 1 9\\nXMask 3075\\nX 4\\nCZ 4 15\\n')\n"
+        "    want, _ = util.run_engine(text, QEngineRestate, prec)\n"
+        "    got, _ = util.run_engine(text, QEngineCUDA, prec)\n"
+        "    util.assert_states_close(got, want, prec, 'knobs')\n"
+        "print('ok')\n"
+    ) % (util.ROOT, os.path.join(util.ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])

@@ -179,6 +179,11 @@ template <> struct AmpOps<float> {
         x = f2add(x, y);
         y = f2fma(y, pk(-2.0f, -2.0f), x);
     }
+    static __device__ __forceinline__ void hadneg(A& x, A& y) // butterfly after a -1 phase on y: (x - y, x + y)
+    {
+        x = f2fma(y, pk(-1.0f, -1.0f), x);
+        y = f2fma(y, pk(2.0f, 2.0f), x);
+    }
     static __device__ __forceinline__ void rot(A& x, A& y, float c, float s)
     {
         const ull cc = pk(c, c), ss = pk(s, s), ns = pk(-s, -s);
@@ -227,6 +232,13 @@ template <> struct AmpOps<double> {
         y.x = fma(y.x, -2.0, x.x);
         y.y = fma(y.y, -2.0, x.y);
     }
+    static __device__ __forceinline__ void hadneg(A& x, A& y)
+    {
+        x.x -= y.x;
+        x.y -= y.y;
+        y.x = fma(y.x, 2.0, x.x);
+        y.y = fma(y.y, 2.0, x.y);
+    }
     static __device__ __forceinline__ void rot(A& x, A& y, double c, double s)
     {
         const A nx = make_double2(fma(c, x.x, -s * y.x), fma(c, x.y, -s * y.y));
@@ -262,6 +274,15 @@ template <typename R, int JR, int NA> __device__ __forceinline__ void app_rot(ty
     for (int e = 0; e < NA; ++e) {
         if (!(e & (1 << JR))) {
             O::rot(a[e], a[e | (1 << JR)], c, s);
+        }
+    }
+}
+template <typename R, int JR, int NA> __device__ __forceinline__ void app_hadneg(typename AmpOps<R>::A (&a)[NA])
+{
+#pragma unroll
+    for (int e = 0; e < NA; ++e) {
+        if (!(e & (1 << JR))) {
+            AmpOps<R>::hadneg(a[e], a[e | (1 << JR)]);
         }
     }
 }
@@ -362,10 +383,13 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
             // the common shape: per-tile slot phases and butterflies only (no thread-level members)
 #define SV_STAGE_FAST(J)                                                                                               \
     if (((1 << (J)) < NA) && ((act >> (J)) & 1U)) {                                                                    \
+        bool neg = false;                                                                                              \
         if ((sm >> (J)) & 1U) {                                                                                        \
             const R px = tileScale[2U * slot], py = tileScale[2U * slot + 1U];                                         \
             ++slot;                                                                                                    \
-            if (px != (R)1 || py != (R)0) {                                                                            \
+            /* a phase of exactly -1 right before a Hadamard on the same bit costs nothing: negative butterfly */      \
+            neg = (py == (R)0) && (px == (R)-1) && ((hm & ~rm) >> (J) & 1U);                                           \
+            if (!neg && (px != (R)1 || py != (R)0)) {                                                                  \
                 app_phase_reg<R, SV_J(J), NA>(a, O::mkph(px, py));                                                     \
             }                                                                                                          \
         }                                                                                                              \
@@ -373,6 +397,8 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
             if ((rm >> (J)) & 1U) {                                                                                    \
                 app_rot<R, SV_J(J), NA>(a, rotTab[2U * ri], rotTab[2U * ri + 1U]);                                     \
                 ++ri;                                                                                                  \
+            } else if (neg) {                                                                                          \
+                app_hadneg<R, SV_J(J), NA>(a);                                                                         \
             } else {                                                                                                   \
                 app_had<R, SV_J(J), NA>(a);                                                                            \
             }                                                                                                          \
@@ -416,6 +442,7 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
 #define SV_STAGE_BIT(J)                                                                                                \
     if (((1 << (J)) < NA) && ((act >> (J)) & 1U)) {                                                                    \
         const uint32_t c = (cnts >> (ST_CNT_BITS * ((J) + 1))) & ST_CNT_MASK;                                          \
+        bool neg = false;                                                                                              \
         if (((sm >> (J)) & 1U) | c) {                                                                                  \
             R px = (R)1, py = (R)0;                                                                                    \
             if ((sm >> (J)) & 1U) {                                                                                    \
@@ -424,7 +451,8 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
                 ++slot;                                                                                                \
             }                                                                                                          \
             SV_MEMBERS(c)                                                                                              \
-            if (px != (R)1 || py != (R)0) {                                                                            \
+            neg = (py == (R)0) && (px == (R)-1) && ((hm & ~rm) >> (J) & 1U);                                           \
+            if (!neg && (px != (R)1 || py != (R)0)) {                                                                  \
                 app_phase_reg<R, SV_J(J), NA>(a, O::mkph(px, py));                                                     \
             }                                                                                                          \
         }                                                                                                              \
@@ -432,6 +460,8 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
             if ((rm >> (J)) & 1U) {                                                                                    \
                 app_rot<R, SV_J(J), NA>(a, rotTab[2U * ri], rotTab[2U * ri + 1U]);                                     \
                 ++ri;                                                                                                  \
+            } else if (neg) {                                                                                          \
+                app_hadneg<R, SV_J(J), NA>(a);                                                                         \
             } else {                                                                                                   \
                 app_had<R, SV_J(J), NA>(a);                                                                            \
             }                                                                                                          \

@@ -198,3 +198,27 @@ def test_prob_bits_all_order_and_multishot_histogram_path():
     assert np.abs(emp - want).max() < 0.04          # ~5 sigma of a 4000-shot binomial
     with pytest.raises(ValueError):
         q.MultiShotMeasureMask([3], 10)
+
+
+def test_qcircuit_records_the_dispatch_and_replays_it():
+    """QCircuit records every gate method through the same dispatch mirror the engines use and replays it on any
+    engine: gate by gate here (what QCircuit::Run does in the reference), in one ABI call on QEngineCUDA."""
+    import numpy as np
+    from oracle.restate_engine import QEngineRestate
+    from qrack_b200 import QCircuit
+    n = 9
+    text = qscript.random_htcnot(n, 5, seed=3, timed=False) + "QFT 1 7\nCCNOT 0 8 4\nAntiCNOT 2 6\nINC 5 2 6\nU 3 0.3 0.2 0.1\nXMask 24\nCZ 1 7\n"
+    c = QCircuit(n, 32)
+    for _, t in qscript.parse(text):
+        if t[0] == "qubits":
+            continue
+        getattr(c, t[0])(*[(float(x) if "." in x else int(x)) for x in t[1:]])
+    assert c.GetGateCount() > 100
+    q = QEngineRestate(n, 0, random.Random(1), 1.0 + 0j, False, False, precision=32)
+    c.Run(q)
+    ref, _ = qscript.run(text, lambda nq, p: QEngineRestate(nq, p, random.Random(1), 1.0 + 0j, False, False, precision=32))
+    assert np.abs(q.GetQuantumState() - ref[0].GetQuantumState()).max() < 1e-6
+    with pytest.raises(NotImplementedError):
+        c.Prob(0)                      # state access is an engine call, not a circuit element
+    with pytest.raises(ValueError):
+        c.Run(QEngineRestate(n + 1, 0, random.Random(1), 1.0 + 0j, False, False, precision=32))

@@ -238,6 +238,30 @@ def test_multishot_sampling_and_prob_bits_all_on_device():
     assert abs(q.ProbAll(0) - pr[0]) < 1e-6                      # no collapse happened
 
 
+@pytest.mark.parametrize("prec", [32, 64])
+def test_whole_circuit_submission_matches_per_gate_calls(prec):
+    """QCircuit.Run -> b200sv_apply_gates (one ABI call) must leave the same state as the per-gate Apply2x2 path,
+    and both must match the oracle (20 qubits: fused sweeps with several tiles)."""
+    from qrack_b200 import QCircuit
+    n = 20
+    text = qscript.random_htcnot(n, 8, seed=21, timed=False) + qscript.quantum_volume(n, depth=3, seed=4, timed=False).split("\n", 1)[1] + \
+        "QFT 3 12\nCCNOT 0 19 7\nINC 9 4 10\n"
+    c = QCircuit(n, prec)
+    for _, t in qscript.parse(text):
+        if t[0] != "qubits":
+            getattr(c, t[0])(*[(float(x) if ("." in x or "e" in x) else int(x)) for x in t[1:]])
+    qa = QEngineCUDA(n, 0, random.Random(1), 1.0 + 0j, False, False, precision=prec)
+    c.Run(qa)
+    got_batched = qa.GetQuantumState()
+    got_pergate, _ = util.run_engine(text, QEngineCUDA, prec)
+    want, _ = util.run_engine(text, QEngineRestate, prec)
+    util.assert_states_close({0: got_batched}, want, prec, "batched")
+    util.assert_states_close(got_pergate, want, prec, "per gate")
+    qd = QEngineCUDA(n, 0, random.Random(1), 1.0 + 0j, True, False, precision=prec)   # doNormalize engines refuse the batch
+    with pytest.raises(ValueError):
+        c.Run(qd)
+
+
 def test_normalize_and_calc_norm_path():
     """doNormalize engines: Apply2x2 with doCalcNorm and NormalizeState against the oracle."""
     rng = np.random.default_rng(2)

@@ -51,6 +51,15 @@ class _RecordBackend:
         self.gates.append((off1, off2, pmask, tuple(complex(z) for z in mtrx)))
         return None
 
+    def xmask(self, mask):
+        # XMask = X on every masked qubit (QInterface::XMask, src/qinterface/gates.cpp); the engine's scheduler turns the
+        # XMask ... XMask wrappers of anti-controlled gates into control polarities
+        b = 0
+        while mask >> b:
+            if (mask >> b) & 1:
+                self.gates.append((0, 1 << b, 1 << b, (0j, 1 + 0j, 1 + 0j, 0j)))
+            b += 1
+
     def __getattr__(self, name):
         raise NotImplementedError("QCircuit: %r is not a gate that lowers to Apply2x2 (state access, measurement and the "
                                   "native sweeps are engine calls, not circuit elements)" % name)

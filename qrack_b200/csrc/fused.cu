@@ -639,6 +639,17 @@ __global__ void __launch_bounds__(NT, MINB)
     const DevMember<R>* members = reinterpret_cast<const DevMember<R>*>(sprog + sw.memOff);
     uint2* const effTab = reinterpret_cast<uint2*>(tileTab + 2U * tabStride);
     const R* const rotTab = reinterpret_cast<const R*>(sprog + sw.rotOff); // (c, s) of the stages' real rotations
+    // tile-chunk index of this thread's sub-block base in every pass (depends on the pass's bit assignment only, not on the tile)
+    unsigned short* const depTab = reinterpret_cast<unsigned short*>(effTab + 2U * (uint32_t)nMem);
+    for (int p = 0; p < nPass; ++p) {
+        const DevPass& ps = sw.pass[p];
+        const int nb = ps.nsb < 8 ? ps.nsb : 8;
+        uint32_t dep = 0;
+        for (int i = 0; i < nb; ++i) {
+            dep |= ((tid >> i) & 1U) << ps.sbit[i];
+        }
+        depTab[p * NT + tid] = (unsigned short)dep;
+    }
     __syncthreads();
 
     uint32_t par = 0;
@@ -733,13 +744,7 @@ __global__ void __launch_bounds__(NT, MINB)
         for (int p = 0; p < nPass; ++p) {
             const DevPass& ps = sw.pass[p];
             const bool fromGlobal = (p == 0) && sw.directIn, toGlobal = (p == nPass - 1) && sw.directOut;
-            uint32_t dep = 0;
-            {
-                const int nb = ps.nsb < 8 ? ps.nsb : 8;
-                for (int i = 0; i < nb; ++i) {
-                    dep |= ((tid >> i) & 1U) << ps.sbit[i];
-                }
-            }
+            const uint32_t dep = depTab[p * NT + tid];
             const int opBegin = ps.opBegin, opEnd = ps.opEnd;
             const uint2* const effCur = effTab + par * (uint32_t)nMem;
             for (int it = 0; it < ps.nIt; ++it) {
@@ -2005,7 +2010,8 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
         const int lcb = cfg.L - cfg.apcLog;
         const size_t rows = (size_t)1 << (kc > lcb ? kc - lcb : 0);
         ds.scratchBytes =
-            (int)((rows * 8U + (size_t)4 * (size_t)ds.nSlots * sizeof(R) + (size_t)16 * memberList.size() + 15U) & ~(size_t)15U);
+            (int)((rows * 8U + (size_t)4 * (size_t)ds.nSlots * sizeof(R) + (size_t)16 * memberList.size() +
+                      (size_t)2 * (size_t)ds.nPass * (size_t)NT + 15U) & ~(size_t)15U); // + per-(pass, thread) sub-block bases
     }
     ds.nMem = (int)memberList.size();
     ds.slotBeg[0] = 0;

@@ -7,7 +7,8 @@ import subprocess
 from ctypes import POINTER, c_char_p, c_double, c_int, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sv.so")
+# B200SV_LIB selects another build of the same library (tuning variants: scripts/build_variants.sh); default = the in-tree product
+LIB_PATH = os.environ.get("B200SV_LIB") or os.path.join(_HERE, "libb200sv.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["b200sv.cu", "fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

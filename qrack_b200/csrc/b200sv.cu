@@ -275,7 +275,37 @@ __global__ void __launch_bounds__(256) k_apply_m(typename Cx<R>::type* psi, uint
     typename Cx<R>::type nrm)
 {
     typedef typename Cx<R>::type C;
-    map_amps<R>(psi, n, [&](uint64_t i, C a) { return ((i & mask) == result) ? cmul<C>(nrm, a) : mk<R>(0, 0); });
+    // the dropped part is only WRITTEN (zeros): 1.5 instead of 2 state sizes of traffic.  128-bit accesses: fp32 handles the
+    // amplitude pair (2j, 2j+1) per chunk and loads it only if at least one of the two is kept.
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sizeof(R) == 4 && n >= 2) {
+        float4* p = reinterpret_cast<float4*>(psi);
+        for (uint64_t j = gid; j < (n >> 1); j += stride) {
+            const bool k0 = ((2U * j) & mask) == result, k1 = ((2U * j + 1U) & mask) == result;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 | k1) {
+                const float4 w = p[j];
+                if (k0) {
+                    v.x = (float)nrm.x * w.x - (float)nrm.y * w.y;
+                    v.y = (float)nrm.x * w.y + (float)nrm.y * w.x;
+                }
+                if (k1) {
+                    v.z = (float)nrm.x * w.z - (float)nrm.y * w.w;
+                    v.w = (float)nrm.x * w.w + (float)nrm.y * w.z;
+                }
+            }
+            p[j] = v;
+        }
+        return;
+    }
+    for (uint64_t i = gid; i < n; i += stride) {
+        if ((i & mask) == result) {
+            psi[i] = cmul<C>(nrm, psi[i]);
+        } else {
+            psi[i] = mk<R>(0, 0);
+        }
+    }
 }
 
 template <typename R>

@@ -351,12 +351,19 @@ template <typename R> struct alignas(16) DevMember {
     R ph[2];
 };
 
-template <typename R, int NA, bool FULL>
+#ifdef SV_NO_NEG
+#define SV_NEG_OK false
+#else
+#define SV_NEG_OK true
+#endif
+template <typename R, int NA, int VAR>
 __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const DevOp<R>& op, const uint4 hd, uint32_t xsb,
     const R* __restrict__ tileScale, const DevMember<R>* __restrict__ members, const uint2* __restrict__ eff, const R* __restrict__ rotTab)
 {
     typedef AmpOps<R> O;
     typedef typename O::A A;
+    constexpr bool FULL = (VAR == 2);  // swap / general-matrix ops compiled in
+    constexpr bool ROT = (VAR >= 1);   // stages may hold real rotations
     const R* m = op.m;
 #define SV_J(J) (((1 << (J)) < NA) ? (J) : 0)
 #define SV_CASES(J)                                                                                                    \
@@ -377,8 +384,9 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
         break;
     if ((hd.x & 0xffU) == OPC_STAGE) {
         const uint32_t hm = hd.y & ST_MASK, sm = (hd.y >> ST_SM_SHIFT) & ST_MASK, act = (hd.y >> ST_ACT_SHIFT) & ST_MASK,
-                       rm = (hd.y >> ST_RM_SHIFT) & ST_MASK;
+                       rm = ROT ? ((hd.y >> ST_RM_SHIFT) & ST_MASK) : 0U;
         uint32_t slot = hd.z, mk = hd.w & 0xffffU, ri = hd.w >> 16;
+#ifndef SV_NO_FASTPATH
         if (!FULL && !(hd.y & (1U << ST_ANY_BIT))) {
             // the common shape: per-tile slot phases and butterflies only (no thread-level members)
 #define SV_STAGE_FAST(J)                                                                                               \
@@ -388,13 +396,13 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
             const R px = tileScale[2U * slot], py = tileScale[2U * slot + 1U];                                         \
             ++slot;                                                                                                    \
             /* a phase of exactly -1 right before a Hadamard on the same bit costs nothing: negative butterfly */      \
-            neg = (py == (R)0) && (px == (R)-1) && ((hm & ~rm) >> (J) & 1U);                                           \
+            neg = SV_NEG_OK && (py == (R)0) && (px == (R)-1) && ((hm & ~rm) >> (J) & 1U);                              \
             if (!neg && (px != (R)1 || py != (R)0)) {                                                                  \
                 app_phase_reg<R, SV_J(J), NA>(a, O::mkph(px, py));                                                     \
             }                                                                                                          \
         }                                                                                                              \
         if ((hm >> (J)) & 1U) {                                                                                        \
-            if ((rm >> (J)) & 1U) {                                                                                    \
+            if (ROT && ((rm >> (J)) & 1U)) {                                                                           \
                 app_rot<R, SV_J(J), NA>(a, rotTab[2U * ri], rotTab[2U * ri + 1U]);                                     \
                 ++ri;                                                                                                  \
             } else if (neg) {                                                                                          \
@@ -413,6 +421,7 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
 #undef SV_STAGE_FAST
             return;
         }
+#endif
         const uint32_t cnts = (hd.y & (1U << ST_ANY_BIT)) ? *reinterpret_cast<const uint32_t*>(op.m) : 0U;
         // product of the thread-level members [mk, mk + c) that fire for this thread, times (px, py)
 #define SV_MEMBERS(c)                                                                                                  \
@@ -451,13 +460,13 @@ __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const De
                 ++slot;                                                                                                \
             }                                                                                                          \
             SV_MEMBERS(c)                                                                                              \
-            neg = (py == (R)0) && (px == (R)-1) && ((hm & ~rm) >> (J) & 1U);                                           \
+            neg = SV_NEG_OK && (py == (R)0) && (px == (R)-1) && ((hm & ~rm) >> (J) & 1U);                              \
             if (!neg && (px != (R)1 || py != (R)0)) {                                                                  \
                 app_phase_reg<R, SV_J(J), NA>(a, O::mkph(px, py));                                                     \
             }                                                                                                          \
         }                                                                                                              \
         if ((hm >> (J)) & 1U) {                                                                                        \
-            if ((rm >> (J)) & 1U) {                                                                                    \
+            if (ROT && ((rm >> (J)) & 1U)) {                                                                           \
                 app_rot<R, SV_J(J), NA>(a, rotTab[2U * ri], rotTab[2U * ri + 1U]);                                     \
                 ++ri;                                                                                                  \
             } else if (neg) {                                                                                          \
@@ -584,7 +593,7 @@ __device__ __noinline__ void stage_out(typename Cx<R>::type* __restrict__ tilePs
     }
 }
 
-template <typename R, int KC, int RB, int NT, int MINB, bool FULL>
+template <typename R, int KC, int RB, int NT, int MINB, int VAR>
 __global__ void __launch_bounds__(NT, MINB)
     k_fused_sweep(typename Cx<R>::type* __restrict__ psi, const unsigned char* __restrict__ prog, uint32_t progBytes, uint64_t nTiles)
 {
@@ -776,14 +785,18 @@ __global__ void __launch_bounds__(NT, MINB)
                 uint4 hdNext = *reinterpret_cast<const uint4*>(&ops[opBegin].code);
 #pragma unroll 1
                 for (int o = opBegin; o < opEnd; ++o) {
-                    const uint4 hd = FULL ? *reinterpret_cast<const uint4*>(&ops[o].code) : hdNext;
-                    if (!FULL) {
+#ifdef SV_NO_PREFETCH
+                    const uint4 hd = *reinterpret_cast<const uint4*>(&ops[o].code);
+#else
+                    const uint4 hd = (VAR == 2) ? *reinterpret_cast<const uint4*>(&ops[o].code) : hdNext;
+                    if (VAR != 2) {
                         hdNext = *reinterpret_cast<const uint4*>(&ops[o + 1].code);
                     }
+#endif
                     if ((hd.x & CODE_HAS_OUTER) && !((ballots[par][o >> 5] >> (o & 31)) & 1U)) {
                         continue;
                     }
-                    exec_op<R, NA, FULL>(a, ops[o], hd, xsb, tileScale, members, effCur, rotTab);
+                    exec_op<R, NA, VAR>(a, ops[o], hd, xsb, tileScale, members, effCur, rotTab);
                 }
                 if (toGlobal) {
 #pragma unroll
@@ -2159,10 +2172,10 @@ struct KernelCfg {
     int KC, RB, NT, MINB;
 };
 
-template <typename R, int KC, int RB, int NT, int MINB, bool FULL>
+template <typename R, int KC, int RB, int NT, int MINB, int VAR>
 static int launch_sweep_v(State* s, const unsigned char* dprog, uint32_t progBytes, uint32_t scratchBytes, uint64_t nTiles)
 {
-    auto kern = k_fused_sweep<R, KC, RB, NT, MINB, FULL>;
+    auto kern = k_fused_sweep<R, KC, RB, NT, MINB, VAR>;
     const size_t shm = ((size_t)16 << KC) + progBytes + scratchBytes;
     static std::atomic<unsigned long long> attr_set_mask{ 0 }; // per device: the attribute is per-context
     if (!(attr_set_mask.load() & (1ULL << s->dev))) {
@@ -2227,10 +2240,12 @@ static const FusedKnobs& knobs()
     return k;
 }
 template <typename R, int KC, int RB, int NT, int MINB>
-static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes, uint32_t scratchBytes, uint64_t nTiles, bool full)
+static int launch_sweep(State* s, const unsigned char* dprog, uint32_t progBytes, uint32_t scratchBytes, uint64_t nTiles, int var)
 {
-    return full ? launch_sweep_v<R, KC, RB, NT, MINB, true>(s, dprog, progBytes, scratchBytes, nTiles)
-                : launch_sweep_v<R, KC, RB, NT, MINB, false>(s, dprog, progBytes, scratchBytes, nTiles);
+    // var: 0 = light (STAGE / phase ops, Hadamard butterflies only), 1 = light + rotation stages, 2 = full (+ swap / general-matrix ops)
+    return var == 2 ? launch_sweep_v<R, KC, RB, NT, MINB, 2>(s, dprog, progBytes, scratchBytes, nTiles)
+                    : (var == 1 ? launch_sweep_v<R, KC, RB, NT, MINB, 1>(s, dprog, progBytes, scratchBytes, nTiles)
+                                : launch_sweep_v<R, KC, RB, NT, MINB, 0>(s, dprog, progBytes, scratchBytes, nTiles));
 }
 static int knob_prefetch() { return knobs().pf; }
 static int knob_plan_search()
@@ -2282,7 +2297,7 @@ static int knob_rb5()
 {
     static const int v = [] {
         const char* e = getenv("B200SV_RB5");
-        return e ? atoi(e) : 1;
+        return e ? atoi(e) : 0; // measured r2 (profiles/r2_tuning.md): 20 % fewer instructions, but 8 warps / SM do not hide the latency
     }();
     return v;
 }
@@ -2364,31 +2379,33 @@ int fused_flush(State* s)
     for (size_t i = 0; i < segs.size(); ++i) {
         const unsigned char* dp = ar->dev + segs[i].off;
         const uint32_t pb = (uint32_t)segs[i].bytes, sb = (uint32_t)segs[i].scratch;
-        const bool full = knob_force_full() || reinterpret_cast<const DevSweep*>(buf.data() + segs[i].off)->needFull != 0;
+        const DevSweep* dsw = reinterpret_cast<const DevSweep*>(buf.data() + segs[i].off);
+        const bool full = knob_force_full() || dsw->needFull != 0;
+        const int var = full ? 2 : (dsw->nRot ? 1 : 0);
         if (cfg.RB == 5) {
             if (full) {
                 set_error("fused sweep: a full op in a light flush");
                 return B200SV_ESTATE;
             }
             if (s->prec == 32) {
-                SV_TRY((launch_sweep_v<float, FUSED_KC, 5, 128, 2, false>(s, dp, pb, sb, nTiles)));
+                SV_TRY((launch_sweep_v<float, FUSED_KC, 5, 128, 2, 1>(s, dp, pb, sb, nTiles)));
             } else {
-                SV_TRY((launch_sweep_v<double, FUSED_KC, 5, 128, 2, false>(s, dp, pb, sb, nTiles)));
+                SV_TRY((launch_sweep_v<double, FUSED_KC, 5, 128, 2, 1>(s, dp, pb, sb, nTiles)));
             }
         } else if (s->prec == 32) {
             if (cfg.RB == 4) {
-                SV_TRY((launch_sweep<float, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles, full)));
+                SV_TRY((launch_sweep<float, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles, var)));
             } else {
-                SV_TRY((launch_sweep<float, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles, full)));
+                SV_TRY((launch_sweep<float, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles, var)));
             }
         } else {
             if (cfg.RB == 4) {
-                SV_TRY((launch_sweep<double, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles, full)));
+                SV_TRY((launch_sweep<double, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles, var)));
             } else {
                 if (knobs().minb64 == 2) {
-                    SV_TRY((launch_sweep<double, FUSED_KC, 3, FUSED_NT, 2>(s, dp, pb, sb, nTiles, full)));
+                    SV_TRY((launch_sweep<double, FUSED_KC, 3, FUSED_NT, 2>(s, dp, pb, sb, nTiles, var)));
                 } else {
-                    SV_TRY((launch_sweep<double, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles, full)));
+                    SV_TRY((launch_sweep<double, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles, var)));
                 }
             }
         }

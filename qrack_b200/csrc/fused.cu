@@ -351,10 +351,12 @@ template <typename R> struct alignas(16) DevMember {
     R ph[2];
 };
 
-#ifdef SV_NO_NEG
-#define SV_NEG_OK false
-#else
+// SV_NEG: fold a phase of exactly -1 that precedes a Hadamard on the same bit into a negative butterfly.  Measured r2 (same box,
+// profiles/r2e_bench_variants.jsonl): the test costs more than the skipped phase applications save (270.0 vs 262.9 ms/step): off.
+#ifdef SV_NEG
 #define SV_NEG_OK true
+#else
+#define SV_NEG_OK false
 #endif
 template <typename R, int NA, int VAR>
 __device__ __forceinline__ void exec_op(typename AmpOps<R>::A (&a)[NA], const DevOp<R>& op, const uint4 hd, uint32_t xsb,

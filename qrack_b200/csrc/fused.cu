@@ -31,9 +31,9 @@ constexpr int MAX_PASS = 8;
 constexpr int MAX_OPS = 96;
 constexpr int MAX_HOST_OPS = 384; // gates per sweep before merging (LAYER / DIAG groups shrink them to <= MAX_OPS device ops)
 constexpr int MAX_SLOTS = 128; // per-tile phase table (1 + register-bit phases of the DIAG ops); filled by warps 4..7
-constexpr int MAX_NCH = 32; // register chunks per sub-block (RB <= 5)
-constexpr int MAX_NA = 64;  // register amplitudes per sub-block
-constexpr int MAX_JR = 6;   // register-bit indices (fp32 RB = 5: qubit 0 + 5 chunk bits)
+constexpr int MAX_NCH = 16; // register chunks per sub-block (RB <= 4; RB = 5 was measured and dropped, profiles/r2_tuning.md)
+constexpr int MAX_NA = 32;  // register amplitudes per sub-block
+constexpr int MAX_JR = 6;   // register-bit indices the STAGE header has room for (5 are used)
 
 // device op codes.  Single-gate ops: kind * 5 + jr (jr = register-bit index of the target; dense so that the dispatch is a
 // shallow branch tree).  OPC_STAGE = per-bit phases + Hadamard butterflies; OPC_SCALE = per-tile scalar.
@@ -781,20 +781,10 @@ __global__ void __launch_bounds__(NT, MINB)
                 }
                 const uint32_t xsb = sbc * APC;
                 // linear walk over the pass's ops; only ops with a predicate on outer qubits look at the per-tile ballot
-                // (the next op's header is fetched while the current body runs: the read past the last op lands in the
-                // program / scratch area behind the op array and is never used)
-                // (only in the light variant: the full one has no registers to spare for it)
-                uint4 hdNext = *reinterpret_cast<const uint4*>(&ops[opBegin].code);
 #pragma unroll 1
                 for (int o = opBegin; o < opEnd; ++o) {
-#ifdef SV_NO_PREFETCH
+                    // (fetching the next op's header one op ahead was measured: no effect, 4 more live registers)
                     const uint4 hd = *reinterpret_cast<const uint4*>(&ops[o].code);
-#else
-                    const uint4 hd = (VAR == 2) ? *reinterpret_cast<const uint4*>(&ops[o].code) : hdNext;
-                    if (VAR != 2) {
-                        hdNext = *reinterpret_cast<const uint4*>(&ops[o + 1].code);
-                    }
-#endif
                     if ((hd.x & CODE_HAS_OUTER) && !((ballots[par][o >> 5] >> (o & 31)) & 1U)) {
                         continue;
                     }
@@ -2287,6 +2277,14 @@ static int knob_rewrite()
 constexpr int FUSED_KC = 12;
 constexpr int FUSED_NT = 256;
 
+static int knob_minb3()
+{
+    static const int v = [] {
+        const char* e = getenv("B200SV_MINB3");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
 static int knob_rot()
 {
     static const int v = [] {
@@ -2295,26 +2293,11 @@ static int knob_rot()
     }();
     return v;
 }
-static int knob_rb5()
-{
-    static const int v = [] {
-        const char* e = getenv("B200SV_RB5");
-        return e ? atoi(e) : 0; // measured r2 (profiles/r2_tuning.md): 20 % fewer instructions, but 8 warps / SM do not hide the latency
-    }();
-    return v;
-}
-// light = the flush holds no swap / general-matrix op: its sweeps run on the light kernel variant, which has the registers for
-// 2^5-chunk sub-blocks (fp32: 64 amplitudes, 6 register qubits per pass) on 128-thread CTAs — half the decode work per
-// amplitude and fewer passes per sweep.  Needs full-size tiles.
 static TileCfg state_cfg(int nq, int prec, bool light = false)
 {
     const FusedKnobs& k = knobs();
-    int rb = prec == 32 ? k.RB : k.RB64, nt = FUSED_NT;
-    if (light && knob_rb5() && rb == 4 && nq >= FUSED_KC + 2) {
-        rb = 5;
-        nt = 128;
-    }
-    TileCfg c = make_cfg(nq, prec, FUSED_KC, rb, prec == 32 ? k.L32 : k.L64, nt);
+    (void)light;
+    TileCfg c = make_cfg(nq, prec, FUSED_KC, prec == 32 ? k.RB : k.RB64, prec == 32 ? k.L32 : k.L64, FUSED_NT);
     c.bundle = k.bundle;
     return c;
 }
@@ -2361,6 +2344,9 @@ int fused_flush(State* s)
         int npass = 0;
         SV_TRY(plan_and_encode(pending, cfg, s->prec, buf, &bytes, &scratch, &nops, &npass));
         segs.push_back({ off, bytes, scratch });
+        if (getenv("B200SV_FUSED_DEBUG")) {
+            fprintf(stderr, "  program %zu B + scratch %zu B\n", bytes, scratch);
+        }
     }
     const uint64_t nTiles = s->dim() >> cfg.kA;
     if (ar->pending) {
@@ -2384,18 +2370,12 @@ int fused_flush(State* s)
         const DevSweep* dsw = reinterpret_cast<const DevSweep*>(buf.data() + segs[i].off);
         const bool full = knob_force_full() || dsw->needFull != 0;
         const int var = full ? 2 : (dsw->nRot ? 1 : 0);
-        if (cfg.RB == 5) {
-            if (full) {
-                set_error("fused sweep: a full op in a light flush");
-                return B200SV_ESTATE;
-            }
-            if (s->prec == 32) {
-                SV_TRY((launch_sweep_v<float, FUSED_KC, 5, 128, 2, 1>(s, dp, pb, sb, nTiles)));
-            } else {
-                SV_TRY((launch_sweep_v<double, FUSED_KC, 5, 128, 2, 1>(s, dp, pb, sb, nTiles)));
-            }
-        } else if (s->prec == 32) {
-            if (cfg.RB == 4) {
+        if (s->prec == 32) {
+            if (cfg.RB == 4 && var != 2 && knob_minb3() && (size_t)pb + (size_t)sb <= MAX_PROG_BYTES_3CTA) {
+                // light sweeps whose program fits beside three 64 KB tiles run three CTAs per SM (80 registers: the few spills sit
+                // in the per-pass setup, not in the op loop): 24 instead of 16 warps per SM hide more of the decode latency
+                SV_TRY((launch_sweep<float, FUSED_KC, 4, FUSED_NT, 3>(s, dp, pb, sb, nTiles, var)));
+            } else if (cfg.RB == 4) {
                 SV_TRY((launch_sweep<float, FUSED_KC, 4, FUSED_NT, 2>(s, dp, pb, sb, nTiles, var)));
             } else {
                 SV_TRY((launch_sweep<float, FUSED_KC, 3, FUSED_NT, 3>(s, dp, pb, sb, nTiles, var)));
@@ -2792,6 +2772,9 @@ int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targ
         buf.clear();
         size_t scratch = 0;
         SV_TRY(plan_and_encode(pending, cfg, precision, buf, &bytes, &scratch, &nops, &npass));
+        if (getenv("B200SV_FUSED_DEBUG")) {
+            fprintf(stderr, "  program %zu B + scratch %zu B%s\n", bytes, scratch, (bytes + scratch <= MAX_PROG_BYTES_3CTA) ? " (fits 3 CTAs/SM)" : "");
+        }
         ++sweeps;
         passes += npass;
     }

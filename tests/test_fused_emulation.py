@@ -66,8 +66,9 @@ def test_emulated_sweeps_under_every_tile_shape(knobs, search):
         "    util.assert_states_close({k: v.GetQuantumState() for k, v in regs.items()}, want, prec, 'knobs')\n"
         "print('ok')\n"
     ) % (util.ROOT, os.path.join(util.ROOT, "tests"))
-    # half of the settings also switch the 2^5-chunk sub-blocks of light flushes (RB = 5, 128-thread CTAs) off
-    env = dict(os.environ, B200SV_FUSED=knobs, B200SV_PLAN_SEARCH=search, B200SV_RB5=("0" if search in ("0", "4") else "1"))
+    # half of the settings also switch the rotation stages (rewrite R5) and the lazy diagonals off
+    env = dict(os.environ, B200SV_FUSED=knobs, B200SV_PLAN_SEARCH=search, B200SV_ROT=("0" if search in ("0", "4") else "1"),
+               B200SV_LAZY_DIAG=("0" if search == "1" else "1"))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 

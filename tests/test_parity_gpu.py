@@ -544,11 +544,11 @@ def test_memoised_marginals_follow_every_state_change(prec):
         assert abs(g2.Prob(q) - w) <= tol
 
 
-@pytest.mark.parametrize("env", [{"B200SV_RB5": "0"}, {"B200SV_ROT": "0"}, {"B200SV_LAZY_DIAG": "0"}, {"B200SV_REWRITE": "0"},
+@pytest.mark.parametrize("env", [{"B200SV_MINB3": "1"}, {"B200SV_ROT": "0"}, {"B200SV_LAZY_DIAG": "0"}, {"B200SV_REWRITE": "0"},
                                  {"B200SV_FORCE_FULL": "1"}, {"B200SV_FUSED": "3,6,6,7,3"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_scheduler_knobs_keep_parity_on_the_device(env):
-    """Every scheduler / kernel-variant switch (sub-block size, rotation stages, lazy diagonals, the rewrite itself, the full kernel
+    """Every scheduler / kernel-variant switch (three CTAs per SM for small programs, rotation stages, lazy diagonals, the rewrite itself, the full kernel
     variant, the RB=3 tile shape) must reproduce the oracle on the DEVICE kernels too (the library reads its knobs once per process,
     hence the subprocess).  17-18 qubits: several tiles, high tile qubits, outer controls, thread-level members, several passes."""
     import subprocess

@@ -1366,6 +1366,7 @@ struct SweepPlan {
 
 // Count-only twin of greedy_select for a FIXED tile (no copies): how many of the first `lookahead` pending ops could run in
 // a sweep whose tile qubits are `inTile`.
+static int knob_plan_weight();
 static size_t greedy_count(const std::vector<HostOp>& pending, size_t maxTake, size_t lookahead, uint64_t inTile)
 {
     uint64_t blockedT = 0, blockedD = 0;
@@ -1382,7 +1383,8 @@ static size_t greedy_count(const std::vector<HostOp>& pending, size_t maxTake, s
                 break; // every tile qubit is blocked: only stray diagonal gates could still be taken
             }
         } else {
-            ++taken;
+            // objective of the search: non-diagonal ops weigh `w`, diagonal ops 1 (knob B200SV_PLAN_WEIGHT, default 1 = plain count)
+            taken += (op.kind == OP_PHASE) ? 1U : (size_t)knob_plan_weight();
         }
     }
     return taken;
@@ -2277,6 +2279,14 @@ static int knob_rewrite()
 constexpr int FUSED_KC = 12;
 constexpr int FUSED_NT = 256;
 
+static int knob_plan_weight()
+{
+    static const int v = [] {
+        const char* e = getenv("B200SV_PLAN_WEIGHT");
+        return e ? std::max(1, atoi(e)) : 1;
+    }();
+    return v;
+}
 static int knob_minb3()
 {
     static const int v = [] {

@@ -338,17 +338,24 @@ def test_full_size_parity_against_the_compiled_reference(n, prec, kind, tmp_path
     sp.write_text(text)
     subprocess.run([util.ref_harness(prec), str(sp), "--results", str(tmp_path / "r.txt")], check=True, timeout=1500)
     want = qscript.parse_results(open(str(tmp_path / "r.txt")).read())
+    # the fp32 reference sums each Prob (2^29 terms) in fp32 per worker thread with a dynamic work split, so its own value wanders by
+    # up to ~1e-4 from run to run (measured: 9e-5 between two runs at 24 qubits): the per-qubit probabilities of the fp32 case are
+    # taken from the fp64 build of the reference on the same circuit
+    want_prob = want
+    if prec == 32 and util.ref_harness(64) is not None:
+        subprocess.run([util.ref_harness(64), str(sp), "--results", str(tmp_path / "r64.txt")], check=True, timeout=1500)
+        want_prob = qscript.parse_results(open(str(tmp_path / "r64.txt")).read())
     _, got = qscript.run(text, util.make_factory(QEngineCUDA, prec))
     assert len(got) == len(want) == n + 64
     worst_p = worst_a = 0.0
-    for (gn, gv), (wn, wv) in zip(got, want):
+    for (gn, gv), (wn, wv), (_, wpv) in zip(got, want, want_prob):
         assert gn == wn
         if gn == "Prob":
-            worst_p = max(worst_p, abs(gv[0] - wv[0]))
+            worst_p = max(worst_p, abs(gv[0] - wpv[0]))
         else:
             worst_a = max(worst_a, abs(complex(*gv) - complex(*wv)))
     assert worst_a <= util.AMP_TOL[prec], "max |delta amp| over 64 samples = %.3e" % worst_a
-    # Prob is a 2^(n-1)-term reduction: the reference sums per thread in real1 (fp32: ~1e-5 of drift by itself)
+    # Prob: ours accumulates in double; against the fp64 reference what is left is the fp32 state's own rounding
     assert worst_p <= (2e-5 if prec == 32 else 1e-10), "max |delta Prob| = %.3e" % worst_p
 
 

@@ -113,6 +113,12 @@ def test_sharded_26q_against_the_compiled_reference(kind, tmp_path):
     sp.write_text(text)
     subprocess.run([util.ref_harness(32), str(sp), "--results", str(tmp_path / "r.txt")], check=True, timeout=1200)
     want = np.array([v for _, vals in qscript.parse_results(open(str(tmp_path / "r.txt")).read()) for v in vals], dtype=np.float64)
+    # the fp32 reference sums each Prob (2^25 terms) in fp32 per worker thread with a dynamic work split: its own value wanders by
+    # ~1e-4 from run to run.  The per-qubit probabilities are therefore taken from the fp64 build of the reference (same circuit).
+    want_p = want[:n]
+    if util.ref_harness(64) is not None:
+        subprocess.run([util.ref_harness(64), str(sp), "--results", str(tmp_path / "r64.txt")], check=True, timeout=1200)
+        want_p = np.array([v for _, vals in qscript.parse_results(open(str(tmp_path / "r64.txt")).read()) for v in vals], dtype=np.float64)[:n]
     import torch.multiprocessing as mp
     out = str(tmp_path / "o.npz")
     for attempt in range(3):
@@ -126,6 +132,6 @@ def test_sharded_26q_against_the_compiled_reference(kind, tmp_path):
     got = z["results"]
     assert got.shape == want.shape
     assert np.abs(got[n:] - want[n:]).max() <= util.AMP_TOL[32], np.abs(got[n:] - want[n:]).max()   # amplitudes (re, im pairs): the parity bar
-    # Prob: the reference sums 2^25 terms per qubit in fp32 per worker thread (its own drift is a few 1e-5); ours accumulates in double
-    assert np.abs(got[:n] - want[:n]).max() <= 1e-4, np.abs(got[:n] - want[:n]).max()
+    # Prob (ours: fp32 state, double accumulation) against the fp64 reference: what is left is the fp32 state's own rounding
+    assert np.abs(got[:n] - want_p).max() <= 2e-5, np.abs(got[:n] - want_p).max()
     assert abs(float(z["norm"]) - 1.0) < 1e-4 and float(z["amp"]) > 0.999

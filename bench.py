@@ -491,7 +491,10 @@ def main():
             page_bytes = (1 << args.qubits) * amp_bytes
             line["sharding"] = {"exchanges_per_step": exchanges / max(1, args.steps),
                                 "nvlink_bytes_out_per_gpu_per_step": exchanges / max(1, args.steps) * page_bytes * (world - 1) / world,
-                                "sweeps_per_step": stats["fused_sweeps"] / max(1, args.steps)}
+                                "sweeps_per_step": stats["fused_sweeps"] / max(1, args.steps),
+                                # exchanges carried by the first sweep of the next window (b200sv_exchange_pull) instead of a pass of their own
+                                "pull_sweeps_per_step": stats.get("pull_sweeps", 0) / max(1, args.steps),
+                                "exchange_mode": "pull (fused into the next sweep)" if stats.get("pull_sweeps", 0) else "push kernel"}
         if check is not None:
             line["check"] = check
         if e2e_batched is not None:

@@ -152,6 +152,16 @@ int b200sv_ipc_export(int device, void* ptr, unsigned char handle_out[64]);
 int b200sv_ipc_import(int device, const unsigned char handle[64], void** ptr);
 int b200sv_ipc_release(int device, void* ptr);
 int b200sv_exchange_scatter(b200sv_t s, int k, const int* victim_bits, int rank, void* const* dst_pages);
+/* The same re-page in PULL mode, fused into the next gate sweep: declares that this state's content is now the exchanged view
+ * of the ranks' current pages (src_pages[r] = rank r's page as mapped in this process, src_pages[rank] = this state's own
+ * page; element i of the new page = element (i with the victim bits := this rank's bits) of the page of rank r' = the victim
+ * bits of i) and that it lives in out_page from now on.  Nothing is copied by this call: the FIRST fused sweep of the next
+ * flush reads its tiles straight through the peer mappings and writes out_page (k_fused_sweep<PULL>), so the exchange costs
+ * no pass of its own; a flush with no sweep to carry it runs a plain gather kernel.  The caller orders the ranks: a barrier
+ * between the last write of every source page and this call's first use, and none of the source pages may be written until
+ * every rank has flushed (the next barrier).  1 <= k <= 3.  (Reference: QPager::MetaSwap / SeparateEngines re-paging,
+ * src/qpager.cpp:316-367,425-432, always a separate pass there.) */
+int b200sv_exchange_pull(b200sv_t s, int k, const int* victim_bits, int rank, void* const* src_pages, void* out_page);
 
 /* ---- queue / fusion control ---- */
 int b200sv_flush(b200sv_t s);  /* launch everything queued; does not wait */
@@ -201,6 +211,11 @@ int b200sv_plan_dry_run(int n_qubits, int precision, int n_gates, const int* tar
  * pmasks[i]) in its single-target form.  `pytest -m "not gpu"` checks scheduler + encoder against the oracle with it. */
 int b200sv_emulate_fused(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,
     const uint64_t* pmasks, const double* mats8, void* host_state);
+/* TEST HOOK (host only): the same with a pending b200sv_exchange_pull — src_states[r] are HOST arrays standing in for the
+ * ranks' pages, out_state receives this rank's new page after the gates (first sweep reads through the pull mapping). */
+int b200sv_emulate_fused_pull(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,
+    const uint64_t* pmasks, const double* mats8, int k, const int* victim_bits, int rank, void* const* src_states,
+    void* out_state);
 
 typedef struct b200sv_stats {
     uint64_t gates_submitted;  /* apply2x2-class calls accepted */
@@ -209,6 +224,7 @@ typedef struct b200sv_stats {
     uint64_t fused_gates;      /* gates executed inside fused sweeps */
     uint64_t single_launches;  /* unfused single-gate launches */
     uint64_t bytes_swept;      /* physical bytes read+written by gate kernels */
+    uint64_t pull_sweeps;      /* fused sweeps that also carried a pending re-page (b200sv_exchange_pull) */
 } b200sv_stats;
 int b200sv_get_stats(b200sv_t s, b200sv_stats* out);
 int b200sv_reset_stats(b200sv_t s);

@@ -19,7 +19,8 @@ B200SV_OK, B200SV_EINVAL, B200SV_ENOMEM, B200SV_ECUDA, B200SV_ESTATE = 0, -1, -2
 
 class Stats(ctypes.Structure):
     _fields_ = [("gates_submitted", c_uint64), ("kernel_launches", c_uint64), ("fused_sweeps", c_uint64),
-                ("fused_gates", c_uint64), ("single_launches", c_uint64), ("bytes_swept", c_uint64)]
+                ("fused_gates", c_uint64), ("single_launches", c_uint64), ("bytes_swept", c_uint64),
+                ("pull_sweeps", c_uint64)]
 
 
 # name -> (argtypes)  — every symbol include/b200sv.h declares; tests/test_abi.py checks the two stay in sync
@@ -83,6 +84,7 @@ SIGNATURES = {
     "b200sv_ipc_import": [c_int, c_void_p, POINTER(c_void_p)],
     "b200sv_ipc_release": [c_int, c_void_p],
     "b200sv_exchange_scatter": [H, c_int, POINTER(c_int), c_int, POINTER(c_void_p)],
+    "b200sv_exchange_pull": [H, c_int, POINTER(c_int), c_int, POINTER(c_void_p), c_void_p],
     "b200sv_rol": [H, c_int, c_int, c_int],
     "b200sv_inc": [H, c_uint64, c_int, c_int, c_uint64],
     "b200sv_incdecc": [H, c_uint64, c_int, c_int, c_int],
@@ -100,6 +102,8 @@ SIGNATURES = {
                             POINTER(c_int)],
     "b200sv_emulate_fused": [c_int, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double),
                              c_void_p],
+    "b200sv_emulate_fused_pull": [c_int, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double),
+                                  c_int, POINTER(c_int), c_int, POINTER(c_void_p), c_void_p],
     "b200sv_get_stats": [H, POINTER(Stats)],
     "b200sv_reset_stats": [H],
     "b200sv_timer_begin": [H],

@@ -1122,6 +1122,40 @@ __global__ void __launch_bounds__(256) k_exchange_scatter(const uint4* __restric
     }
 }
 
+// The same re-page seen from the receiving side (PullArgs, sv_common.cuh): chunk c of this rank's new page comes from the rank
+// named by the victim bits of c.  Used when a pending pull is not followed by a fused sweep that could carry it.
+struct GatherArgs {
+    const uint4* src[8];
+    int cb[3];
+    int k;
+    uint64_t vmask, rankDep; // in chunks
+};
+__global__ void __launch_bounds__(256) k_exchange_gather(uint4* __restrict__ out, uint64_t nChunks, const __grid_constant__ GatherArgs a)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t c0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c0 < nChunks; c0 += stride * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t c = c0 + u * stride;
+            if (c < nChunks) {
+                unsigned r = 0;
+                for (int b = 0; b < a.k; ++b) {
+                    r |= (unsigned)((c >> a.cb[b]) & 1ULL) << b;
+                }
+                v[u] = a.src[r][(c & ~a.vmask) | a.rankDep];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t c = c0 + u * stride;
+            if (c < nChunks) {
+                out[c] = v[u];
+            }
+        }
+    }
+}
+
 __global__ void k_fill_bytes(uint4* p, uint64_t n, unsigned v)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -1329,10 +1363,47 @@ static int run_gate_unfused(State* s, const GateOp& g)
                            : launch_apply2x2<double>(s, off1, off2, g.m, nb, pows, 1.0, 0.0, nullptr);
 }
 
+int launch_pull_gather(State* s)
+{
+    if (!s->pullPending) {
+        return B200SV_OK;
+    }
+    const int apcLog = (s->prec == 32) ? 1 : 0;
+    GatherArgs a;
+    memset(&a, 0, sizeof(a));
+    a.k = s->pull.k;
+    for (int b = 0; b < a.k; ++b) {
+        a.cb[b] = s->pull.vb[b] - apcLog;
+    }
+    for (int r = 0; r < (1 << a.k); ++r) {
+        a.src[r] = (const uint4*)s->pull.peers[r];
+    }
+    a.vmask = s->pull.vmask >> apcLog;
+    a.rankDep = s->pull.rankDep >> apcLog;
+    const uint64_t nChunks = (s->dim() * s->amp_bytes()) / 16U;
+    const unsigned grid = stream_grid(s->dev, (nChunks + 3) / 4, 256);
+    k_exchange_gather<<<grid, 256, 0, s->stream>>>((uint4*)s->pull.out, nChunks, a);
+    SV_CUDA(cudaGetLastError());
+    s->amps = s->pull.out;
+    s->pullPending = false;
+    s->stats.kernel_launches++;
+    return B200SV_OK;
+}
+
+// the queue (and a pending re-page) no longer matter: the caller overwrites the whole state
+static void drop_pending(State* s)
+{
+    s->queue.clear();
+    if (s->pullPending) {
+        s->amps = s->pull.out;
+        s->pullPending = false;
+    }
+}
+
 static int flush_queue(State* s)
 {
     if (s->queue.empty()) {
-        return B200SV_OK;
+        return s->pullPending ? launch_pull_gather(s) : B200SV_OK;
     }
     // fused_flush consumes the queue.  If its planner / encoder gives up (ESTATE: "no progress", "does not fit") nothing has been
     // launched yet, so the gates are replayed one by one on the generic kernel instead of being dropped; a CUDA failure
@@ -1345,6 +1416,7 @@ static int flush_queue(State* s)
     const int rc = fused_flush(s);
     if (rc == B200SV_ESTATE && keep) {
         s->queue.clear();
+        SV_TRY(launch_pull_gather(s)); // (no-op unless a re-page is still pending)
         for (const GateOp& g : saved) {
             SV_TRY(run_gate_unfused(s, g));
         }
@@ -1651,6 +1723,57 @@ int b200sv_exchange_scatter(b200sv_t s, int k, const int* victim_bits, int rank,
     return B200SV_OK;
 }
 
+static int fill_pull_args(int nq, int prec, int k, const int* victim_bits, int rank, const void* const* src_pages, void* out_page,
+    PullArgs* pa)
+{
+    if (k < 1 || k > 3 || !victim_bits || !src_pages || !out_page || rank < 0 || rank >= (1 << k)) {
+        return einval("exchange_pull: bad arguments (1 <= k <= 3)");
+    }
+    const int apcLog = (prec == 32) ? 1 : 0;
+    memset(pa, 0, sizeof(*pa));
+    pa->k = k;
+    for (int b = 0; b < k; ++b) {
+        if (victim_bits[b] < apcLog || victim_bits[b] >= nq) {
+            return einval("exchange_pull: victim qubit out of range (must be a local qubit above the 16-byte chunk)");
+        }
+        for (int b2 = 0; b2 < b; ++b2) {
+            if (victim_bits[b2] == victim_bits[b]) {
+                return einval("exchange_pull: duplicate victim qubit");
+            }
+        }
+        pa->vb[b] = victim_bits[b];
+        pa->vmask |= 1ULL << victim_bits[b];
+        if ((rank >> b) & 1) {
+            pa->rankDep |= 1ULL << victim_bits[b];
+        }
+    }
+    for (int r = 0; r < (1 << k); ++r) {
+        if (!src_pages[r]) {
+            return einval("exchange_pull: null source page");
+        }
+        if (src_pages[r] == out_page) {
+            return einval("exchange_pull: the out page must differ from every source page");
+        }
+        pa->peers[r] = src_pages[r];
+    }
+    pa->out = out_page;
+    return B200SV_OK;
+}
+
+int b200sv_exchange_pull(b200sv_t s, int k, const int* victim_bits, int rank, void* const* src_pages, void* out_page)
+{
+    SV_ENTER(s);
+    if (!s->external || !s->amps) {
+        return einval("exchange_pull: needs a state over an external page");
+    }
+    PullArgs pa;
+    SV_TRY(fill_pull_args(s->nq, s->prec, k, victim_bits, rank, src_pages, out_page, &pa));
+    SV_TRY(flush_queue(s)); // everything queued so far belongs to the old layout (and resolves an earlier pending pull)
+    s->pull = pa;
+    s->pullPending = true;
+    return B200SV_OK;
+}
+
 int b200sv_set_stream(b200sv_t s, void* stream, int adopt)
 {
     SV_ENTER(s);
@@ -1794,7 +1917,7 @@ int b200sv_set_permutation(b200sv_t s, uint64_t perm, double re, double im)
     if (perm >= s->dim()) {
         return einval("SetPermutation: permutation out of bounds");
     }
-    s->queue.clear(); // Dump(): pending gates are irrelevant (reference state.cpp:230)
+    drop_pending(s); // Dump(): pending gates are irrelevant (reference state.cpp:230)
     SV_TRY(alloc_amps(s, false));
     SV_CUDA(cudaMemsetAsync(s->amps, 0, (size_t)s->dim() * s->amp_bytes(), s->stream));
     if (s->prec == 32) {
@@ -1812,7 +1935,7 @@ int b200sv_set_permutation(b200sv_t s, uint64_t perm, double re, double im)
 int b200sv_zero(b200sv_t s)
 {
     SV_ENTER(s);
-    s->queue.clear();
+    drop_pending(s);
     if (s->external) {
         if (s->amps) {
             SV_CUDA(cudaMemsetAsync(s->amps, 0, (size_t)s->dim() * s->amp_bytes(), s->stream));
@@ -1838,7 +1961,7 @@ int b200sv_set_state(b200sv_t s, const void* host)
     if (!host) {
         return einval("null host pointer");
     }
-    s->queue.clear();
+    drop_pending(s);
     SV_TRY(alloc_amps(s, false));
     SV_CUDA(cudaMemcpyAsync(s->amps, host, (size_t)s->dim() * s->amp_bytes(), cudaMemcpyHostToDevice, s->stream));
     SV_CUDA(cudaStreamSynchronize(s->stream));
@@ -2068,7 +2191,7 @@ int b200sv_copy_state(b200sv_t dst, b200sv_t src)
     if (!src->amps && src->queue.empty()) {
         return b200sv_zero(dst);
     }
-    dst->queue.clear();
+    drop_pending(dst);
     return b200sv_copy_page(dst, src, 0, 0, src->dim());
 }
 
@@ -3305,6 +3428,27 @@ int b200sv_emulate_fused(int n_qubits, int precision, int n_gates, const uint64_
         make_gate_op(precision, off1[i], off2[i], pmasks[i], mats8 + 8 * (size_t)i, 1.0, q[(size_t)i]);
     }
     return fused_emulate(n_qubits, precision, q, host_state);
+}
+
+int b200sv_emulate_fused_pull(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,
+    const uint64_t* pmasks, const double* mats8, int k, const int* victim_bits, int rank, void* const* src_states, void* out_state)
+{
+    if (n_gates < 0 || (n_gates && (!off1 || !off2 || !pmasks || !mats8)) || (precision != 32 && precision != 64) || n_qubits < 5 ||
+        n_qubits > 30) {
+        return einval("emulate_fused_pull: bad arguments");
+    }
+    PullArgs pa;
+    SV_TRY(fill_pull_args(n_qubits, precision, k, victim_bits, rank, src_states, out_state, &pa));
+    std::vector<GateOp> q((size_t)n_gates);
+    const uint64_t dim = 1ULL << n_qubits;
+    for (int i = 0; i < n_gates; ++i) {
+        const uint64_t diff = off1[i] ^ off2[i];
+        if (!diff || (diff & (diff - 1U)) || pmasks[i] >= dim || ((off1[i] | off2[i]) & ~pmasks[i])) {
+            return einval("emulate_fused_pull: not a single-target gate");
+        }
+        make_gate_op(precision, off1[i], off2[i], pmasks[i], mats8 + 8 * (size_t)i, 1.0, q[(size_t)i]);
+    }
+    return fused_emulate(n_qubits, precision, q, out_state, &pa);
 }
 
 int b200sv_flush_l2(b200sv_t s, uint64_t bytes)

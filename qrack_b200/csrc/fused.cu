@@ -557,6 +557,45 @@ constexpr int MAX_OUTER = 192;
 
 // Staged tile copies (used when the first / last pass has register bits on low chunk bits): coalesced HBM <-> swizzled
 // smem.  Kept out of line so that their registers do not weigh on the pass loop.
+// Source address of amplitude index i of this rank's NEW page while a pull re-page is pending (PullArgs): the victim bits of i
+// name the rank whose old page holds it, at index i with the victim bits replaced by this rank's bits.
+template <typename C> __device__ __forceinline__ const C* pull_src(const PullArgs& pa, uint64_t i)
+{
+    unsigned r = (unsigned)((i >> pa.vb[0]) & 1ULL);
+    if (pa.k > 1) {
+        r |= (unsigned)((i >> pa.vb[1]) & 1ULL) << 1;
+    }
+    if (pa.k > 2) {
+        r |= (unsigned)((i >> pa.vb[2]) & 1ULL) << 2;
+    }
+    return reinterpret_cast<const C*>(pa.peers[r]) + ((i & ~pa.vmask) | pa.rankDep);
+}
+
+template <typename R, int NT>
+__device__ __noinline__ void stage_in_pull(const PullArgs& pa, uint64_t base, unsigned char* tileB, const uint64_t* rowOff,
+    uint32_t nChunk, int lcb, uint32_t colMask, int tid)
+{
+    typedef typename Cx<R>::type C;
+    constexpr int APC = AmpOps<R>::APC;
+    for (uint32_t c0 = (uint32_t)tid; c0 < nChunk; c0 += 4U * NT) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t c = c0 + (uint32_t)u * NT;
+            if (c < nChunk) {
+                v[u] = ld_stream(reinterpret_cast<const uint4*>(pull_src<C>(pa, base + rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC)));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t c = c0 + (uint32_t)u * NT;
+            if (c < nChunk) {
+                *reinterpret_cast<uint4*>(tileB + ((size_t)swz(c) << 4)) = v[u];
+            }
+        }
+    }
+}
+
 template <typename R, int NT>
 __device__ __noinline__ void stage_in(const typename Cx<R>::type* __restrict__ tilePsi, unsigned char* tileB, const uint64_t* rowOff,
     uint32_t nChunk, int lcb, uint32_t colMask, int tid)
@@ -595,9 +634,12 @@ __device__ __noinline__ void stage_out(typename Cx<R>::type* __restrict__ tilePs
     }
 }
 
-template <typename R, int KC, int RB, int NT, int MINB, int VAR>
+// PULL: the sweep also performs a pending re-page (PullArgs): its first pass (or the staged tile copy) reads every chunk through
+// the peer mapping that holds it, its last pass writes this rank's other page; everything between is unchanged.
+template <typename R, int KC, int RB, int NT, int MINB, int VAR, bool PULL = false>
 __global__ void __launch_bounds__(NT, MINB)
-    k_fused_sweep(typename Cx<R>::type* __restrict__ psi, const unsigned char* __restrict__ prog, uint32_t progBytes, uint64_t nTiles)
+    k_fused_sweep(typename Cx<R>::type* __restrict__ psi, const unsigned char* __restrict__ prog, uint32_t progBytes, uint64_t nTiles,
+        const __grid_constant__ PullArgs pull)
 {
     typedef typename Cx<R>::type C;
     typedef AmpOps<R> O;
@@ -670,7 +712,7 @@ __global__ void __launch_bounds__(NT, MINB)
             const uint64_t lo = base & sw.highLow[h];
             base = ((base ^ lo) << 1) | lo;
         }
-        C* const tilePsi = psi + base;
+        C* const tilePsi = (PULL ? reinterpret_cast<C*>(pull.out) : psi) + base; // PULL: the tile's place in the OUT page
         R* const tileScale = tileTab + par * tabStride;
         // ---- per-tile preamble ------------------------------------------------------------------------------------
         // warps 0..2: which ops act on this tile (predicates on qubits outside the tile are uniform per tile)
@@ -729,7 +771,7 @@ __global__ void __launch_bounds__(NT, MINB)
                 eff[i] = ok ? make_uint2(mb.lmask, mb.lval) : make_uint2(0U, 1U);
             }
         }
-        if (sw.prefetch && (t + gridDim.x < nTiles) && ((tid & 7) == 0)) {
+        if (!PULL && sw.prefetch && (t + gridDim.x < nTiles) && ((tid & 7) == 0)) {
             // one 128-byte line per 8 chunks: the CTA's next tile streams into L2 under the passes below
             uint64_t nb = (t + gridDim.x) << sw.lowAmpBits;
             for (int h = 0; h < sw.nHigh; ++h) {
@@ -745,7 +787,11 @@ __global__ void __launch_bounds__(NT, MINB)
             // split sectors): coalesced copy global -> swizzled smem.  The extra barrier keeps slow warps of the
             // previous tile from still reading the tile area.
             __syncthreads();
-            stage_in<R, NT>(tilePsi, tileB, rowOff, nChunk, lcb, colMask, tid);
+            if (PULL) {
+                stage_in_pull<R, NT>(pull, base, tileB, rowOff, nChunk, lcb, colMask, tid);
+            } else {
+                stage_in<R, NT>(tilePsi, tileB, rowOff, nChunk, lcb, colMask, tid);
+            }
         }
         // The barrier publishes the tables (and the staged tile) and closes the previous tile: nobody still reads the
         // tile area of smem.
@@ -766,7 +812,14 @@ __global__ void __launch_bounds__(NT, MINB)
                 const uint32_t swb = swz(sbc) << 4;
                 C* const gsub = tilePsi + rowOff[sbc >> lcb] + (uint64_t)(sbc & colMask) * APC;
                 A a[NA];
-                if (fromGlobal) {
+                if (fromGlobal && PULL) {
+                    const uint64_t gi = base + rowOff[sbc >> lcb] + (uint64_t)(sbc & colMask) * APC;
+#pragma unroll
+                    for (int e = 0; e < NCH; ++e) {
+                        const uint4 v = ld_stream(reinterpret_cast<const uint4*>(pull_src<C>(pull, gi + ps.goff[e])));
+                        O::get(*reinterpret_cast<const Chunk*>(&v), &a[e * APC]);
+                    }
+                } else if (fromGlobal) {
 #pragma unroll
                     for (int e = 0; e < NCH; ++e) {
                         const uint4 v = ld_stream(reinterpret_cast<const uint4*>(gsub + ps.goff[e]));
@@ -2166,10 +2219,10 @@ struct KernelCfg {
     int KC, RB, NT, MINB;
 };
 
-template <typename R, int KC, int RB, int NT, int MINB, int VAR>
+template <typename R, int KC, int RB, int NT, int MINB, int VAR, bool PULL = false>
 static int launch_sweep_v(State* s, const unsigned char* dprog, uint32_t progBytes, uint32_t scratchBytes, uint64_t nTiles)
 {
-    auto kern = k_fused_sweep<R, KC, RB, NT, MINB, VAR>;
+    auto kern = k_fused_sweep<R, KC, RB, NT, MINB, VAR, PULL>;
     const size_t shm = ((size_t)16 << KC) + progBytes + scratchBytes;
     static std::atomic<unsigned long long> attr_set_mask{ 0 }; // per device: the attribute is per-context
     if (!(attr_set_mask.load() & (1ULL << s->dev))) {
@@ -2179,8 +2232,13 @@ static int launch_sweep_v(State* s, const unsigned char* dprog, uint32_t progByt
     }
     const uint64_t maxGrid = (uint64_t)sm_count(s->dev) * MINB;
     const unsigned grid = (unsigned)std::min<uint64_t>(nTiles, maxGrid);
-    kern<<<grid, NT, shm, s->stream>>>(reinterpret_cast<typename Cx<R>::type*>(s->amps), dprog, progBytes, nTiles);
+    kern<<<grid, NT, shm, s->stream>>>(reinterpret_cast<typename Cx<R>::type*>(s->amps), dprog, progBytes, nTiles,
+        PULL ? s->pull : PullArgs{});
     SV_CUDA(cudaGetLastError());
+    if (PULL) {
+        s->amps = s->pull.out; // the rest of the flush (and everything after it) works in place on the new page
+        s->pullPending = false;
+    }
     return B200SV_OK;
 }
 
@@ -2321,10 +2379,19 @@ static bool flush_is_light(const std::vector<HostOp>& ops)
     return true;
 }
 
+static int knob_pull_fused()
+{
+    static const int v = [] {
+        const char* e = getenv("B200SV_PULL_FUSED");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+
 int fused_flush(State* s)
 {
     if (s->queue.empty()) {
-        return B200SV_OK;
+        return s->pullPending ? launch_pull_gather(s) : B200SV_OK;
     }
     if (!s->amps) {
         s->queue.clear();
@@ -2333,11 +2400,15 @@ int fused_flush(State* s)
     std::vector<HostOp> pending;
     const uint64_t xtail = lower_queue(s->queue, pending);
     const size_t nGates = s->queue.size();
+    const TileCfg cfg = state_cfg(s->nq, s->prec, flush_is_light(pending));
+    // A pending re-page rides on the first sweep when there is one (RB = 4 instantiations only); otherwise it is a plain gather.
+    if (s->pullPending && (pending.empty() || cfg.RB != 4 || !knob_pull_fused())) {
+        SV_TRY(launch_pull_gather(s));
+    }
     s->queue.clear();
     if (pending.empty()) {
         return xtail ? launch_xmask(s, xtail) : B200SV_OK;
     }
-    const TileCfg cfg = state_cfg(s->nq, s->prec, flush_is_light(pending));
     Arena* ar = get_arena(s);
     if (!ar->done) {
         SV_CUDA(cudaEventCreateWithFlags(&ar->done, cudaEventDisableTiming));
@@ -2380,7 +2451,15 @@ int fused_flush(State* s)
         const DevSweep* dsw = reinterpret_cast<const DevSweep*>(buf.data() + segs[i].off);
         const bool full = knob_force_full() || dsw->needFull != 0;
         const int var = full ? 2 : (dsw->nRot ? 1 : 0);
-        if (s->prec == 32) {
+        if (s->pullPending) {
+            // (i == 0) the re-page rides on this sweep: the full variant, two CTAs per SM
+            if (s->prec == 32) {
+                SV_TRY((launch_sweep_v<float, FUSED_KC, 4, FUSED_NT, 2, 2, true>(s, dp, pb, sb, nTiles)));
+            } else {
+                SV_TRY((launch_sweep_v<double, FUSED_KC, 4, FUSED_NT, 2, 2, true>(s, dp, pb, sb, nTiles)));
+            }
+            s->stats.pull_sweeps++;
+        } else if (s->prec == 32) {
             if (cfg.RB == 4 && var != 2 && knob_minb3() && (size_t)pb + (size_t)sb <= MAX_PROG_BYTES_3CTA) {
                 // light sweeps whose program fits beside three 64 KB tiles run three CTAs per SM (80 registers: the few spills sit
                 // in the per-pass setup, not in the op loop): 24 instead of 16 warps per SM hide more of the decode latency
@@ -2571,7 +2650,19 @@ static void emu_exec_op(std::vector<EmuC<R>>& a, const DevOp<R>& op, uint32_t xs
     }
 }
 
-template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<R>* psi, int nq, const TileCfg& cfg)
+// `pull` (first sweep of a flush with a pending re-page): reads go through the source pages with the device's pull_src mapping,
+// writes go to `psi` (the out page)
+template <typename R> static EmuC<R> emu_pull_load(const PullArgs& pa, uint64_t i)
+{
+    unsigned r = 0;
+    for (int b = 0; b < pa.k; ++b) {
+        r |= (unsigned)((i >> pa.vb[b]) & 1ULL) << b;
+    }
+    return reinterpret_cast<const EmuC<R>*>(pa.peers[r])[(i & ~pa.vmask) | pa.rankDep];
+}
+
+template <typename R>
+static void emulate_sweep(const unsigned char* prog, EmuC<R>* psi, int nq, const TileCfg& cfg, const PullArgs* pull = nullptr)
 {
     const DevSweep& sw = *reinterpret_cast<const DevSweep*>(prog);
     const DevOp<R>* ops = reinterpret_cast<const DevOp<R>*>(prog + sizeof(DevSweep));
@@ -2643,7 +2734,8 @@ template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<
         if (!sw.directIn) {
             for (uint32_t c = 0; c < nChunk; ++c) {
                 for (int w = 0; w < APC; ++w) {
-                    tile[(size_t)swz(c) * APC + w] = tilePsi[rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC + w];
+                    const uint64_t off = rowOff[c >> lcb] + (uint64_t)(c & colMask) * APC + w;
+                    tile[(size_t)swz(c) * APC + w] = pull ? emu_pull_load<R>(*pull, base + off) : tilePsi[off];
                 }
             }
         }
@@ -2665,8 +2757,9 @@ template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<
                     EmuC<R>* const gsub = tilePsi + rowOff[sbc >> lcb] + (uint64_t)(sbc & colMask) * APC;
                     for (int e = 0; e < NCH; ++e) {
                         for (int w = 0; w < APC; ++w) {
-                            a[(size_t)e * APC + w] =
-                                fromGlobal ? gsub[ps.goff[e] + w] : tile[(size_t)((swb ^ ps.pswzB[e]) >> 4) * APC + w];
+                            a[(size_t)e * APC + w] = !fromGlobal
+                                ? tile[(size_t)((swb ^ ps.pswzB[e]) >> 4) * APC + w]
+                                : (pull ? emu_pull_load<R>(*pull, (uint64_t)(gsub - psi) + ps.goff[e] + w) : gsub[ps.goff[e] + w]);
                         }
                     }
                     const uint32_t xsb = sbc * (uint32_t)APC;
@@ -2697,22 +2790,34 @@ template <typename R> static void emulate_sweep(const unsigned char* prog, EmuC<
     }
 }
 
-int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state)
+int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state, const PullArgs* pull)
 {
     std::vector<HostOp> pending;
     const uint64_t xtail = lower_queue(q, pending);
     const TileCfg cfg = state_cfg(n_qubits, precision, flush_is_light(pending));
     std::vector<unsigned char> buf;
+    if (pull && (pending.empty() || cfg.RB != 4 || !knob_pull_fused())) { // launch_pull_gather on the device
+        const uint64_t dim = 1ULL << n_qubits;
+        for (uint64_t i = 0; i < dim; ++i) {
+            if (precision == 32) {
+                reinterpret_cast<EmuC<float>*>(host_state)[i] = emu_pull_load<float>(*pull, i);
+            } else {
+                reinterpret_cast<EmuC<double>*>(host_state)[i] = emu_pull_load<double>(*pull, i);
+            }
+        }
+        pull = nullptr;
+    }
     while (!pending.empty()) {
         size_t bytes = 0, scratch = 0, nops = 0;
         int npass = 0;
         buf.clear();
         SV_TRY(plan_and_encode(pending, cfg, precision, buf, &bytes, &scratch, &nops, &npass));
         if (precision == 32) {
-            emulate_sweep<float>(buf.data(), reinterpret_cast<EmuC<float>*>(host_state), n_qubits, cfg);
+            emulate_sweep<float>(buf.data(), reinterpret_cast<EmuC<float>*>(host_state), n_qubits, cfg, pull);
         } else {
-            emulate_sweep<double>(buf.data(), reinterpret_cast<EmuC<double>*>(host_state), n_qubits, cfg);
+            emulate_sweep<double>(buf.data(), reinterpret_cast<EmuC<double>*>(host_state), n_qubits, cfg, pull);
         }
+        pull = nullptr; // only the first sweep carries the re-page
     }
     if (xtail) { // the trailing XMask sweep (launch_xmask on the device)
         const uint64_t dim = 1ULL << n_qubits;

@@ -77,6 +77,19 @@ struct GateOp {
     int kind;           // 0 general, 1 diagonal (m1=m2=0), 2 anti-diagonal (m0=m3=0)
 };
 
+// Pending "pull" re-page (multi-process exchange, b200sv_exchange_pull): the state's content is DEFINED as the exchanged view of
+// the ranks' source pages — element i of this rank's new page is element ((i & ~vmask) | rankDep) of the page of the rank named by
+// the victim bits of i — and is materialised into `out` by the first sweep of the next flush (k_fused_sweep<..., PULL>), whose
+// first pass reads through the peer mappings, or by the plain gather kernel when no sweep follows.  Indices in amplitudes.
+struct PullArgs {
+    const void* peers[8];
+    void* out;
+    uint64_t vmask;   // OR of the victim bits
+    uint64_t rankDep; // this rank's index bits deposited at the victim positions
+    int vb[3];
+    int k;
+};
+
 struct State {
     int dev = 0;
     int nq = 0;
@@ -96,6 +109,8 @@ struct State {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx = nullptr;
     int fusion = 1;
     std::vector<GateOp> queue;
+    bool pullPending = false; // see PullArgs
+    PullArgs pull{};
     b200sv_stats stats{};
     // memoised single-qubit marginals: marg[b] = sum |psi_i|^2 over i with bit b set, marg[64] = sum over all i.
     // Filled by ONE sweep on the first Prob(q) after a change; every mutating ABI call clears `margValid`.
@@ -130,7 +145,8 @@ int fused_flush(State* s);
 int launch_xmask(State* s, uint64_t mask); // the dedicated XMask permutation sweep (b200sv.cu); does not flush
 bool fused_accepts(const State* s, const GateOp& g);
 void fused_release(State* s);
-int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state);
+int launch_pull_gather(State* s); // the pending pull as a plain gather kernel (b200sv.cu); adopts the out page
+int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state, const PullArgs* pull = nullptr);
 int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks, const int* kinds,
     int* n_sweeps, int* n_passes);
 

@@ -159,6 +159,7 @@ class P2PShardBuffers:
                 ptrs.append(p.value)
             self.peer_pages.append(ptrs)
         self.live = 0
+        self.pull = os.environ.get("B200SV_SHARD_PULL", "1") != "0"  # 0: the push kernel (b200sv_exchange_scatter), one pass per exchange
         self.engine = QEngineCUDA.over_buffer(self.pages[0], n_local, device_index, precision, random.Random(1))
         self.engine.be.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.zero_live()
@@ -176,9 +177,22 @@ class P2PShardBuffers:
     def exchange(self, dist, world, rank, k, victim_bits):
         import ctypes
         other = 1 - self.live
-        dst = (ctypes.c_void_p * world)(*[self.peer_pages[r][other] for r in range(world)])
         vb = (ctypes.c_int * k)(*victim_bits)
         be = self.engine.be
+        if self.pull and k <= 3:
+            # PULL mode (b200sv_exchange_pull): nothing moves now.  The first fused sweep of the next window reads its tiles straight
+            # from the ranks' current pages through the peer mappings and writes this rank's other page, so the re-page costs no pass
+            # of its own.  Ordering: the flush puts the old window's last sweeps (and an earlier pending pull, which still reads the
+            # peers' previous pages) on the stream, the stream-ordered barrier then says every rank's current page is final and
+            # nobody reads my other page any more; the current pages stay untouched until the barrier of the next exchange.
+            be.flush()
+            dist.barrier()
+            src = (ctypes.c_void_p * world)(*[self.peer_pages[r][self.live] for r in range(world)])
+            be._ck(self.lib.b200sv_exchange_pull(be.h, k, vb, rank, src, ctypes.c_void_p(self.pages[other])))
+            self.live = other
+            self.engine.runningNorm = REAL1_DEFAULT_ARG
+            return self.nbytes * (world - 1) // world
+        dst = (ctypes.c_void_p * world)(*[self.peer_pages[r][other] for r in range(world)])
         be._ck(self.lib.b200sv_exchange_scatter(be.h, k, vb, rank, dst))
         # every rank's stores into my `other` page are complete once the stream-ordered barrier has completed everywhere
         dist.barrier()

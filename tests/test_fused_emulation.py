@@ -138,3 +138,74 @@ def test_emulated_sweeps_fuzz_mixed_gates():
         want, _ = util.run_engine(text, QEngineRestate, prec)
         got, _, _ = run_emu(text, prec)
         util.assert_states_close(got, want, prec, "fuzz %d" % trial)
+
+
+def _random_gate_arrays(n, n_gates, rng):
+    """random single-target gates in the ABI's (off1, off2, pmask, m) form: H, T, X, random unitaries, 0-2 controls of either polarity"""
+    import cmath
+    import ctypes
+    o1, o2, pm, mats = [], [], [], []
+    for _ in range(n_gates):
+        t = rng.randrange(n)
+        ctrls = rng.sample([q for q in range(n) if q != t], rng.choice([0, 0, 1, 1, 2]))
+        cval = sum((1 << c) for c in ctrls if rng.random() < 0.7)
+        kind = rng.choice("HHTXU")
+        if kind == "H":
+            m = [2 ** -0.5, 2 ** -0.5, 2 ** -0.5, -(2 ** -0.5)]
+        elif kind == "T":
+            m = [1, 0, 0, cmath.exp(0.25j * cmath.pi)]
+        elif kind == "X":
+            m = [0, 1, 1, 0]
+        else:
+            th, a, b = rng.uniform(0, 3.1), rng.uniform(0, 6.2), rng.uniform(0, 6.2)
+            m = [cmath.cos(th), -cmath.exp(1j * a) * cmath.sin(th), cmath.exp(1j * b) * cmath.sin(th),
+                 cmath.exp(1j * (a + b)) * cmath.cos(th)]
+        o1.append(cval)
+        o2.append(cval | (1 << t))
+        pm.append((1 << t) | sum(1 << c for c in ctrls))
+        mats.extend(x for z in m for x in (complex(z).real, complex(z).imag))
+    g = len(o1)
+    return (g, (ctypes.c_uint64 * g)(*o1), (ctypes.c_uint64 * g)(*o2), (ctypes.c_uint64 * g)(*pm), (ctypes.c_double * (8 * g))(*mats))
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("k,nl,n_gates", [(1, 14, 30), (2, 15, 60), (3, 14, 25), (2, 13, 0), (3, 16, 90)])
+def test_emulated_pull_exchange_equals_exchange_then_sweeps(prec, k, nl, n_gates):
+    """b200sv_exchange_pull rides on the first fused sweep: the host interpreter of the same programs, reading through the pull
+    mapping from W host 'pages', must give bit for bit what the plain exchange (numpy permutation) followed by the same
+    flush gives — on every rank, for victim bits anywhere in the page (tile-low, tile-high and outer qubits)."""
+    import ctypes
+    from qrack_b200 import _abi
+    lib = _abi.load()
+    rng = random.Random(1000 * k + nl + prec)
+    nrng = np.random.default_rng(k * 77 + nl)
+    W = 1 << k
+    cplx = np.complex64 if prec == 32 else np.complex128
+    pages = [(nrng.standard_normal(1 << nl) + 1j * nrng.standard_normal(1 << nl)).astype(cplx) for _ in range(W)]
+    lo = 1 if prec == 32 else 0
+    vb = rng.sample(range(lo, nl), k)
+    vmask = sum(1 << b for b in vb)
+    g, o1, o2, pm, mats = _random_gate_arrays(nl, n_gates, rng)
+    idx = np.arange(1 << nl, dtype=np.uint64)
+    src_rank = np.zeros(1 << nl, dtype=np.int64)
+    for b in range(k):
+        src_rank |= (((idx >> np.uint64(vb[b])) & np.uint64(1)).astype(np.int64) << b)
+    src = (ctypes.c_void_p * W)(*[p.ctypes.data for p in pages])
+    vbc = (ctypes.c_int * k)(*vb)
+    for rank in range(W):
+        dep = sum((1 << vb[b]) for b in range(k) if (rank >> b) & 1)
+        src_idx = (idx & np.uint64(~vmask & ((1 << nl) - 1))) | np.uint64(dep)
+        want = np.empty(1 << nl, dtype=cplx)
+        for r in range(W):
+            sel = src_rank == r
+            want[sel] = pages[r][src_idx[sel]]
+        if g:
+            _abi.check(lib, lib.b200sv_emulate_fused(nl, prec, g, o1, o2, pm, mats, want.ctypes.data_as(ctypes.c_void_p)))
+        got = np.full(1 << nl, np.nan, dtype=cplx)
+        _abi.check(lib, lib.b200sv_emulate_fused_pull(nl, prec, g, o1, o2, pm, mats, k, vbc, rank, src,
+                                                      got.ctypes.data_as(ctypes.c_void_p)))
+        assert np.array_equal(got, want), (rank, vb)
+    # argument checks: the out page may not alias a source, k is bounded by the 8 peers of one box
+    assert lib.b200sv_emulate_fused_pull(nl, prec, 0, None, None, None, None, k, vbc, 0, src, ctypes.c_void_p(pages[0].ctypes.data)) \
+        == _abi.B200SV_EINVAL
+    assert lib.b200sv_emulate_fused_pull(nl, prec, 0, None, None, None, None, 4, vbc, 0, src, None) == _abi.B200SV_EINVAL

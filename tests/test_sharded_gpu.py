@@ -23,9 +23,11 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, port, text, prec, out_path, p2p):
+def _worker(rank, world, port, text, prec, out_path, mode):
     import torch
     import torch.distributed as dist
+    p2p = mode != "nccl"
+    os.environ["B200SV_SHARD_PULL"] = "1" if mode == "pull" else "0"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -39,14 +41,14 @@ def _worker(rank, world, port, text, prec, out_path, p2p):
         regs, results = qscript.run(text, make)
         st = regs[0].GetQuantumState()
         if rank == 0:
-            np.savez(out_path, state=st, exchanges=regs[0].be.exchanges)
+            np.savez(out_path, state=st, exchanges=regs[0].be.exchanges, pull_sweeps=regs[0].be.shard.stats().get("pull_sweeps", 0))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [False, True], ids=["nccl_all_to_all", "p2p_scatter_kernel"])
+@pytest.mark.parametrize("mode", ["nccl", "push", "pull"], ids=["nccl_all_to_all", "p2p_scatter_kernel", "p2p_pull_fused_into_sweep"])
 @pytest.mark.parametrize("prec", [32, 64])
-def test_sharded_nccl_matches_oracle(prec, p2p, tmp_path):
+def test_sharded_nccl_matches_oracle(prec, mode, tmp_path):
     world = 2 if _ngpu() < 4 else 4
     if _ngpu() < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -56,7 +58,7 @@ def test_sharded_nccl_matches_oracle(prec, p2p, tmp_path):
     out = str(tmp_path / "o.npz")
     for attempt in range(3):  # the rendezvous port can be taken between probing and binding
         try:
-            mp.spawn(_worker, args=(world, _free_port(), text, prec, out, p2p), nprocs=world, join=True)
+            mp.spawn(_worker, args=(world, _free_port(), text, prec, out, mode), nprocs=world, join=True)
             break
         except Exception as e:
             if "EADDRINUSE" not in str(e) or attempt == 2:
@@ -65,6 +67,10 @@ def test_sharded_nccl_matches_oracle(prec, p2p, tmp_path):
     d = float(np.abs(z["state"].astype(np.complex128) - want[0].astype(np.complex128)).max())
     assert d <= util.AMP_TOL[prec], d
     assert int(z["exchanges"]) >= 1
+    if mode == "pull":
+        assert int(z["pull_sweeps"]) >= 1     # the re-page really rode on a fused sweep (b200sv_exchange_pull)
+    else:
+        assert int(z["pull_sweeps"]) == 0
 
 
 def _worker_queries(rank, world, port, text, prec, out_path):

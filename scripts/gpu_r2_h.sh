@@ -23,10 +23,10 @@ for l in sys.stdin:
   tail -2 gpurun_out/bench_${name}_$N.err
 }
 bench htcnot_pull B200SV_SHARD_PULL=1 --steps 3 --warmup 3
-bench htcnot_push B200SV_SHARD_PULL=0 --steps 3 --warmup 3 --skip-check
+[ "${PUSH:-1}" = "1" ] && bench htcnot_push B200SV_SHARD_PULL=0 --steps 3 --warmup 3 --skip-check
 if [ "${QV:-1}" = "1" ]; then
 bench qv_pull B200SV_SHARD_PULL=1 --steps 2 --warmup 3 --workload qv
-bench qv_push B200SV_SHARD_PULL=0 --steps 2 --warmup 3 --workload qv --skip-check
+[ "${PUSH:-1}" = "1" ] && bench qv_push B200SV_SHARD_PULL=0 --steps 2 --warmup 3 --workload qv --skip-check
 fi
 if [ "${GROVER:-1}" = "1" ]; then
 bench grover_pull B200SV_SHARD_PULL=1 --steps 2 --warmup 3 --workload grover --qubits 31 --depth 3

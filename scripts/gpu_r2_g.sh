@@ -2,6 +2,8 @@
 # r2 final GPU call (1 GPU): the bench contract lines of both arms, the ncu launch list of the same command, one ncu --set full capture
 set -u
 mkdir -p gpurun_out
+echo "== re-page primitives on one device (pull fused into the sweep / gather / push)"
+timeout 600 python -m pytest tests/test_exchange_gpu.py -q -m gpu 2>&1 | tail -5 | tee gpurun_out/pytest_exchange_gpu.log
 echo "== bench (default flags, incl. cpu_baseline)"
 timeout 900 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench.err | tee gpurun_out/bench.json
 echo "== bench --impl reference"

@@ -211,6 +211,9 @@ int b200sv_plan_dry_run(int n_qubits, int precision, int n_gates, const int* tar
  * pmasks[i]) in its single-target form.  `pytest -m "not gpu"` checks scheduler + encoder against the oracle with it. */
 int b200sv_emulate_fused(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,
     const uint64_t* pmasks, const double* mats8, void* host_state);
+/* DIAGNOSTIC (host only): what one flush of this gate list would launch — fused sweeps, register passes, device ops */
+int b200sv_plan_gates(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,
+    const uint64_t* pmasks, const double* mats8, int* n_sweeps, int* n_passes, int* n_ops);
 /* TEST HOOK (host only): the same with a pending b200sv_exchange_pull — src_states[r] are HOST arrays standing in for the
  * ranks' pages, out_state receives this rank's new page after the gates (first sweep reads through the pull mapping). */
 int b200sv_emulate_fused_pull(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,

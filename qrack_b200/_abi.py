@@ -102,6 +102,8 @@ SIGNATURES = {
                             POINTER(c_int)],
     "b200sv_emulate_fused": [c_int, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double),
                              c_void_p],
+    "b200sv_plan_gates": [c_int, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double),
+                          POINTER(c_int), POINTER(c_int), POINTER(c_int)],
     "b200sv_emulate_fused_pull": [c_int, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double),
                                   c_int, POINTER(c_int), c_int, POINTER(c_void_p), c_void_p],
     "b200sv_get_stats": [H, POINTER(Stats)],

@@ -3411,6 +3411,24 @@ int b200sv_plan_dry_run(int n_qubits, int precision, int n_gates, const int* tar
     return fused_plan_dry_run(n_qubits, precision, n_gates, targets, cmasks, kinds, n_sweeps, n_passes);
 }
 
+int b200sv_plan_gates(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2, const uint64_t* pmasks,
+    const double* mats8, int* n_sweeps, int* n_passes, int* n_ops)
+{
+    if (n_gates < 0 || (n_gates && (!off1 || !off2 || !pmasks || !mats8)) || (precision != 32 && precision != 64) || n_qubits < 5 ||
+        n_qubits > 62 || !n_sweeps || !n_passes || !n_ops) {
+        return einval("plan_gates: bad arguments");
+    }
+    std::vector<GateOp> q((size_t)n_gates);
+    for (int i = 0; i < n_gates; ++i) {
+        const uint64_t diff = off1[i] ^ off2[i];
+        if (!diff || (diff & (diff - 1U)) || (n_qubits < 64 && (pmasks[i] >> n_qubits)) || ((off1[i] | off2[i]) & ~pmasks[i])) {
+            return einval("plan_gates: not a single-target gate");
+        }
+        make_gate_op(precision, off1[i], off2[i], pmasks[i], mats8 + 8 * (size_t)i, 1.0, q[(size_t)i]);
+    }
+    return fused_plan_gates(n_qubits, precision, q, n_sweeps, n_passes, n_ops);
+}
+
 int b200sv_emulate_fused(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2, const uint64_t* pmasks,
     const double* mats8, void* host_state)
 {

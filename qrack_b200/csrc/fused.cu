@@ -2836,6 +2836,29 @@ int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, voi
     return B200SV_OK;
 }
 
+// what a flush of this gate list would launch: sweeps, passes, device ops (host only; scripts/shard_sweep_count.py)
+int fused_plan_gates(int n_qubits, int precision, const std::vector<GateOp>& q, int* n_sweeps, int* n_passes, int* n_ops)
+{
+    std::vector<HostOp> pending;
+    (void)lower_queue(q, pending);
+    const TileCfg cfg = state_cfg(n_qubits, precision, flush_is_light(pending));
+    int sweeps = 0, passes = 0, ops = 0;
+    std::vector<unsigned char> buf;
+    while (!pending.empty()) {
+        size_t bytes = 0, nops = 0, scratch = 0;
+        int npass = 0;
+        buf.clear();
+        SV_TRY(plan_and_encode(pending, cfg, precision, buf, &bytes, &scratch, &nops, &npass));
+        ++sweeps;
+        passes += npass;
+        ops += (int)nops;
+    }
+    *n_sweeps = sweeps;
+    *n_passes = passes;
+    *n_ops = ops;
+    return B200SV_OK;
+}
+
 int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks, const int* kinds,
     int* n_sweeps, int* n_passes)
 {

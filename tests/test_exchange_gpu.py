@@ -51,7 +51,7 @@ def test_exchange_pull_and_push_on_one_device(prec, k, nl, n_gates):
     cplx = np.complex64 if prec == 32 else np.complex128
     nbytes = (1 << nl) * (8 if prec == 32 else 16)
     cur, nxt, psh = _pages(lib, W, nbytes), _pages(lib, W, nbytes), _pages(lib, W, nbytes)
-    host = [(nrng.standard_normal(1 << nl) + 1j * nrng.standard_normal(1 << nl)).astype(cplx) / np.sqrt(2.0 ** (nl + 1))
+    host = [((nrng.standard_normal(1 << nl) + 1j * nrng.standard_normal(1 << nl)) / np.sqrt(2.0 ** (nl + 1))).astype(cplx)
             for _ in range(W)]
     eng = [QEngineCUDA.over_buffer(cur[r], nl, 0, prec, random.Random(1)) for r in range(W)]
     try:

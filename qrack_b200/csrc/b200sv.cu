@@ -1798,6 +1798,58 @@ int b200sv_flush(b200sv_t s)
     return flush_queue(s);
 }
 
+static int copy_carry(const CarryReq& c, int cap, int* n_out, uint64_t* off1, uint64_t* off2, uint64_t* pmasks, double* mats8)
+{
+    const size_t n = c.off1.size();
+    if (n > (size_t)cap) {
+        set_error("flush_carry: internal error (more ops handed back than the caller's capacity)");
+        return B200SV_ESTATE;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        off1[i] = c.off1[i];
+        off2[i] = c.off2[i];
+        pmasks[i] = c.pmask[i];
+    }
+    if (n) {
+        memcpy(mats8, c.m8.data(), n * 8 * sizeof(double));
+    }
+    *n_out = (int)n;
+    return B200SV_OK;
+}
+
+int b200sv_flush_carry(b200sv_t s, int min_ops, uint64_t must_mask, int cap, int* n_out, uint64_t* off1, uint64_t* off2,
+    uint64_t* pmasks, double* mats8)
+{
+    SV_ENTER_RO(s);
+    if (min_ops < 0 || cap < 0 || !n_out || (cap && (!off1 || !off2 || !pmasks || !mats8))) {
+        return einval("flush_carry: bad arguments");
+    }
+    *n_out = 0;
+    if (s->queue.empty() || !min_ops || !cap) {
+        return flush_queue(s);
+    }
+    std::vector<GateOp> saved;
+    const bool keep = s->queue.size() <= 8192;
+    if (keep) {
+        saved = s->queue;
+    }
+    CarryReq c;
+    c.minOps = (size_t)min_ops;
+    c.mustMask = must_mask;
+    c.cap = (size_t)cap;
+    const int rc = fused_flush(s, &c);
+    if (rc == B200SV_ESTATE && keep) { // planner gave up before anything was launched: gate by gate, nothing handed back
+        s->queue.clear();
+        SV_TRY(launch_pull_gather(s));
+        for (const GateOp& g : saved) {
+            SV_TRY(run_gate_unfused(s, g));
+        }
+        return B200SV_OK;
+    }
+    SV_TRY(rc);
+    return copy_carry(c, cap, n_out, off1, off2, pmasks, mats8);
+}
+
 int b200sv_finish(b200sv_t s)
 {
     SV_ENTER_RO(s);
@@ -3446,6 +3498,34 @@ int b200sv_emulate_fused(int n_qubits, int precision, int n_gates, const uint64_
         make_gate_op(precision, off1[i], off2[i], pmasks[i], mats8 + 8 * (size_t)i, 1.0, q[(size_t)i]);
     }
     return fused_emulate(n_qubits, precision, q, host_state);
+}
+
+int b200sv_emulate_fused_carry(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,
+    const uint64_t* pmasks, const double* mats8, void* host_state, int min_ops, uint64_t must_mask, int cap, int* n_out,
+    uint64_t* out_off1, uint64_t* out_off2, uint64_t* out_pmasks, double* out_mats8, int* n_sweeps)
+{
+    if (n_gates < 0 || (n_gates && (!off1 || !off2 || !pmasks || !mats8)) || (precision != 32 && precision != 64) || n_qubits < 5 ||
+        n_qubits > 62 || (host_state && n_qubits > 30) || min_ops < 0 || cap < 0 || !n_out ||
+        (cap && (!out_off1 || !out_off2 || !out_pmasks || !out_mats8))) {
+        return einval("emulate_fused_carry: bad arguments");
+    }
+    std::vector<GateOp> q((size_t)n_gates);
+    for (int i = 0; i < n_gates; ++i) {
+        const uint64_t diff = off1[i] ^ off2[i];
+        if (!diff || (diff & (diff - 1U)) || (pmasks[i] >> n_qubits) || ((off1[i] | off2[i]) & ~pmasks[i])) {
+            return einval("emulate_fused_carry: not a single-target gate");
+        }
+        make_gate_op(precision, off1[i], off2[i], pmasks[i], mats8 + 8 * (size_t)i, 1.0, q[(size_t)i]);
+    }
+    CarryReq c;
+    c.minOps = (size_t)min_ops;
+    c.mustMask = must_mask;
+    c.cap = (size_t)cap;
+    SV_TRY(fused_emulate(n_qubits, precision, q, host_state, nullptr, &c));
+    if (n_sweeps) {
+        *n_sweeps = c.sweepsLaunched;
+    }
+    return copy_carry(c, cap, n_out, out_off1, out_off2, out_pmasks, out_mats8);
 }
 
 int b200sv_emulate_fused_pull(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,

@@ -2155,6 +2155,120 @@ static int plan_and_encode(std::vector<HostOp>& pending, const TileCfg& cfg0, in
     }
 }
 
+// One encoded sweep inside the flush's program buffer
+struct Seg {
+    size_t off, bytes, scratch, nops;
+    int npass;
+};
+
+// a lowered op as a single-target gate (b200sv_apply_gates layout); a predicated phase takes its lowest predicate qubit as "target"
+static void export_op(const HostOp& h, CarryReq* c)
+{
+    double m[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    uint64_t o1 = 0, o2 = 0, pm = 0;
+    if (h.kind == OP_PHASE) {
+        if (!h.cmask) { // a global phase
+            m[0] = m[6] = h.m[0];
+            m[1] = m[7] = h.m[1];
+            o2 = pm = 1ULL;
+        } else {
+            const uint64_t tb = h.cmask & (~h.cmask + 1ULL);
+            o1 = h.cval & h.cmask & ~tb;
+            o2 = o1 | tb;
+            pm = h.cmask;
+            if (h.cval & tb) {
+                m[0] = 1.0;
+                m[6] = h.m[0];
+                m[7] = h.m[1];
+            } else {
+                m[0] = h.m[0];
+                m[1] = h.m[1];
+                m[6] = 1.0;
+            }
+        }
+    } else {
+        const uint64_t tb = bitq(h.tq);
+        o1 = h.cval & h.cmask;
+        o2 = o1 | tb;
+        pm = h.cmask | tb;
+        if (h.kind == OP_ROT) {
+            m[0] = h.m[0];
+            m[2] = -h.m[1];
+            m[4] = h.m[1];
+            m[6] = h.m[0];
+        } else {
+            memcpy(m, h.m, sizeof(m));
+        }
+    }
+    c->off1.push_back(o1);
+    c->off2.push_back(o2);
+    c->pmask.push_back(pm);
+    c->m8.insert(c->m8.end(), m, m + 8);
+}
+
+// Plans and encodes every sweep of a flush.  With `carry`, the under-filled tail is cut off: the longest run of trailing sweeps that
+// each hold fewer than carry->minOps lowered ops, such that nothing left over is a non-diagonal op on a qubit of carry->mustMask
+// (and the leftovers fit carry->cap), is dropped from `segs` and its ops — everything not executed, in program order, plus a
+// trailing XMask as X gates — are exported instead.  *xtail is cleared when it was exported.
+static int plan_all(std::vector<HostOp>& pending, const TileCfg& cfg, int prec, std::vector<unsigned char>& buf, std::vector<Seg>& segs,
+    CarryReq* carry, uint64_t* xtail)
+{
+    std::vector<std::vector<HostOp>> snaps;
+    while (!pending.empty()) {
+        if (carry && carry->minOps) {
+            snaps.push_back(pending);
+        }
+        const size_t off = buf.size();
+        size_t bytes = 0, scratch = 0, nops = 0;
+        int npass = 0;
+        SV_TRY(plan_and_encode(pending, cfg, prec, buf, &bytes, &scratch, &nops, &npass));
+        segs.push_back({ off, bytes, scratch, nops, npass });
+        if (getenv("B200SV_FUSED_DEBUG")) {
+            fprintf(stderr, "  program %zu B + scratch %zu B\n", bytes, scratch);
+        }
+    }
+    if (carry && carry->minOps && !segs.empty()) {
+        size_t cut = segs.size();
+        while (cut > 0) {
+            const size_t j = cut - 1;
+            if (segs[j].nops >= carry->minOps || snaps[j].size() + 64 > carry->cap) {
+                break;
+            }
+            bool ok = true;
+            for (const HostOp& h : snaps[j]) {
+                if (h.tq >= 0 && ((carry->mustMask >> h.tq) & 1ULL)) {
+                    ok = false;
+                    break;
+                }
+            }
+            if (!ok) {
+                break;
+            }
+            cut = j;
+        }
+        if (cut < segs.size()) {
+            for (const HostOp& h : snaps[cut]) {
+                export_op(h, carry);
+            }
+            for (uint64_t m = *xtail; m; m &= m - 1ULL) { // the trailing XMask follows the carried ops
+                HostOp x;
+                memset(&x, 0, sizeof(x));
+                x.kind = OP_XSWAP;
+                x.tq = __builtin_ctzll(m);
+                x.m[2] = x.m[4] = 1.0;
+                export_op(x, carry);
+            }
+            *xtail = 0;
+            buf.resize(segs[cut].off);
+            segs.resize(cut);
+        }
+    }
+    if (carry) {
+        carry->sweepsLaunched = (int)segs.size();
+    }
+    return B200SV_OK;
+}
+
 // per-state program arena (device + pinned host), guarded by an event
 struct Arena {
     unsigned char* dev = nullptr;
@@ -2388,7 +2502,7 @@ static int knob_pull_fused()
     return v;
 }
 
-int fused_flush(State* s)
+int fused_flush(State* s, CarryReq* carry)
 {
     if (s->queue.empty()) {
         return s->pullPending ? launch_pull_gather(s) : B200SV_OK;
@@ -2398,36 +2512,24 @@ int fused_flush(State* s)
         return B200SV_OK;
     }
     std::vector<HostOp> pending;
-    const uint64_t xtail = lower_queue(s->queue, pending);
+    uint64_t xtail = lower_queue(s->queue, pending);
     const size_t nGates = s->queue.size();
     const TileCfg cfg = state_cfg(s->nq, s->prec, flush_is_light(pending));
+    // build every sweep of this flush (nothing is launched before the whole flush is planned: a planner failure leaves the state as it was)
+    std::vector<unsigned char> buf;
+    std::vector<Seg> segs;
+    SV_TRY(plan_all(pending, cfg, s->prec, buf, segs, carry, &xtail));
+    s->queue.clear();
     // A pending re-page rides on the first sweep when there is one (RB = 4 instantiations only); otherwise it is a plain gather.
-    if (s->pullPending && (pending.empty() || cfg.RB != 4 || !knob_pull_fused())) {
+    if (s->pullPending && (segs.empty() || cfg.RB != 4 || !knob_pull_fused())) {
         SV_TRY(launch_pull_gather(s));
     }
-    s->queue.clear();
-    if (pending.empty()) {
+    if (segs.empty()) {
         return xtail ? launch_xmask(s, xtail) : B200SV_OK;
     }
     Arena* ar = get_arena(s);
     if (!ar->done) {
         SV_CUDA(cudaEventCreateWithFlags(&ar->done, cudaEventDisableTiming));
-    }
-    // build every sweep of this flush
-    std::vector<unsigned char> buf;
-    struct Seg {
-        size_t off, bytes, scratch;
-    };
-    std::vector<Seg> segs;
-    while (!pending.empty()) {
-        const size_t off = buf.size();
-        size_t bytes = 0, scratch = 0, nops = 0;
-        int npass = 0;
-        SV_TRY(plan_and_encode(pending, cfg, s->prec, buf, &bytes, &scratch, &nops, &npass));
-        segs.push_back({ off, bytes, scratch });
-        if (getenv("B200SV_FUSED_DEBUG")) {
-            fprintf(stderr, "  program %zu B + scratch %zu B\n", bytes, scratch);
-        }
     }
     const uint64_t nTiles = s->dim() >> cfg.kA;
     if (ar->pending) {
@@ -2790,13 +2892,18 @@ static void emulate_sweep(const unsigned char* prog, EmuC<R>* psi, int nq, const
     }
 }
 
-int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state, const PullArgs* pull)
+int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state, const PullArgs* pull, CarryReq* carry)
 {
     std::vector<HostOp> pending;
-    const uint64_t xtail = lower_queue(q, pending);
+    uint64_t xtail = lower_queue(q, pending);
     const TileCfg cfg = state_cfg(n_qubits, precision, flush_is_light(pending));
     std::vector<unsigned char> buf;
-    if (pull && (pending.empty() || cfg.RB != 4 || !knob_pull_fused())) { // launch_pull_gather on the device
+    std::vector<Seg> segs;
+    SV_TRY(plan_all(pending, cfg, precision, buf, segs, carry, &xtail));
+    if (!host_state) { // plan only (scripts/shard_sweep_count.py)
+        return B200SV_OK;
+    }
+    if (pull && (segs.empty() || cfg.RB != 4 || !knob_pull_fused())) { // launch_pull_gather on the device
         const uint64_t dim = 1ULL << n_qubits;
         for (uint64_t i = 0; i < dim; ++i) {
             if (precision == 32) {
@@ -2807,15 +2914,11 @@ int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, voi
         }
         pull = nullptr;
     }
-    while (!pending.empty()) {
-        size_t bytes = 0, scratch = 0, nops = 0;
-        int npass = 0;
-        buf.clear();
-        SV_TRY(plan_and_encode(pending, cfg, precision, buf, &bytes, &scratch, &nops, &npass));
+    for (const Seg& sg : segs) {
         if (precision == 32) {
-            emulate_sweep<float>(buf.data(), reinterpret_cast<EmuC<float>*>(host_state), n_qubits, cfg, pull);
+            emulate_sweep<float>(buf.data() + sg.off, reinterpret_cast<EmuC<float>*>(host_state), n_qubits, cfg, pull);
         } else {
-            emulate_sweep<double>(buf.data(), reinterpret_cast<EmuC<double>*>(host_state), n_qubits, cfg, pull);
+            emulate_sweep<double>(buf.data() + sg.off, reinterpret_cast<EmuC<double>*>(host_state), n_qubits, cfg, pull);
         }
         pull = nullptr; // only the first sweep carries the re-page
     }

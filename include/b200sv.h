@@ -165,6 +165,12 @@ int b200sv_exchange_pull(b200sv_t s, int k, const int* victim_bits, int rank, vo
 
 /* ---- queue / fusion control ---- */
 int b200sv_flush(b200sv_t s);  /* launch everything queued; does not wait */
+/* Rank bits of a sharded register as VIRTUAL qubits n_qubits .. n_qubits+k-1 of this page's engine: index bits the page does not
+ * hold, with the constant value `rank` here.  Gates passed to b200sv_apply_gates may then use them as controls, and diagonal
+ * gates as their own qubit; the predicate is folded when a sweep is encoded (an op that cannot fire on this rank emits nothing),
+ * and what b200sv_flush_carry hands back keeps them — so that it stays valid after an exchange has turned them into real qubits
+ * of the page (a gate specialised for this rank by the caller would not).  k = 0 switches them off. */
+int b200sv_set_rank_bits(b200sv_t s, int k, uint64_t rank);
 /* b200sv_flush that leaves the under-filled TAIL of the window un-executed: trailing fused sweeps that would hold fewer than
  * `min_ops` lowered ops are not launched; everything not executed is handed back, in program order, as single-target gates in
  * the layout of b200sv_apply_gates (n_out <= cap of them) for the caller to submit again later — e.g. after a page exchange,
@@ -226,7 +232,8 @@ int b200sv_plan_gates(int n_qubits, int precision, int n_gates, const uint64_t* 
  * *n_sweeps = sweeps that ran */
 int b200sv_emulate_fused_carry(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,
     const uint64_t* pmasks, const double* mats8, void* host_state, int min_ops, uint64_t must_mask, int cap, int* n_out,
-    uint64_t* out_off1, uint64_t* out_off2, uint64_t* out_pmasks, double* out_mats8, int* n_sweeps);
+    uint64_t* out_off1, uint64_t* out_off2, uint64_t* out_pmasks, double* out_mats8, int* n_sweeps, int n_virtual,
+    uint64_t rank);
 /* TEST HOOK (host only): the same with a pending b200sv_exchange_pull — src_states[r] are HOST arrays standing in for the
  * ranks' pages, out_state receives this rank's new page after the gates (first sweep reads through the pull mapping). */
 int b200sv_emulate_fused_pull(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,

@@ -1350,8 +1350,60 @@ static int launch_apply2x2(State* s, uint64_t off1, uint64_t off2, const double*
     double* normOutDev);
 
 // A queued gate back in its (offset1, offset2, powers) form on the generic kernel
-static int run_gate_unfused(State* s, const GateOp& g)
+// Gates may name "virtual" qubits >= nq (b200sv_set_rank_bits), constant on this state: strip them.  Returns false when the gate
+// never fires here.  A diagonal gate whose own qubit is virtual leaves one diagonal entry d: a phase on its last real control
+// under the others, or a global scalar.
+static bool fold_virtual(const State* s, GateOp& g)
 {
+    if (!s->nVirt) {
+        return true;
+    }
+    const uint64_t vm = ((1ULL << s->nVirt) - 1ULL) << s->nq;
+    if (g.cmask & vm) {
+        if ((g.cval & g.cmask & vm) != (s->virtVal & g.cmask & vm)) {
+            return false;
+        }
+        g.cmask &= ~vm;
+        g.cval &= ~vm;
+    }
+    if (g.target >= s->nq) {
+        const bool one = ((s->virtVal >> g.target) & 1ULL) != 0;
+        const double dx = one ? g.m[6] : g.m[0], dy = one ? g.m[7] : g.m[1];
+        if (dx == 1.0 && dy == 0.0) {
+            return false;
+        }
+        memset(g.m, 0, sizeof(g.m));
+        if (g.cmask) {
+            const int c = 63 - __builtin_clzll(g.cmask);
+            const bool want = ((g.cval >> c) & 1ULL) != 0;
+            g.cmask &= ~(1ULL << c);
+            g.cval &= ~(1ULL << c);
+            g.target = c;
+            if (want) {
+                g.m[0] = 1.0;
+                g.m[6] = dx;
+                g.m[7] = dy;
+            } else {
+                g.m[0] = dx;
+                g.m[1] = dy;
+                g.m[6] = 1.0;
+            }
+        } else {
+            g.target = 0;
+            g.m[0] = g.m[6] = dx;
+            g.m[1] = g.m[7] = dy;
+        }
+        g.kind = 1;
+    }
+    return true;
+}
+
+static int run_gate_unfused(State* s, const GateOp& gin)
+{
+    GateOp g = gin;
+    if (!fold_virtual(s, g)) {
+        return B200SV_OK;
+    }
     uint64_t pows[64];
     int nb = 0;
     const uint64_t pmask = g.cmask | (1ULL << g.target);
@@ -2399,7 +2451,11 @@ int b200sv_apply_gates(b200sv_t s, int n_gates, const uint64_t* off1, const uint
     const uint64_t dim = s->dim();
     for (int i = 0; i < n_gates; ++i) {
         const uint64_t diff = off1[i] ^ off2[i];
-        if (!diff || (diff & (diff - 1U)) || pmasks[i] >= dim || ((off1[i] | off2[i]) & ~pmasks[i])) {
+        // controls (and the qubit of a DIAGONAL gate) may be virtual qubits when the state has them (b200sv_set_rank_bits)
+        const bool diagonal = mats8[8 * (size_t)i + 2] == 0 && mats8[8 * (size_t)i + 3] == 0 && mats8[8 * (size_t)i + 4] == 0 &&
+            mats8[8 * (size_t)i + 5] == 0;
+        if (!diff || (diff & (diff - 1U)) || (pmasks[i] >> (s->nq + s->nVirt)) || ((off1[i] | off2[i]) & ~pmasks[i]) ||
+            (diff >= dim && !diagonal)) {
             return einval("apply_gates: every gate must be a single-target Apply2x2 form within the qubit bounds");
         }
     }
@@ -2419,17 +2475,20 @@ int b200sv_apply_gates(b200sv_t s, int n_gates, const uint64_t* off1, const uint
         }
         // unfused engines (tiny registers, fusion switched off): the generic kernel, gate by gate
         SV_TRY(flush_queue(s));
-        uint64_t pows[64];
-        int nb = 0;
-        for (uint64_t m = pmasks[i]; m; m &= m - 1U) {
-            pows[nb++] = m & (~m + 1U);
-        }
-        if (s->prec == 32) {
-            SV_TRY(launch_apply2x2<float>(s, off1[i], off2[i], mats8 + 8 * (size_t)i, nb, pows, 1.0, 0.0, nullptr));
-        } else {
-            SV_TRY(launch_apply2x2<double>(s, off1[i], off2[i], mats8 + 8 * (size_t)i, nb, pows, 1.0, 0.0, nullptr));
-        }
+        SV_TRY(run_gate_unfused(s, g));
     }
+    return B200SV_OK;
+}
+
+int b200sv_set_rank_bits(b200sv_t s, int k, uint64_t rank)
+{
+    SV_ENTER(s);
+    if (k < 0 || k > 16 || s->nq + k > 62 || (k < 64 && (rank >> k))) {
+        return einval("set_rank_bits: 0 <= k <= 16, rank < 2^k, nq + k <= 62");
+    }
+    SV_TRY(flush_queue(s)); // what is queued was submitted under the old rank bits
+    s->nVirt = k;
+    s->virtVal = rank << s->nq;
     return B200SV_OK;
 }
 
@@ -3502,17 +3561,18 @@ int b200sv_emulate_fused(int n_qubits, int precision, int n_gates, const uint64_
 
 int b200sv_emulate_fused_carry(int n_qubits, int precision, int n_gates, const uint64_t* off1, const uint64_t* off2,
     const uint64_t* pmasks, const double* mats8, void* host_state, int min_ops, uint64_t must_mask, int cap, int* n_out,
-    uint64_t* out_off1, uint64_t* out_off2, uint64_t* out_pmasks, double* out_mats8, int* n_sweeps)
+    uint64_t* out_off1, uint64_t* out_off2, uint64_t* out_pmasks, double* out_mats8, int* n_sweeps, int n_virtual, uint64_t rank)
 {
     if (n_gates < 0 || (n_gates && (!off1 || !off2 || !pmasks || !mats8)) || (precision != 32 && precision != 64) || n_qubits < 5 ||
         n_qubits > 62 || (host_state && n_qubits > 30) || min_ops < 0 || cap < 0 || !n_out ||
-        (cap && (!out_off1 || !out_off2 || !out_pmasks || !out_mats8))) {
+        (cap && (!out_off1 || !out_off2 || !out_pmasks || !out_mats8)) || n_virtual < 0 || n_virtual > 16 || n_qubits + n_virtual > 62 ||
+        (rank >> n_virtual)) {
         return einval("emulate_fused_carry: bad arguments");
     }
     std::vector<GateOp> q((size_t)n_gates);
     for (int i = 0; i < n_gates; ++i) {
         const uint64_t diff = off1[i] ^ off2[i];
-        if (!diff || (diff & (diff - 1U)) || (pmasks[i] >> n_qubits) || ((off1[i] | off2[i]) & ~pmasks[i])) {
+        if (!diff || (diff & (diff - 1U)) || (pmasks[i] >> (n_qubits + n_virtual)) || ((off1[i] | off2[i]) & ~pmasks[i])) {
             return einval("emulate_fused_carry: not a single-target gate");
         }
         make_gate_op(precision, off1[i], off2[i], pmasks[i], mats8 + 8 * (size_t)i, 1.0, q[(size_t)i]);
@@ -3521,7 +3581,7 @@ int b200sv_emulate_fused_carry(int n_qubits, int precision, int n_gates, const u
     c.minOps = (size_t)min_ops;
     c.mustMask = must_mask;
     c.cap = (size_t)cap;
-    SV_TRY(fused_emulate(n_qubits, precision, q, host_state, nullptr, &c));
+    SV_TRY(fused_emulate(n_qubits, precision, q, host_state, nullptr, &c, n_virtual, rank << n_qubits));
     if (n_sweeps) {
         *n_sweeps = c.sweepsLaunched;
     }

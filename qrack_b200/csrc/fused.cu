@@ -1296,6 +1296,8 @@ struct TileCfg {
     int NT;   // threads per CTA
     int maxOps; // ops per sweep (bounded by the shared-memory program area: 3 CTAs/SM must fit)
     int bundle; // bit 0: merge Hadamards on distinct register bits into one LAYER op
+    // virtual qubits (>= n, State::nVirt): constant on this state; predicates on them are folded when the sweep is encoded
+    uint64_t virtMask = 0, virtVal = 0;
 };
 
 static TileCfg make_cfg(int n, int prec, int KC, int RB, int Lpref, int NT = 256)
@@ -1847,7 +1849,17 @@ static size_t encode_sweep(const SweepPlan& sp, const TileCfg& cfg, std::vector<
             stage_reset();
         };
         dp.opBegin = (int)dops.size();
-        for (const HostOp& hop : pp.ops) {
+        for (const HostOp& hopSym : pp.ops) {
+            // fold the predicate on virtual qubits (rank bits of a sharded register: constant here): the op either never fires on
+            // this state — nothing is emitted — or loses those bits
+            HostOp hop = hopSym;
+            if (hop.cmask & cfg.virtMask) {
+                if ((hop.cval & hop.cmask & cfg.virtMask) != (cfg.virtVal & hop.cmask & cfg.virtMask)) {
+                    continue;
+                }
+                hop.cmask &= ~cfg.virtMask;
+                hop.cval &= ~cfg.virtMask;
+            }
             uint32_t lmask, lval;
             local_pred(hop, lmask, lval);
             const uint32_t lmr = lmask & regAmpMask, lvr = lval & regAmpMask;
@@ -2228,26 +2240,64 @@ static int plan_all(std::vector<HostOp>& pending, const TileCfg& cfg, int prec, 
         }
     }
     if (carry && carry->minOps && !segs.empty()) {
-        size_t cut = segs.size();
-        while (cut > 0) {
-            const size_t j = cut - 1;
-            if (segs[j].nops >= carry->minOps || snaps[j].size() + 64 > carry->cap) {
-                break;
-            }
-            bool ok = true;
-            for (const HostOp& h : snaps[j]) {
-                if (h.tq >= 0 && ((carry->mustMask >> h.tq) & 1ULL)) {
-                    ok = false;
-                    break;
+        // Candidate cuts: j = first sweep of a trailing run of sweeps that each hold fewer than minOps ops.  Of what is left over at
+        // cut j (snaps[j], program order) the ops that MUST still run now are the non-diagonal ops on mustMask qubits together with
+        // every earlier left-over op that does not commute with one of them (backward closure under the scheduler's conflict rule:
+        // shared qubits must be used diagonally by both).  They are planned again on their own; everything else is handed back.  The
+        // cut with the fewest sweeps in total wins (ties: the latest cut = fewest ops handed back).
+        size_t firstSmall = segs.size();
+        if (*xtail & carry->mustMask) {
+            firstSmall = 0; // (a trailing X on a must-qubit: nothing may be handed back — the loops below then do nothing)
+        }
+        while ((*xtail & carry->mustMask) == 0 && firstSmall > 0 && segs[firstSmall - 1].nops < carry->minOps) {
+            --firstSmall;
+        }
+        size_t bestCut = segs.size(), bestTotal = segs.size();
+        std::vector<unsigned char> bestBuf;
+        std::vector<Seg> bestSegs;
+        std::vector<HostOp> bestCarried;
+        for (size_t j = segs.size(); (*xtail & carry->mustMask) == 0 && j-- > firstSmall;) {
+            const std::vector<HostOp>& left = snaps[j];
+            std::vector<char> must(left.size(), 0);
+            uint64_t mT = 0, mD = 0;
+            size_t nMust = 0;
+            for (size_t i = left.size(); i-- > 0;) {
+                const HostOp& h = left[i];
+                const uint64_t usesT = h.tq >= 0 ? bitq(h.tq) : 0;
+                const uint64_t usesD = h.cmask;
+                if ((usesT & carry->mustMask) || (usesT & (mT | mD)) || (usesD & mT)) {
+                    must[i] = 1;
+                    mT |= usesT;
+                    mD |= usesD;
+                    ++nMust;
                 }
             }
-            if (!ok) {
-                break;
+            if (left.size() - nMust + 64 > carry->cap) {
+                continue;
             }
-            cut = j;
+            std::vector<HostOp> mustOps, carried;
+            for (size_t i = 0; i < left.size(); ++i) {
+                (must[i] ? mustOps : carried).push_back(left[i]);
+            }
+            std::vector<unsigned char> mbuf;
+            std::vector<Seg> msegs;
+            if (!mustOps.empty()) {
+                uint64_t noX = 0;
+                if (plan_all(mustOps, cfg, prec, mbuf, msegs, nullptr, &noX) != B200SV_OK) {
+                    continue;
+                }
+            }
+            const size_t total = j + msegs.size();
+            if (total < bestTotal) {
+                bestTotal = total;
+                bestCut = j;
+                bestBuf.swap(mbuf);
+                bestSegs.swap(msegs);
+                bestCarried.swap(carried);
+            }
         }
-        if (cut < segs.size()) {
-            for (const HostOp& h : snaps[cut]) {
+        if (bestCut < segs.size()) {
+            for (const HostOp& h : bestCarried) {
                 export_op(h, carry);
             }
             for (uint64_t m = *xtail; m; m &= m - 1ULL) { // the trailing XMask follows the carried ops
@@ -2259,8 +2309,15 @@ static int plan_all(std::vector<HostOp>& pending, const TileCfg& cfg, int prec, 
                 export_op(x, carry);
             }
             *xtail = 0;
-            buf.resize(segs[cut].off);
-            segs.resize(cut);
+            buf.resize(segs[bestCut].off);
+            segs.resize(bestCut);
+            // the re-planned must-ops follow: their programs are appended (offsets stay 16-byte aligned: every program is)
+            for (const Seg& ms : bestSegs) {
+                Seg t = ms;
+                t.off = buf.size() + (ms.off - bestSegs.front().off);
+                segs.push_back(t);
+            }
+            buf.insert(buf.end(), bestBuf.begin(), bestBuf.end());
         }
     }
     if (carry) {
@@ -2514,7 +2571,9 @@ int fused_flush(State* s, CarryReq* carry)
     std::vector<HostOp> pending;
     uint64_t xtail = lower_queue(s->queue, pending);
     const size_t nGates = s->queue.size();
-    const TileCfg cfg = state_cfg(s->nq, s->prec, flush_is_light(pending));
+    TileCfg cfg = state_cfg(s->nq, s->prec, flush_is_light(pending));
+    cfg.virtMask = s->nVirt ? (((1ULL << s->nVirt) - 1ULL) << s->nq) : 0ULL;
+    cfg.virtVal = s->virtVal;
     // build every sweep of this flush (nothing is launched before the whole flush is planned: a planner failure leaves the state as it was)
     std::vector<unsigned char> buf;
     std::vector<Seg> segs;
@@ -2892,11 +2951,14 @@ static void emulate_sweep(const unsigned char* prog, EmuC<R>* psi, int nq, const
     }
 }
 
-int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state, const PullArgs* pull, CarryReq* carry)
+int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state, const PullArgs* pull, CarryReq* carry,
+    int n_virtual, uint64_t virt_value)
 {
     std::vector<HostOp> pending;
     uint64_t xtail = lower_queue(q, pending);
-    const TileCfg cfg = state_cfg(n_qubits, precision, flush_is_light(pending));
+    TileCfg cfg = state_cfg(n_qubits, precision, flush_is_light(pending));
+    cfg.virtMask = n_virtual ? (((1ULL << n_virtual) - 1ULL) << n_qubits) : 0ULL;
+    cfg.virtVal = virt_value;
     std::vector<unsigned char> buf;
     std::vector<Seg> segs;
     SV_TRY(plan_all(pending, cfg, precision, buf, segs, carry, &xtail));

@@ -109,6 +109,11 @@ struct State {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx = nullptr;
     int fusion = 1;
     std::vector<GateOp> queue;
+    // "virtual" qubits nq .. nq+nVirt-1 (b200sv_set_rank_bits): index bits this page does not hold — the rank index of a sharded
+    // register — with a constant value on this state.  Queued gates may use them as controls / phased qubits; the predicate is
+    // folded when a sweep is encoded (or a gate runs unfused), and ops handed back by b200sv_flush_carry keep them.
+    int nVirt = 0;
+    uint64_t virtVal = 0; // already shifted to bit nq
     bool pullPending = false; // see PullArgs
     PullArgs pull{};
     b200sv_stats stats{};
@@ -159,7 +164,7 @@ bool fused_accepts(const State* s, const GateOp& g);
 void fused_release(State* s);
 int launch_pull_gather(State* s); // the pending pull as a plain gather kernel (b200sv.cu); adopts the out page
 int fused_emulate(int n_qubits, int precision, const std::vector<GateOp>& q, void* host_state, const PullArgs* pull = nullptr,
-    CarryReq* carry = nullptr);
+    CarryReq* carry = nullptr, int n_virtual = 0, uint64_t virt_value = 0);
 int fused_plan_gates(int n_qubits, int precision, const std::vector<GateOp>& q, int* n_sweeps, int* n_passes, int* n_ops);
 int fused_plan_dry_run(int n_qubits, int precision, int n_gates, const int* targets, const uint64_t* cmasks, const int* kinds,
     int* n_sweeps, int* n_passes);

@@ -356,6 +356,7 @@ def main():
     sampler.start()
     ms_steps = []
     ex0 = q.be.exchanges if sharded else 0
+    car0 = getattr(q.be, "carried_ops", 0) if sharded else 0
     stats0 = get_stats()
     if not sharded:
         q.be.reset_stats()
@@ -382,6 +383,7 @@ def main():
     stats1 = get_stats()
     stats = {k: stats1[k] - stats0.get(k, 0) for k in stats1}
     exchanges = (q.be.exchanges - ex0) if sharded else 0
+    carried = (getattr(q.be, "carried_ops", 0) - car0) if sharded else 0
     # ---- end-to-end arm: public API, host submission + init + result read inside the timed region -----------
     h2d = gates * (8 * 8 + 8 * 4)  # per gate: 8 doubles of matrix + offsets/powers words crossing the C ABI
     d2h = n * 8
@@ -494,7 +496,10 @@ def main():
                                 "sweeps_per_step": stats["fused_sweeps"] / max(1, args.steps),
                                 # exchanges carried by the first sweep of the next window (b200sv_exchange_pull) instead of a pass of their own
                                 "pull_sweeps_per_step": stats.get("pull_sweeps", 0) / max(1, args.steps),
-                                "exchange_mode": "pull (fused into the next sweep)" if stats.get("pull_sweeps", 0) else "push kernel"}
+                                "exchange_mode": "pull (fused into the next sweep)" if stats.get("pull_sweeps", 0) else "push kernel",
+                                # lowered ops the local engine handed back instead of running them in a nearly empty last sweep of a window
+                                # (b200sv_flush_carry); they ran at the head of the next window
+                                "ops_carried_across_exchanges_per_step": carried / max(1, args.steps)}
         if check is not None:
             line["check"] = check
         if e2e_batched is not None:

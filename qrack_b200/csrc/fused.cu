@@ -876,6 +876,7 @@ struct HostOp {
     uint64_t cmask; // predicate mask over qubits (controls; for OP_PHASE includes the phased qubit)
     uint64_t cval;
     double m[8];
+    int id; // position in the lowered list (set by plan_all when it needs to tell ops apart)
 };
 
 static inline uint64_t bitq(int q) { return 1ULL << q; }
@@ -2218,17 +2219,13 @@ static void export_op(const HostOp& h, CarryReq* c)
     c->m8.insert(c->m8.end(), m, m + 8);
 }
 
-// Plans and encodes every sweep of a flush.  With `carry`, the under-filled tail is cut off: the longest run of trailing sweeps that
-// each hold fewer than carry->minOps lowered ops, such that nothing left over is a non-diagonal op on a qubit of carry->mustMask
-// (and the leftovers fit carry->cap), is dropped from `segs` and its ops — everything not executed, in program order, plus a
-// trailing XMask as X gates — are exported instead.  *xtail is cleared when it was exported.
-static int plan_all(std::vector<HostOp>& pending, const TileCfg& cfg, int prec, std::vector<unsigned char>& buf, std::vector<Seg>& segs,
-    CarryReq* carry, uint64_t* xtail)
+// Plans and encodes the sweeps of `pending` (consumed), nothing else.
+static int plan_list(std::vector<HostOp>& pending, const TileCfg& cfg, int prec, std::vector<unsigned char>& buf, std::vector<Seg>& segs,
+    std::vector<std::vector<HostOp>>* snaps)
 {
-    std::vector<std::vector<HostOp>> snaps;
     while (!pending.empty()) {
-        if (carry && carry->minOps) {
-            snaps.push_back(pending);
+        if (snaps) {
+            snaps->push_back(pending);
         }
         const size_t off = buf.size();
         size_t bytes = 0, scratch = 0, nops = 0;
@@ -2239,24 +2236,44 @@ static int plan_all(std::vector<HostOp>& pending, const TileCfg& cfg, int prec, 
             fprintf(stderr, "  program %zu B + scratch %zu B\n", bytes, scratch);
         }
     }
-    if (carry && carry->minOps && !segs.empty()) {
-        // Candidate cuts: j = first sweep of a trailing run of sweeps that each hold fewer than minOps ops.  Of what is left over at
-        // cut j (snaps[j], program order) the ops that MUST still run now are the non-diagonal ops on mustMask qubits together with
-        // every earlier left-over op that does not commute with one of them (backward closure under the scheduler's conflict rule:
-        // shared qubits must be used diagonally by both).  They are planned again on their own; everything else is handed back.  The
-        // cut with the fewest sweeps in total wins (ties: the latest cut = fewest ops handed back).
-        size_t firstSmall = segs.size();
-        if (*xtail & carry->mustMask) {
-            firstSmall = 0; // (a trailing X on a must-qubit: nothing may be handed back — the loops below then do nothing)
+    return B200SV_OK;
+}
+
+// Plans and encodes every sweep of a flush.
+//
+// With `carry` the under-filled tail of the window is not executed.  Phase A decides WHAT is handed back, on the symbolic op list
+// (virtual-qubit predicates unfolded), so that every rank of a sharded register — same queue, same knobs, deterministic planner —
+// takes the same decision: an exchange redistributes amplitudes between the ranks, an op executed before it on one rank and after
+// it on another would hit some amplitudes twice.  Candidate cuts: j = first sweep of a trailing run of sweeps that each hold fewer
+// than minOps ops.  Of what is left over at cut j (program order) the ops that MUST still run now are the non-diagonal ops on
+// mustMask qubits together with every earlier left-over op that does not commute with one of them (backward closure under the
+// scheduler's conflict rule: shared qubits must be used diagonally by both); they are planned on their own, everything else is
+// handed back (plus a trailing XMask as X gates; *xtail is cleared then).  The cut with the fewest sweeps in total wins (ties: the
+// latest cut = fewest ops handed back).  Phase B plans what is executed for THIS state: ops whose virtual-qubit predicate cannot
+// hold here are identities and are dropped, the others lose those bits.
+static int plan_all(std::vector<HostOp>& pending, const TileCfg& cfg, int prec, std::vector<unsigned char>& buf, std::vector<Seg>& segs,
+    CarryReq* carry, uint64_t* xtail)
+{
+    std::vector<HostOp> exec;
+    if (carry && carry->minOps && !pending.empty() && !(*xtail & carry->mustMask)) {
+        TileCfg sym = cfg;
+        sym.virtMask = sym.virtVal = 0;
+        for (size_t i = 0; i < pending.size(); ++i) {
+            pending[i].id = (int)i;
         }
-        while ((*xtail & carry->mustMask) == 0 && firstSmall > 0 && segs[firstSmall - 1].nops < carry->minOps) {
+        std::vector<HostOp> work = pending;
+        std::vector<std::vector<HostOp>> snaps;
+        std::vector<unsigned char> symBuf;
+        std::vector<Seg> symSegs;
+        SV_TRY(plan_list(work, sym, prec, symBuf, symSegs, &snaps));
+        size_t firstSmall = symSegs.size();
+        while (firstSmall > 0 && symSegs[firstSmall - 1].nops < carry->minOps) {
             --firstSmall;
         }
-        size_t bestCut = segs.size(), bestTotal = segs.size();
-        std::vector<unsigned char> bestBuf;
-        std::vector<Seg> bestSegs;
+        size_t bestTotal = symSegs.size();
+        bool found = false;
         std::vector<HostOp> bestCarried;
-        for (size_t j = segs.size(); (*xtail & carry->mustMask) == 0 && j-- > firstSmall;) {
+        for (size_t j = symSegs.size(); j-- > firstSmall;) {
             const std::vector<HostOp>& left = snaps[j];
             std::vector<char> must(left.size(), 0);
             uint64_t mT = 0, mD = 0;
@@ -2281,23 +2298,20 @@ static int plan_all(std::vector<HostOp>& pending, const TileCfg& cfg, int prec, 
             }
             std::vector<unsigned char> mbuf;
             std::vector<Seg> msegs;
-            if (!mustOps.empty()) {
-                uint64_t noX = 0;
-                if (plan_all(mustOps, cfg, prec, mbuf, msegs, nullptr, &noX) != B200SV_OK) {
-                    continue;
-                }
+            if (!mustOps.empty() && plan_list(mustOps, sym, prec, mbuf, msegs, nullptr) != B200SV_OK) {
+                continue;
             }
             const size_t total = j + msegs.size();
             if (total < bestTotal) {
                 bestTotal = total;
-                bestCut = j;
-                bestBuf.swap(mbuf);
-                bestSegs.swap(msegs);
+                found = true;
                 bestCarried.swap(carried);
             }
         }
-        if (bestCut < segs.size()) {
+        if (found) {
+            std::vector<char> gone(pending.size(), 0);
             for (const HostOp& h : bestCarried) {
+                gone[(size_t)h.id] = 1;
                 export_op(h, carry);
             }
             for (uint64_t m = *xtail; m; m &= m - 1ULL) { // the trailing XMask follows the carried ops
@@ -2309,17 +2323,41 @@ static int plan_all(std::vector<HostOp>& pending, const TileCfg& cfg, int prec, 
                 export_op(x, carry);
             }
             *xtail = 0;
-            buf.resize(segs[bestCut].off);
-            segs.resize(bestCut);
-            // the re-planned must-ops follow: their programs are appended (offsets stay 16-byte aligned: every program is)
-            for (const Seg& ms : bestSegs) {
-                Seg t = ms;
-                t.off = buf.size() + (ms.off - bestSegs.front().off);
-                segs.push_back(t);
+            for (size_t i = 0; i < pending.size(); ++i) {
+                if (!gone[i]) {
+                    exec.push_back(pending[i]);
+                }
             }
-            buf.insert(buf.end(), bestBuf.begin(), bestBuf.end());
+        } else {
+            exec.swap(pending);
+        }
+    } else {
+        exec.swap(pending);
+    }
+    pending.clear();
+    if (cfg.virtMask) {
+        size_t w = 0;
+        bool changed = false;
+        for (size_t i = 0; i < exec.size(); ++i) {
+            HostOp h = exec[i];
+            if (h.cmask & cfg.virtMask) {
+                changed = true;
+                if ((h.cval & h.cmask & cfg.virtMask) != (cfg.virtVal & h.cmask & cfg.virtMask)) {
+                    continue; // cannot fire on this state: the identity
+                }
+                h.cmask &= ~cfg.virtMask;
+                h.cval &= ~cfg.virtMask;
+            }
+            exec[w++] = h;
+        }
+        exec.resize(w);
+        if (changed && knob_rewrite()) {
+            // the peephole rules once more on what is left: the Hadamard pair around a controlled-X whose rank-bit control fails here is
+            // H . H now, a CZ that lost its rank-bit control is a Z to absorb, ...
+            *xtail ^= rewrite_ops(exec);
         }
     }
+    SV_TRY(plan_list(exec, cfg, prec, buf, segs, nullptr));
     if (carry) {
         carry->sweepsLaunched = (int)segs.size();
     }

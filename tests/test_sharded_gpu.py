@@ -41,7 +41,8 @@ def _worker(rank, world, port, text, prec, out_path, mode):
         regs, results = qscript.run(text, make)
         st = regs[0].GetQuantumState()
         if rank == 0:
-            np.savez(out_path, state=st, exchanges=regs[0].be.exchanges, pull_sweeps=regs[0].be.shard.stats().get("pull_sweeps", 0))
+            np.savez(out_path, state=st, exchanges=regs[0].be.exchanges, pull_sweeps=regs[0].be.shard.stats().get("pull_sweeps", 0),
+                     carried=regs[0].be.carried_ops)
     finally:
         dist.destroy_process_group()
 
@@ -65,8 +66,10 @@ def test_sharded_nccl_matches_oracle(prec, mode, tmp_path):
                 raise
     z = np.load(out)
     d = float(np.abs(z["state"].astype(np.complex128) - want[0].astype(np.complex128)).max())
-    assert d <= util.AMP_TOL[prec], d
+    assert d <= util.AMP_TOL[prec], (d, "ops carried across exchanges: %d" % int(z["carried"]))
     assert int(z["exchanges"]) >= 1
+    if mode == "nccl":
+        assert int(z["carried"]) == 0         # gates are specialised per rank on this route: nothing may cross an exchange
     if mode == "pull":
         assert int(z["pull_sweeps"]) >= 1     # the re-page really rode on a fused sweep (b200sv_exchange_pull)
     else:

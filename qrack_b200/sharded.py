@@ -161,8 +161,10 @@ class P2PShardBuffers:
         self.live = 0
         self.pull = os.environ.get("B200SV_SHARD_PULL", "1") != "0"  # 0: the push kernel (b200sv_exchange_scatter), one pass per exchange
         self.engine = QEngineCUDA.over_buffer(self.pages[0], n_local, device_index, precision, random.Random(1))
-        # the local engine knows the rank index as constant virtual qubits: gates go to it un-specialised (b200sv_set_rank_bits)
-        self.virtual_rank_bits = os.environ.get("B200SV_SHARD_VIRT", "1") != "0"
+        # B200SV_SHARD_VIRT=1: the local engine knows the rank index as constant virtual qubits and gates go to it un-specialised
+        # (b200sv_set_rank_bits) — the precondition of the tail carry (B200SV_SHARD_CARRY).  Off by default: measured on 2 B200s the
+        # carry removes the nearly empty sweeps (39 -> 35 per step) but not time (323.6 vs 319.9 ms, profiles/r2j_tail_carry_2gpu.jsonl)
+        self.virtual_rank_bits = os.environ.get("B200SV_SHARD_VIRT", "0") != "0"
         if self.virtual_rank_bits:
             self.engine.be.set_rank_bits(world.bit_length() - 1, rank)
         self.engine.be.set_stream(torch.cuda.current_stream(self.device).cuda_stream)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# r2 GPU call J (gpurun --gpus N): tail carry across exchanges (b200sv_flush_carry + rank bits as virtual qubits) on/off, same box, back to back,
+# r2 GPU call J (gpurun --gpus N; the run of r2 had VIRT on by default, it is opt-in now): tail carry across exchanges (b200sv_flush_carry + rank bits as virtual qubits) on/off, same box, back to back,
 # after the sharded parity tests (which run with the defaults: pull-mode exchange, carry on)
 set -u
 N=${N:-2}
@@ -21,8 +21,8 @@ for l in sys.stdin:
     print('$name N=$N', '%s=%.0f ms/step=%.1f e2e=%.0f'%(j['unit'],j['value'],j['ms_per_step'],j['e2e']['value']), 'sharding=',j.get('sharding'), 'check=',(j.get('check') or {}).get('ok')); j['run']='$name'; open('gpurun_out/carry_$N.jsonl','a').write(json.dumps(j)+'\n')"
   tail -2 gpurun_out/bench_${name}_$N.err
 }
-bench htcnot_carry B200SV_SHARD_CARRY=1000000 --steps 3 --warmup 3
-bench htcnot_nocarry B200SV_SHARD_CARRY=0 --steps 3 --warmup 3 --skip-check
-bench qv_carry B200SV_SHARD_CARRY=1000000 --steps 2 --warmup 3 --workload qv
-[ "${QVOFF:-1}" = "1" ] && bench qv_nocarry B200SV_SHARD_CARRY=0 --steps 2 --warmup 3 --workload qv --skip-check
+bench htcnot_carry "B200SV_SHARD_VIRT=1 B200SV_SHARD_CARRY=1000000" --steps 3 --warmup 3
+bench htcnot_nocarry "B200SV_SHARD_VIRT=1 B200SV_SHARD_CARRY=0" --steps 3 --warmup 3 --skip-check
+bench qv_carry "B200SV_SHARD_VIRT=1 B200SV_SHARD_CARRY=1000000" --steps 2 --warmup 3 --workload qv
+[ "${QVOFF:-1}" = "1" ] && bench qv_nocarry "B200SV_SHARD_VIRT=1 B200SV_SHARD_CARRY=0" --steps 2 --warmup 3 --workload qv --skip-check
 echo "== done"

@@ -108,7 +108,7 @@ def algorithmic_bytes(calls, n, amp_bytes):
 def committed_traffic(kernel_bytes_per_launch):
     """dram__bytes_read+write per launch of the fused sweep from the newest committed `ncu --set full` summary under
     profiles/ (a 28-qubit capture), scaled to this run's state size.  NOT measured in this run — labelled as such."""
-    for fn in ("r2_fused_ncu_full.json", "r1_fused_v9_ncu_full.json"):
+    for fn in ("r2_final_fused_ncu_full.json", "r2_fused_ncu_full.json", "r1_fused_v9_ncu_full.json"):
         p = os.path.join(ROOT, "profiles", fn)
         try:
             j = json.load(open(p))

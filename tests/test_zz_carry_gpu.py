@@ -1,6 +1,7 @@
 """GPU test (sorted last on purpose: the newest entry points, after the established suites) of b200sv_set_rank_bits (the rank index as
 constant virtual qubits) and b200sv_flush_carry (the under-filled tail of a window is handed back) on one device; the check body is
 shared with the host-interpreter test (tests/carry_checks.py)."""
+import random
 
 import pytest
 

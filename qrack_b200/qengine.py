@@ -81,17 +81,26 @@ class QEngineHost:
 
     def _c(self, z) -> complex:
         """round a python complex to the engine's complex type (what `complex(real1, real1)` does in the reference)"""
-        return complex(self.cplx(z))
+        try:
+            return self._memo("c", z, lambda: complex(self.cplx(z)))
+        except TypeError:
+            return complex(self.cplx(z))
 
     def _r(self, x) -> float:
-        return float(self.real(x))
+        try:
+            return self._memo("r", x, lambda: float(self.real(x)))
+        except TypeError:
+            return float(self.real(x))
 
     def _norm(self, z) -> float:
         z = self.cplx(z)
         return float(self.real(z.real) * self.real(z.real) + self.real(z.imag) * self.real(z.imag))
 
     def _is_norm_0(self, z) -> bool:  # IS_NORM_0, qrack_types.hpp:28
-        return self._norm(z) <= self.FP_NORM_EPSILON
+        try:
+            return self._memo("n", z, lambda: self._norm(z) <= self.FP_NORM_EPSILON)
+        except TypeError:
+            return self._norm(z) <= self.FP_NORM_EPSILON
 
     def GetNonunitaryPhase(self) -> complex:  # qinterface.hpp:169-177
         if self.randGlobalPhase:
@@ -107,21 +116,43 @@ class QEngineHost:
         if q < 0 or q >= self.qubitCount:
             raise ValueError("%s qubit index parameter must be within allocated qubit bounds!" % what)
 
+    # A circuit applies the same few matrices (H, T, X, ...) thousands of times; rounding them to the engine's complex type and
+    # classifying them goes through numpy scalars (~1 us each), which is most of the per-gate cost of this mirror.  The results are
+    # pure functions of the entries, so they are memoised per engine (the table is dropped when it grows: random-angle circuits).
+    _MEMO_CAP = 4096
+
+    def _memo(self, kind, key, fn):
+        tab = self.__dict__.setdefault("_mtrx_memo", {})
+        k = (kind, key)
+        v = tab.get(k)
+        if v is None:
+            if len(tab) >= self._MEMO_CAP:
+                tab.clear()
+            v = tab[k] = fn()
+        return v
+
     def _mtrx(self, m) -> List[complex]:
-        return [self._c(x) for x in m]
+        try:
+            key = tuple(m)
+            return list(self._memo("m", key, lambda: tuple(self._c(x) for x in key)))
+        except TypeError:  # unhashable entries: no memo
+            return [self._c(x) for x in m]
 
     def IsPhase(self, m) -> bool:
-        return self._is_norm_0(m[1]) and self._is_norm_0(m[2])
+        return self._memo("p", (m[1], m[2]), lambda: self._is_norm_0(m[1]) and self._is_norm_0(m[2]))
 
     def IsInvert(self, m) -> bool:
-        return self._is_norm_0(m[0]) and self._is_norm_0(m[3])
+        return self._memo("i", (m[0], m[3]), lambda: self._is_norm_0(m[0]) and self._is_norm_0(m[3]))
 
-    def IsIdentity(self, m, isControlled: bool) -> bool:  # qengine.hpp:46-67
+    def _is_identity(self, m, isControlled: bool) -> bool:
         if not self._is_norm_0(self._c(m[0] - m[3])) or not self.IsPhase(m):
             return False
         if (isControlled or not self.randGlobalPhase) and not self._is_norm_0(self._c(1.0 - m[0])):
             return False
         return True
+
+    def IsIdentity(self, m, isControlled: bool) -> bool:  # qengine.hpp:46-67
+        return self._memo("d", (m[0], m[1], m[2], m[3], bool(isControlled), bool(self.randGlobalPhase)), lambda: self._is_identity(m, isControlled))
 
     # ---- the engine-level virtuals (reference qengine.hpp) ----------------------------------------------------------
     def Finish(self):
@@ -1331,11 +1362,22 @@ class _CudaBackend:
 
     def apply2x2(self, off1, off2, mtrx, pows, nrm, thresh, calc_norm):
         import ctypes
-        m8 = (ctypes.c_double * 8)()
-        for k in range(4):
-            m8[2 * k] = mtrx[k].real
-            m8[2 * k + 1] = mtrx[k].imag
-        pw = (ctypes.c_uint64 * max(len(pows), 1))(*pows)
+        # the marshalled matrix / power arrays are read-only on the C side and repeat thousands of times per circuit: keep them
+        cache = self.__dict__.setdefault("_marshal_cache", {})
+        if len(cache) > 8192:
+            cache.clear()
+        mk = ("m", mtrx[0], mtrx[1], mtrx[2], mtrx[3])
+        m8 = cache.get(mk)
+        if m8 is None:
+            m8 = (ctypes.c_double * 8)()
+            for k in range(4):
+                m8[2 * k] = mtrx[k].real
+                m8[2 * k + 1] = mtrx[k].imag
+            cache[mk] = m8
+        pk = ("p",) + tuple(pows)
+        pw = cache.get(pk)
+        if pw is None:
+            pw = cache[pk] = (ctypes.c_uint64 * max(len(pows), 1))(*pows)
         if calc_norm:
             out = ctypes.c_double()
             self._ck(self.lib.b200sv_apply2x2(self.h, off1, off2, m8, len(pows), pw, nrm, thresh, ctypes.byref(out)))

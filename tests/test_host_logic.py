@@ -222,3 +222,50 @@ def test_qcircuit_records_the_dispatch_and_replays_it():
         c.Prob(0)                      # state access is an engine call, not a circuit element
     with pytest.raises(ValueError):
         c.Run(QEngineRestate(n + 1, 0, random.Random(1), 1.0 + 0j, False, False, precision=32))
+
+
+def test_cuda_backend_marshalling_with_a_fake_library():
+    """_CudaBackend.apply2x2 (every gate of the GPU tests and of bench.py goes through it) against a stand-in library: argument
+    order, matrix / power arrays, the cached arrays on repeated gates, the norm read-back.  No device, no libb200sv call."""
+    from qrack_b200.qengine import _CudaBackend
+    be = object.__new__(_CudaBackend)
+    calls = []
+
+    class Lib:
+        def b200sv_apply2x2(self, h, o1, o2, m8, n, pw, nrm, th, out):
+            calls.append((h, o1, o2, list(m8), n, list(pw)[:n], nrm, th))
+            if out is not None:
+                out._obj.value = 0.75
+            return 0
+    be.lib, be.h = Lib(), 123
+    be._ck = lambda rc: None
+    s = 2 ** -0.5
+    had = [complex(s), complex(s), complex(s), complex(-s)]
+    for _ in range(2):
+        assert be.apply2x2(0, 4, had, [4], 1.0, 0.0, False) is None
+        assert be.apply2x2(1, 5, [0j, 1 + 0j, 1 + 0j, 0j], [1, 4], 1.0, 0.0, False) is None
+    assert abs(be.apply2x2(0, 2, [1 + 0j, 0j, 0j, 1j], [2], 0.5, 1e-9, True) - 0.75) < 1e-12
+    assert calls[0] == (123, 0, 4, [s, 0, s, 0, s, 0, -s, 0], 1, [4], 1.0, 0.0)
+    assert calls[1] == (123, 1, 5, [0, 0, 1, 0, 1, 0, 0, 0], 2, [1, 4], 1.0, 0.0)
+    assert calls[2] == calls[0] and calls[3] == calls[1]
+    assert calls[4][3] == [1, 0, 0, 0, 0, 0, 0, 1] and calls[4][6] == 0.5 and calls[4][7] == 1e-9
+
+
+def test_matrix_memo_keeps_the_dispatch_semantics():
+    """the memoised rounding / classification of gate matrices (QEngineHost._mtrx, IsIdentity, IsPhase, IsInvert) returns what the
+    direct computation returns, for both precisions, and hands out fresh lists"""
+    import cmath
+    for prec in (32, 64):
+        q = QEngineRestate(3, 0, random.Random(1), 1.0 + 0j, False, False, precision=prec)
+        mats = [[1, 0, 0, 1], [1, 0, 0, -1], [0, 1, 1, 0], [2 ** -0.5] * 3 + [-(2 ** -0.5)], [1, 0, 0, cmath.exp(0.25j * cmath.pi)],
+                [0.6, 0.8j, 0.8j, 0.6], [1 + 1e-9, 0, 0, 1], [1, 1e-12, 0, 1]]
+        for m in mats * 2:
+            got = q._mtrx(m)
+            assert got == [complex(q.cplx(x)) for x in m]
+            got[0] = 99  # a caller may scribble on its copy
+            assert q._mtrx(m)[0] == complex(q.cplx(m[0]))
+            r = q._mtrx(m)
+            assert q.IsPhase(r) == (q._norm(r[1]) <= q.FP_NORM_EPSILON and q._norm(r[2]) <= q.FP_NORM_EPSILON)
+            assert q.IsInvert(r) == (q._norm(r[0]) <= q.FP_NORM_EPSILON and q._norm(r[3]) <= q.FP_NORM_EPSILON)
+            for ctl in (False, True):
+                assert q.IsIdentity(r, ctl) == q._is_identity(r, ctl)

@@ -169,14 +169,19 @@ int b200sv_flush(b200sv_t s);  /* launch everything queued; does not wait */
  * hold, with the constant value `rank` here.  Gates passed to b200sv_apply_gates may then use them as controls, and diagonal
  * gates as their own qubit; the predicate is folded when a sweep is encoded (an op that cannot fire on this rank emits nothing),
  * and what b200sv_flush_carry hands back keeps them — so that it stays valid after an exchange has turned them into real qubits
- * of the page (a gate specialised for this rank by the caller would not).  k = 0 switches them off. */
+ * of the page (a gate specialised for this rank by the caller would not).  k = 0 switches them off.
+ * (Reference: QPager keeps the page index outside its engines and specialises every gate per page on the host — meta-controlled
+ * gates select pages, src/qpager.cpp:452-593; there is no counterpart of a gate list that survives a re-page.) */
 int b200sv_set_rank_bits(b200sv_t s, int k, uint64_t rank);
 /* b200sv_flush that leaves the under-filled TAIL of the window un-executed: trailing fused sweeps that would hold fewer than
  * `min_ops` lowered ops are not launched; everything not executed is handed back, in program order, as single-target gates in
  * the layout of b200sv_apply_gates (n_out <= cap of them) for the caller to submit again later — e.g. after a page exchange,
  * relabelled, where they merge into the dense first sweeps of the next window instead of costing nearly empty passes over the
  * state (each sweep streams the whole page whatever it holds).  No op handed back is a non-diagonal gate on a qubit of
- * `must_mask` (the qubits about to leave the page); min_ops = 0 is b200sv_flush. */
+ * `must_mask` (the qubits about to leave the page); min_ops = 0 is b200sv_flush.  On a sharded register every rank must call it
+ * with the same queue and arguments (b200sv_set_rank_bits makes the queues equal): the choice of what is handed back is made on
+ * the symbolic op list and is then the same everywhere.  (Reference: QPager executes gate by gate, swap-compute-swap around each
+ * gate on a paged qubit, src/qpager.cpp:425-432 — there is no window to cut.) */
 int b200sv_flush_carry(b200sv_t s, int min_ops, uint64_t must_mask, int cap, int* n_out, uint64_t* off1, uint64_t* off2,
     uint64_t* pmasks, double* mats8);
 int b200sv_finish(b200sv_t s); /* flush + wait for the device (QInterface::Finish) */
